@@ -1,0 +1,1057 @@
+// dugks_capi.cu — extern "C" boundary (include/dugks.h) and host orchestration of the
+// sm_100a kernels in dugks_kernels.cuh.  No CPU fallback: every entry point needs a
+// CUDA device and fails loudly (DUGKS_ERR_NO_DEVICE) without one.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
+#include <string>
+#include <vector>
+
+#include "../../include/dugks.h"
+#include "dugks_kernels.cuh"
+
+// ------------------------------------------------------------------------------
+// NCCL through dlopen (the library is present in every torch install and on the
+// system; binding at run time keeps libdugks.so loadable on CPU-only boxes for the
+// symbol checks).
+typedef struct { char internal[128]; } nccl_uid_t;
+typedef int (*nccl_get_uid_fn)(nccl_uid_t*);
+typedef int (*nccl_init_rank_fn)(void** comm, int nranks, nccl_uid_t id, int rank);
+typedef int (*nccl_allreduce_fn)(const void* send, void* recv, size_t count, int dtype, int op, void* comm,
+                                 cudaStream_t stream);
+typedef int (*nccl_destroy_fn)(void* comm);
+typedef const char* (*nccl_errstr_fn)(int);
+
+struct Nccl {
+    void* lib = nullptr;
+    nccl_get_uid_fn get_uid = nullptr;
+    nccl_init_rank_fn init_rank = nullptr;
+    nccl_allreduce_fn allreduce = nullptr;
+    nccl_destroy_fn destroy = nullptr;
+    nccl_errstr_fn errstr = nullptr;
+    bool load(std::string& err) {
+        if (lib) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+        for (int i = 0; names[i] && !lib; i++) lib = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) { err = std::string("cannot dlopen libnccl.so.2: ") + dlerror(); return false; }
+        get_uid = (nccl_get_uid_fn)dlsym(lib, "ncclGetUniqueId");
+        init_rank = (nccl_init_rank_fn)dlsym(lib, "ncclCommInitRank");
+        allreduce = (nccl_allreduce_fn)dlsym(lib, "ncclAllReduce");
+        destroy = (nccl_destroy_fn)dlsym(lib, "ncclCommDestroy");
+        errstr = (nccl_errstr_fn)dlsym(lib, "ncclGetErrorString");
+        if (!get_uid || !init_rank || !allreduce || !destroy) { err = "libnccl lacks required symbols"; return false; }
+        return true;
+    }
+};
+static Nccl g_nccl;
+
+static thread_local std::string g_create_error = "no error";
+
+// ------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+struct dugks_handle {
+    std::string err = "no error";
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    // sizes
+    int nc = 0, nif = 0, nbf = 0, nf = 0, D = 3;
+    int n1d = 0, nxi = 0;          // global DV grid
+    int nch = 1, L = 0, Rs = 32, nslab = 0, ntab = 0, tabw = 0;
+    int nrows = 0;                 // padded local rows = nslab*Rs
+    int nvl = 0;                   // local (real) DVs
+    bool hasH = true;
+    int nm = NM_MAX;
+    int rank = 0, nranks = 1;
+    double xiMax = 0;
+    DevGas gas{};
+    std::vector<dugks_patch_t> patches;
+    // local DV bookkeeping: for flat padded index k = s*L*Rs + i*Rs + r -> global id or -1
+    std::vector<int> flat_gid;
+    std::vector<int> local_gids;       // sorted global ids of local DVs
+    std::vector<int> local_flat;       // flat index of local_gids[j]
+    std::vector<int> owner_rank_of_gid;
+    // device
+    std::vector<DevBuf> bufs;
+    uint64_t dev_bytes = 0;
+    StepArgs A{};                      // template argument block (slab, dt patched per launch)
+    double *gam_a_g = nullptr, *gam_a_h = nullptr, *gam_b_g = nullptr, *gam_b_h = nullptr;
+    bool gam_flip = false;
+    double *wall_cin = nullptr, *wall_in = nullptr;
+    int* d_bc = nullptr;
+    double* d_pres = nullptr;
+    int* d_mirror = nullptr;           // [3][nflat]
+    double *snap_g = nullptr, *snap_h = nullptr;
+    double* d_co = nullptr;
+    bool has_sym = false, has_wall = false;
+    size_t nflat = 0;                  // nslab*L*Rs
+    // collective
+    dugks_allreduce_fn reduce = nullptr;
+    void* reduce_user = nullptr;
+    void* nccl_comm = nullptr;
+    // stats
+    uint64_t launches = 0, steps = 0;
+    // kernel timing
+    bool timing = false;
+    struct Ev { cudaEvent_t a, b; int which; };
+    std::vector<Ev> events;
+    std::vector<Ev> pool;
+    size_t smem_out1 = 0, smem_out2 = 0, smem_bnd = 0, smem_upd = 0;
+};
+
+static int fail(dugks_handle* h, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(h, call)                                                                      \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return fail(h, (e__ == cudaErrorMemoryAllocation) ? DUGKS_ERR_NOMEM : DUGKS_ERR_CUDA, \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+template <class T>
+static int dev_alloc(dugks_handle* h, T** out, size_t count, bool zero = true) {
+    size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess)
+        return fail(h, DUGKS_ERR_NOMEM, "cudaMalloc of %zu bytes failed: %s (device memory held so far: %llu bytes)",
+                    bytes, cudaGetErrorString(e), (unsigned long long)h->dev_bytes);
+    if (zero) {
+        e = cudaMemsetAsync(p, 0, bytes, h->stream);
+        if (e != cudaSuccess) return fail(h, DUGKS_ERR_CUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
+    }
+    h->bufs.push_back({p, bytes});
+    h->dev_bytes += bytes;
+    *out = (T*)p;
+    return 0;
+}
+
+template <class T>
+static int dev_upload(dugks_handle* h, T** out, const std::vector<T>& v) {
+    int rc = dev_alloc(h, out, v.size(), false);
+    if (rc) return rc;
+    if (!v.empty()) CUDA_TRY(h, cudaMemcpyAsync(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));   // v may be a temporary
+    return 0;
+}
+
+// ------------------------------------------------------------------------------
+// launch helpers
+static int grid_for(long long items) {
+    long long ctas = (items + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    const long long cap = 148LL * 16 * 8;   // multiple of the SM count; grid-stride loops cover the rest
+    return (int)std::max<long long>(1, std::min(ctas, cap));
+}
+
+struct Timed {
+    dugks_handle* h; int which; dugks_handle::Ev ev{};
+    bool on;
+    Timed(dugks_handle* h_, int which_) : h(h_), which(which_), on(h_->timing) {
+        if (on) {
+            if (!h->pool.empty()) { ev = h->pool.back(); h->pool.pop_back(); }
+            else { cudaEventCreate(&ev.a); cudaEventCreate(&ev.b); }
+            ev.which = which;
+            cudaEventRecord(ev.a, h->stream);
+        }
+    }
+    ~Timed() {
+        if (on) { cudaEventRecord(ev.b, h->stream); h->events.push_back(ev); }
+    }
+};
+
+static int check_launch(dugks_handle* h, const char* name) {
+    h->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(h, DUGKS_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e));
+    return 0;
+}
+
+static int do_allreduce(dugks_handle* h, double* buf, size_t n) {
+    if (h->nranks <= 1) return 0;
+    if (h->reduce) {
+        int rc = h->reduce(h->reduce_user, buf, n, (void*)h->stream);
+        if (rc) return fail(h, DUGKS_ERR_COMM, "user allreduce callback returned %d", rc);
+        return 0;
+    }
+    if (!h->nccl_comm) return fail(h, DUGKS_ERR_COMM, "nRanks > 1 but no reducer and no NCCL communicator");
+    int rc = g_nccl.allreduce(buf, buf, n, /*ncclDouble*/ 8, /*ncclSum*/ 0, h->nccl_comm, h->stream);
+    if (rc) return fail(h, DUGKS_ERR_COMM, "ncclAllReduce failed: %s", g_nccl.errstr ? g_nccl.errstr(rc) : "?");
+    return 0;
+}
+
+template <bool H>
+static int launch_slab_kernels_phase1(dugks_handle* h, StepArgs a) {
+    int rc;
+    long long items = (long long)h->nc * (h->Rs / 32);
+    {
+        Timed t(h, 2);
+        k_cell_halfstep<H><<<grid_for(items), WARPS_PER_CTA * 32, 0, h->stream>>>(a, 0);
+    }
+    if ((rc = check_launch(h, "k_cell_halfstep"))) return rc;
+    {
+        Timed t(h, 0);
+        k_cell_outgoing<1, H><<<grid_for(items), WARPS_PER_CTA * 32, h->smem_out1, h->stream>>>(a);
+    }
+    if ((rc = check_launch(h, "k_cell_outgoing<1>"))) return rc;
+    if (h->nbf > 0) {
+        long long bitems = (long long)h->nbf * (h->Rs / 32);
+        k_bnd_outgoing<H><<<grid_for(bitems), WARPS_PER_CTA * 32, h->smem_bnd, h->stream>>>(a);
+        if ((rc = check_launch(h, "k_bnd_outgoing"))) return rc;
+    }
+    return 0;
+}
+
+template <bool H>
+static int launch_slab_kernels_phase2(dugks_handle* h, StepArgs a) {
+    int rc;
+    long long items = (long long)h->nc * (h->Rs / 32);
+    if (h->nbf > 0) {
+        long long bitems = (long long)h->nbf * (h->Rs / 32);
+        k_bnd_relax<H><<<grid_for(bitems), WARPS_PER_CTA * 32, 0, h->stream>>>(a);
+        if ((rc = check_launch(h, "k_bnd_relax"))) return rc;
+    }
+    {
+        Timed t(h, 0);
+        k_cell_outgoing<2, H><<<grid_for(items), WARPS_PER_CTA * 32, h->smem_out2, h->stream>>>(a);
+    }
+    if ((rc = check_launch(h, "k_cell_outgoing<2>"))) return rc;
+    {
+        Timed t(h, 1);
+        k_cell_update<H><<<grid_for(items), WARPS_PER_CTA * 32, h->smem_upd, h->stream>>>(a);
+    }
+    if ((rc = check_launch(h, "k_cell_update"))) return rc;
+    return 0;
+}
+
+template <bool H>
+static int symmetry_stage(dugks_handle* h, StepArgs a) {
+    // snapshot = the reference's dfContainer (fvDVM.C:423-449)
+    size_t n = (size_t)h->nbf * h->nflat;
+    CUDA_TRY(h, cudaMemcpyAsync(h->snap_g, a.gsb, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    if (H) CUDA_TRY(h, cudaMemcpyAsync(h->snap_h, a.hsb, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    for (const auto& p : h->patches) {
+        if ((p.kind != DUGKS_PATCH_DVM_SYMMETRY && p.kind != DUGKS_PATCH_SYMMETRY_PLANE) || p.size <= 0) continue;
+        // mirror axis from the first face normal (discreteVelocity.C:777-779)
+        double s0[3];
+        CUDA_TRY(h, cudaMemcpyAsync(s0, a.m.b_Sf + (size_t)p.start * 3, sizeof s0, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        double mag = std::sqrt(s0[0] * s0[0] + s0[1] * s0[1] + s0[2] * s0[2]);
+        int axis = 0;
+        double best = -1;
+        for (int d = 0; d < 3; d++)
+            if (std::fabs(s0[d] / mag) > best) { best = std::fabs(s0[d] / mag); axis = d; }
+        if (best < 1.0 - 1e-9)
+            return fail(h, DUGKS_ERR_UNSUPPORTED, "symmetry patch normal is not axis aligned (the reference's mirror-id rule, discreteVelocity.C:777-779, needs it)");
+        long long total = (long long)p.size * (long long)h->nflat;
+        int grid = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
+        k_bnd_symmetry<H><<<grid, 256, 0, h->stream>>>(a, h->snap_g, h->snap_h, h->d_mirror, (int)h->nflat, p.start,
+                                                         p.size, axis, s0[0], s0[1], s0[2]);
+        int rc;
+        if ((rc = check_launch(h, "k_bnd_symmetry"))) return rc;
+    }
+    return 0;
+}
+
+template <bool H>
+static int compute_wall_constants(dugks_handle* h) {
+    if (!h->has_wall) return 0;
+    StepArgs a = h->A;
+    CUDA_TRY(h, cudaMemsetAsync(h->wall_cin, 0, (size_t)h->nbf * h->nm * sizeof(double), h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->wall_in, 0, (size_t)h->nbf * sizeof(double), h->stream));
+    long long bitems = (long long)h->nbf * (h->Rs / 32);
+    for (int s = 0; s < h->nslab; s++) {
+        a.slab = s;
+        k_wall_constants<H><<<grid_for(bitems), WARPS_PER_CTA * 32, 0, h->stream>>>(a, h->wall_cin, h->wall_in);
+        int rc;
+        if ((rc = check_launch(h, "k_wall_constants"))) return rc;
+    }
+    int rc;
+    if ((rc = do_allreduce(h, h->wall_cin, (size_t)h->nbf * h->nm))) return rc;   // fvDVM.C:304-305
+    if ((rc = do_allreduce(h, h->wall_in, (size_t)h->nbf))) return rc;
+    return 0;
+}
+
+template <bool H>
+static int step_impl(dugks_handle* h, double dt) {
+    int rc;
+    StepArgs a = h->A;
+    a.dt = dt;
+    // lagged boundary gradient: last step's new values become this step's old ones
+    h->gam_flip = !h->gam_flip;
+    a.gam_old_g = h->gam_flip ? h->gam_b_g : h->gam_a_g;
+    a.gam_old_h = h->gam_flip ? h->gam_b_h : h->gam_a_h;
+    a.gam_new_g = h->gam_flip ? h->gam_a_g : h->gam_b_g;
+    a.gam_new_h = h->gam_flip ? h->gam_a_h : h->gam_b_h;
+    size_t nslots = (size_t)2 * h->nif + h->nbf;
+    CUDA_TRY(h, cudaMemsetAsync(a.fslot, 0, nslots * h->nm * sizeof(double), h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(a.cslot, 0, (size_t)h->nc * h->nm * sizeof(double), h->stream));
+    for (int s = 0; s < h->nslab; s++) {
+        a.slab = s;
+        if ((rc = launch_slab_kernels_phase1<H>(h, a))) return rc;
+    }
+    if (h->has_sym) {
+        if ((rc = symmetry_stage<H>(h, a))) return rc;
+    }
+    if (h->nbf > 0) {
+        long long bitems = (long long)h->nbf * (h->Rs / 32);
+        for (int s = 0; s < h->nslab; s++) {
+            a.slab = s;
+            k_bnd_moments<H><<<grid_for(bitems), WARPS_PER_CTA * 32, 0, h->stream>>>(a);
+            if ((rc = check_launch(h, "k_bnd_moments"))) return rc;
+        }
+    }
+    if ((rc = do_allreduce(h, a.fslot, nslots * h->nm))) return rc;          // fvDVM.C:363,487-489,519
+    k_face_macros<<<(h->nf + 127) / 128, 128, 0, h->stream>>>(a);
+    if ((rc = check_launch(h, "k_face_macros"))) return rc;
+    for (int s = 0; s < h->nslab; s++) {
+        a.slab = s;
+        if ((rc = launch_slab_kernels_phase2<H>(h, a))) return rc;
+    }
+    if ((rc = do_allreduce(h, a.cslot, (size_t)h->nc * h->nm))) return rc;  // fvDVM.C:626-628,725
+    k_cell_macros<<<(h->nc + 127) / 128, 128, 0, h->stream>>>(a);
+    if ((rc = check_launch(h, "k_cell_macros"))) return rc;
+    if (h->nbf > 0) {
+        k_bnd_macros<<<(h->nbf + 127) / 128, 128, 0, h->stream>>>(a, h->d_bc, h->d_pres);
+        if ((rc = check_launch(h, "k_bnd_macros"))) return rc;
+    }
+    h->steps++;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------
+// velocity-space layout
+struct RowDesc {
+    int iy, iz, chunk;
+    double y, z, w;
+};
+
+static int choose_chunks(int n, int D, long long base_rows_local) {
+    // pick the number of ix-chunks minimising padding waste, L <= MAX_L, prefer long rows
+    int best = -1;
+    double best_waste = 1e9;
+    for (int nch = 1; nch <= n; nch++) {
+        int L = (n + nch - 1) / nch;
+        if (L > MAX_L) continue;
+        if (L < 4 && nch > 1) break;
+        if ((long long)nch * L > NT_MAX) continue;
+        if (nch > 1 && base_rows_local < 32) continue;   // a warp must not span more than two chunks
+        long long rows = base_rows_local * nch;
+        long long padded = (rows + 31) / 32 * 32;
+        double waste = 1.0 - (double)(base_rows_local * n) / (double)(padded * L);
+        if (waste < best_waste - 0.02) { best_waste = waste; best = nch; }
+    }
+    return best;
+}
+
+// first base row (iy,iz) owned by rank r: contiguous, balanced blocks
+static int row_begin_of(int nbase, int nranks, int r) {
+    long long q = nbase / nranks, m = nbase % nranks;
+    return (int)(r * q + std::min<long long>(r, m));
+}
+
+extern "C" int dugks_abi_version(void) { return DUGKS_ABI_VERSION; }
+
+extern "C" int dugks_partition(int32_t nXiPerDim, int32_t nSolutionD, int32_t nRanks, int32_t rank, int32_t* ids,
+                               int32_t* n) {
+    if (nXiPerDim < 1 || nSolutionD < 1 || nSolutionD > 3 || nRanks < 1 || rank < 0 || rank >= nRanks || !n)
+        return fail(nullptr, DUGKS_ERR_INVALID, "dugks_partition: bad argument");
+    const int nn = nXiPerDim, ny = (nSolutionD >= 2) ? nn : 1, nz = (nSolutionD == 3) ? nn : 1;
+    const int nbase = ny * nz;
+    if (nbase < nRanks) return fail(nullptr, DUGKS_ERR_UNSUPPORTED, "%d velocity rows cannot be split over %d ranks", nbase, nRanks);
+    int b0 = row_begin_of(nbase, nRanks, rank), b1 = row_begin_of(nbase, nRanks, rank + 1);
+    *n = (b1 - b0) * nn;
+    if (ids)
+        for (int k = 0; k < *n; k++) ids[k] = b0 * nn + k;
+    return 0;
+}
+
+extern "C" const char* dugks_last_error(const dugks_handle_t* h) {
+    return h ? h->err.c_str() : g_create_error.c_str();
+}
+
+extern "C" int dugks_nccl_unique_id(void* out128) {
+    if (!out128) return fail(nullptr, DUGKS_ERR_INVALID, "dugks_nccl_unique_id: NULL output");
+    std::string err;
+    if (!g_nccl.load(err)) return fail(nullptr, DUGKS_ERR_COMM, "%s", err.c_str());
+    nccl_uid_t id;
+    int rc = g_nccl.get_uid(&id);
+    if (rc) return fail(nullptr, DUGKS_ERR_COMM, "ncclGetUniqueId failed (%d)", rc);
+    memcpy(out128, &id, sizeof id);
+    return 0;
+}
+
+extern "C" void dugks_destroy(dugks_handle_t* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->nccl_comm && g_nccl.destroy) g_nccl.destroy(h->nccl_comm);
+    for (auto& b : h->bufs) cudaFree(b.p);
+    for (auto& e : h->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    for (auto& e : h->pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+template <bool H>
+static int init_state(dugks_handle* h) {
+    StepArgs a = h->A;
+    a.dt = 0.0;
+    int rc;
+    k_init_tau<<<(h->nc + 127) / 128, 128, 0, h->stream>>>(a);                  // fvDVM.C:1073
+    if ((rc = check_launch(h, "k_init_tau"))) return rc;
+    if (h->nbf > 0) {
+        k_bnd_macros<<<(h->nbf + 127) / 128, 128, 0, h->stream>>>(a, h->d_bc, h->d_pres);   // fvDVM.C:1072
+        if ((rc = check_launch(h, "k_bnd_macros"))) return rc;
+    }
+    long long items = (long long)h->nc * (h->Rs / 32);
+    for (int s = 0; s < h->nslab; s++) {
+        a.slab = s;
+        k_cell_halfstep<H><<<grid_for(items), WARPS_PER_CTA * 32, 0, h->stream>>>(a, 1);   // initDFtoEq
+        if ((rc = check_launch(h, "k_cell_halfstep(init)"))) return rc;
+        if (h->nbf > 0) {
+            long long total = (long long)h->nbf * h->L * h->Rs;
+            int grid = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
+            k_bnd_init_mixed<H><<<grid, 256, 0, h->stream>>>(a);                            // initBoundaryField
+            if ((rc = check_launch(h, "k_bnd_init_mixed"))) return rc;
+        }
+    }
+    return compute_wall_constants<H>(h);                                                   // fvDVM.C:1069
+}
+
+extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patches, int32_t nPatches,
+                            const dugks_dvset_t* dvset, const dugks_gas_t* gas, const dugks_par_t* par,
+                            const double* rho, const double* U, const double* T, const double* rho_b,
+                            const double* U_b, const double* T_b, dugks_handle_t** out) {
+    if (!out) return fail(nullptr, DUGKS_ERR_INVALID, "dugks_create: out is NULL");
+    *out = nullptr;
+    if (!mesh || !dvset || !gas || !rho || !U || !T)
+        return fail(nullptr, DUGKS_ERR_INVALID, "dugks_create: NULL argument");
+    if (mesh->nCells <= 0 || mesh->nInternalFaces < 0 || mesh->nBoundaryFaces < 0)
+        return fail(nullptr, DUGKS_ERR_INVALID, "dugks_create: bad mesh sizes");
+    if (mesh->nSolutionD < 1 || mesh->nSolutionD > 3)
+        return fail(nullptr, DUGKS_ERR_INVALID, "dugks_create: nSolutionD must be 1, 2 or 3");
+    if (dvset->nXiPerDim < 1 || !dvset->Xis || !dvset->weights)
+        return fail(nullptr, DUGKS_ERR_INVALID, "dugks_create: bad discrete-velocity set");
+    if (mesh->nBoundaryFaces > 0 && (!rho_b || !U_b || !T_b || !patches))
+        return fail(nullptr, DUGKS_ERR_INVALID, "dugks_create: boundary fields missing");
+    dugks_par_t pdef{};
+    pdef.nRanks = 1; pdef.device = -1;
+    if (!par) par = &pdef;
+    int nranks = par->nRanks < 1 ? 1 : par->nRanks;
+    if (par->rank < 0 || par->rank >= nranks) return fail(nullptr, DUGKS_ERR_INVALID, "dugks_create: bad rank");
+
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(nullptr, DUGKS_ERR_NO_DEVICE,
+                    "no CUDA device available (%s); dugksfoam_b200 has no CPU fallback",
+                    ce != cudaSuccess ? cudaGetErrorString(ce) : "device count is 0");
+    dugks_handle* h = new dugks_handle();
+    auto bail = [&](int rc) { g_create_error = h->err; dugks_destroy(h); return rc; };
+    int dev = par->device;
+    if (dev < 0) cudaGetDevice(&dev);
+    if (dev >= ndev) { fail(h, DUGKS_ERR_INVALID, "device %d out of range (%d devices)", dev, ndev); return bail(DUGKS_ERR_INVALID); }
+    h->device = dev;
+    int rc;
+#define TRYB(x) do { rc = (x); if (rc) return bail(rc); } while (0)
+#define CUDAB(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { fail(h, DUGKS_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e__)); return bail(DUGKS_ERR_CUDA); } } while (0)
+    CUDAB(cudaSetDevice(dev));
+    CUDAB(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+
+    const int nc = mesh->nCells, nif = mesh->nInternalFaces, nbf = mesh->nBoundaryFaces, nf = nif + nbf;
+    const int D = mesh->nSolutionD, n = dvset->nXiPerDim;
+    h->nc = nc; h->nif = nif; h->nbf = nbf; h->nf = nf; h->D = D; h->n1d = n;
+    h->rank = par->rank; h->nranks = nranks; h->xiMax = dvset->xiMax;
+    h->gas = DevGas{gas->R, gas->omega, gas->Tref, gas->muRef, gas->Pr, gas->KInner, D};
+    h->patches.assign(patches, patches + nPatches);
+    h->reduce = par->reduce; h->reduce_user = par->reduce_user;
+    // h == 0 identically when K+3-D == 0 (discreteVelocity.C:1043,1059): elide it unless asked not to
+    h->hasH = !((gas->KInner + 3 - D) == 0 && par->store_h == 0);
+    h->nm = h->hasH ? NM_MAX : NM_G;
+
+    // ---- patches: validate, per-face kind / bc tables
+    std::vector<int> b_kind(nbf, -1), b_bc(nbf, 0);
+    std::vector<double> b_pres(nbf, 0.0);
+    for (int p = 0; p < nPatches; p++) {
+        const dugks_patch_t& P = patches[p];
+        if (P.start < 0 || P.size < 0 || P.start + P.size > nbf) { fail(h, DUGKS_ERR_INVALID, "patch %d out of range", p); return bail(DUGKS_ERR_INVALID); }
+        if (P.kind < 0 || P.kind > DUGKS_PATCH_PRESSURE_OUT) { fail(h, DUGKS_ERR_INVALID, "patch %d: unknown kind %d", p, P.kind); return bail(DUGKS_ERR_INVALID); }
+        for (int j = 0; j < P.size; j++) {
+            b_kind[P.start + j] = P.kind;
+            b_bc[P.start + j] = (P.U_bc == DUGKS_BC_ZERO_GRADIENT ? 1 : 0) | (P.T_bc == DUGKS_BC_ZERO_GRADIENT ? 2 : 0);
+            b_pres[P.start + j] = P.pressure;
+        }
+        if (P.size > 0 && (P.kind == DUGKS_PATCH_DVM_SYMMETRY || P.kind == DUGKS_PATCH_SYMMETRY_PLANE)) h->has_sym = true;
+        if (P.size > 0 && P.kind == DUGKS_PATCH_MAXWELL_WALL) h->has_wall = true;
+    }
+    for (int b = 0; b < nbf; b++)
+        if (b_kind[b] < 0) { fail(h, DUGKS_ERR_INVALID, "boundary face %d belongs to no patch", b); return bail(DUGKS_ERR_INVALID); }
+
+    // ---- discrete-velocity layout (global grid as fvDVM.C:140-220)
+    const int ny = (D >= 2) ? n : 1, nz = (D == 3) ? n : 1;
+    h->nxi = n * ny * nz;
+    const int nbase = ny * nz;                      // base rows (iy, iz)
+    // contiguous blocks of base rows per rank (any assignment is valid: sums commute;
+    // the reference's round-robin is fvDVM.C:228-260)
+    if (nbase < nranks) { fail(h, DUGKS_ERR_UNSUPPORTED, "%d velocity rows cannot be split over %d ranks", nbase, nranks); return bail(DUGKS_ERR_UNSUPPORTED); }
+    auto row_begin = [&](int r) { return row_begin_of(nbase, nranks, r); };
+    const int rb0 = row_begin(h->rank), rb1 = row_begin(h->rank + 1);
+    int max_nbl = 0;
+    for (int r = 0; r < nranks; r++) max_nbl = std::max(max_nbl, row_begin(r + 1) - row_begin(r));
+    h->owner_rank_of_gid.resize(h->nxi);
+    for (int r = 0; r < nranks; r++)
+        for (int br = row_begin(r); br < row_begin(r + 1); br++)
+            for (int ix = 0; ix < n; ix++) h->owner_rank_of_gid[br * n + ix] = r;
+    int nch = choose_chunks(n, D, max_nbl);
+    if (nch < 1) { fail(h, DUGKS_ERR_UNSUPPORTED, "nDV = %d cannot be laid out (needs ix-chunks of <= %d points, <= %d table entries)", n, MAX_L, NT_MAX); return bail(DUGKS_ERR_UNSUPPORTED); }
+    const int L = (n + nch - 1) / nch;
+    h->nch = nch; h->L = L; h->ntab = nch * L;
+    h->Rs = 32;
+    // par->dv_chunk is reserved: a slab is one warp of rows (32 rows x L points) because every
+    // moment slot is owned by exactly one warp per launch (atomic-free, deterministic)
+    std::vector<RowDesc> rows;
+    for (int ch = 0; ch < nch; ch++)
+        for (int br = rb0; br < rb1; br++) {
+            int iy = (D >= 2) ? br % n : 0, iz = (D == 3) ? br / n : 0;
+            RowDesc rd;
+            rd.iy = iy; rd.iz = iz; rd.chunk = ch;
+            rd.y = (D >= 2) ? dvset->Xis[iy] : 0.0;
+            rd.z = (D == 3) ? dvset->Xis[iz] : 0.0;
+            // weight = w[iz]*w[iy]*w[ix] (fvDVM.C:158,187,211): the row carries w[iz]*w[iy]
+            rd.w = (D == 3) ? dvset->weights[iz] * dvset->weights[iy] : ((D == 2) ? dvset->weights[iy] : 1.0);
+            rows.push_back(rd);
+        }
+    // keep warps sign-coherent in (xi_y, xi_z): less divergence in the upwind test
+    std::stable_sort(rows.begin(), rows.end(), [](const RowDesc& a, const RowDesc& b) {
+        if (a.chunk != b.chunk) return a.chunk < b.chunk;
+        int sa = (a.z < 0 ? 0 : 2) + (a.y < 0 ? 0 : 1), sb = (b.z < 0 ? 0 : 2) + (b.y < 0 ? 0 : 1);
+        return sa < sb;
+    });
+    const int nreal = (int)rows.size();
+    h->nrows = (nreal + h->Rs - 1) / h->Rs * h->Rs;
+    h->nslab = h->nrows / h->Rs;
+    h->nflat = (size_t)h->nslab * L * h->Rs;
+    std::vector<double> row_y(h->nrows), row_z(h->nrows), row_w(h->nrows, 0.0);
+    std::vector<int> row_cb(h->nrows);
+    for (int k = 0; k < h->nrows; k++) {
+        const RowDesc& rd = rows[std::min(k, nreal - 1)];   // padding rows duplicate the last row with weight 0
+        row_y[k] = rd.y; row_z[k] = rd.z; row_cb[k] = rd.chunk * L;
+        if (k < nreal) row_w[k] = rd.w;
+    }
+    // tables along x: entries beyond n duplicate the last abscissa with weight 0
+    std::vector<double> tx((size_t)5 * h->ntab);
+    for (int t = 0; t < h->ntab; t++) {
+        double x = dvset->Xis[std::min(t, n - 1)], w = (t < n) ? dvset->weights[t] : 0.0;
+        tx[t] = x; tx[h->ntab + t] = w; tx[2 * h->ntab + t] = w * x; tx[3 * h->ntab + t] = w * x * x;
+        tx[4 * h->ntab + t] = w * x * x * x;
+    }
+    // largest table span of any warp
+    h->tabw = L;
+    for (int k0 = 0; k0 < h->nrows; k0 += 32) {
+        int mn = 1 << 30, mx = -1;
+        for (int k = k0; k < k0 + 32; k++) { mn = std::min(mn, row_cb[k]); mx = std::max(mx, row_cb[k]); }
+        h->tabw = std::max(h->tabw, mx + L - mn);
+    }
+    // flat index <-> global id, mirror partners
+    h->flat_gid.assign(h->nflat, -1);
+    std::vector<int> gid_flat(h->nxi, -1);
+    for (int k = 0; k < nreal; k++) {
+        int s = k / h->Rs, r = k % h->Rs;
+        const RowDesc& rd = rows[k];
+        for (int i = 0; i < L; i++) {
+            int ix = rd.chunk * L + i;
+            if (ix >= n) continue;
+            int gid = (rd.iz * ny + rd.iy) * n + ix;
+            size_t flat = ((size_t)s * L + i) * h->Rs + r;
+            h->flat_gid[flat] = gid;
+            gid_flat[gid] = (int)flat;
+        }
+    }
+    for (int g = 0; g < h->nxi; g++)
+        if (gid_flat[g] >= 0) { h->local_gids.push_back(g); h->local_flat.push_back(gid_flat[g]); }
+    h->nvl = (int)h->local_gids.size();
+    std::vector<int> mirror((size_t)3 * h->nflat, -1);
+    bool mirror_local = true;
+    for (size_t flat = 0; flat < h->nflat; flat++) {
+        int g = h->flat_gid[flat];
+        if (g < 0) continue;
+        int ix = g % n, iy = (g / n) % ny, iz = g / (n * ny);
+        int mg[3] = {(iz * ny + iy) * n + (n - 1 - ix),                       // fvDVM.C:162
+                     (D >= 2) ? (iz * ny + (ny - 1 - iy)) * n + ix : 0,        // :163
+                     (D == 3) ? ((nz - 1 - iz) * ny + iy) * n + ix : 0};       // :164
+        for (int d = 0; d < 3; d++) {
+            mirror[(size_t)d * h->nflat + flat] = gid_flat[mg[d]];
+            if (d < D && gid_flat[mg[d]] < 0) mirror_local = false;
+        }
+    }
+    if (h->has_sym && !mirror_local) {
+        fail(h, DUGKS_ERR_UNSUPPORTED, "symmetry patches with a velocity partition that separates mirror partners are not supported yet (use nRanks = 1)");
+        return bail(DUGKS_ERR_UNSUPPORTED);
+    }
+
+    // ---- cell -> face CSR (internal faces first), geometry per entry
+    std::vector<int> cnt(nc, 0), cnt_int(nc, 0);
+    for (int f = 0; f < nif; f++) { cnt[mesh->owner[f]]++; cnt[mesh->neighbour[f]]++; cnt_int[mesh->owner[f]]++; cnt_int[mesh->neighbour[f]]++; }
+    for (int b = 0; b < nbf; b++) cnt[mesh->owner[nif + b]]++;
+    std::vector<int> off(nc + 1, 0);
+    for (int c = 0; c < nc; c++) {
+        if (cnt[c] > MAX_CELL_FACES) { fail(h, DUGKS_ERR_UNSUPPORTED, "cell %d has %d faces (limit %d)", c, cnt[c], MAX_CELL_FACES); return bail(DUGKS_ERR_UNSUPPORTED); }
+        off[c + 1] = off[c] + cnt[c];
+    }
+    const int ne = off[nc];
+    std::vector<int> e_other(ne), e_face(ne), e_owner(ne), fill_i(nc, 0), fill_b(nc, 0);
+    std::vector<double> e_geo((size_t)ne * 9);
+    auto put = [&](int c, int pos, int other, int face, int isown, const double* G) {
+        int e = off[c] + pos;
+        e_other[e] = other; e_face[e] = face; e_owner[e] = isown;
+        for (int d = 0; d < 3; d++) {
+            e_geo[(size_t)e * 9 + d] = G[d];
+            e_geo[(size_t)e * 9 + 3 + d] = mesh->Cf[(size_t)face * 3 + d] - mesh->C[(size_t)c * 3 + d];
+            e_geo[(size_t)e * 9 + 6 + d] = mesh->Sf[(size_t)face * 3 + d];
+        }
+    };
+    for (int f = 0; f < nif; f++) {
+        int o = mesh->owner[f], nb = mesh->neighbour[f];
+        if (o < 0 || o >= nc || nb < 0 || nb >= nc) { fail(h, DUGKS_ERR_INVALID, "face %d: owner/neighbour out of range", f); return bail(DUGKS_ERR_INVALID); }
+        put(o, fill_i[o]++, nb, f, 1, mesh->ownLs + (size_t)f * 3);
+        // grad[nei] -= neiLs*(v_nei - v_own) == neiLs*(v_own - v_nei): the sign is inside neiLs
+        // (zeroBoundaryGrad.C:98, zeroBoundaryVectors.C:183-184)
+        put(nb, fill_i[nb]++, o, f, 0, mesh->neiLs + (size_t)f * 3);
+    }
+    std::vector<int> b_owner(nbf);
+    std::vector<double> b_n((size_t)nbf * 3), b_invdc(nbf), b_Sf((size_t)nbf * 3), b_r((size_t)nbf * 3);
+    for (int b = 0; b < nbf; b++) {
+        int f = nif + b, o = mesh->owner[f];
+        if (o < 0 || o >= nc) { fail(h, DUGKS_ERR_INVALID, "boundary face %d: owner out of range", b); return bail(DUGKS_ERR_INVALID); }
+        put(o, cnt_int[o] + fill_b[o]++, -1 - b, f, 1, mesh->patchLs + (size_t)b * 3);
+        b_owner[b] = o;
+        const double* S = mesh->Sf + (size_t)f * 3;
+        double mag = std::sqrt(S[0] * S[0] + S[1] * S[1] + S[2] * S[2]);
+        for (int d = 0; d < 3; d++) {
+            b_n[(size_t)b * 3 + d] = S[d] / mag;                                 // discreteVelocity.C:438-442
+            b_Sf[(size_t)b * 3 + d] = S[d];
+            b_r[(size_t)b * 3 + d] = mesh->Cf[(size_t)f * 3 + d] - mesh->C[(size_t)o * 3 + d];
+        }
+        b_invdc[b] = 1.0 / mesh->deltaCoeffs[f];
+    }
+
+    // ---- upload static data
+    StepArgs& A = h->A;
+    memset(&A, 0, sizeof A);
+    A.gas = h->gas; A.nm = h->nm;
+    DevMesh& M = A.m;
+    M.nc = nc; M.nif = nif; M.nbf = nbf; M.nf = nf;
+    int *d_i; double* d_d;
+    TRYB(dev_upload(h, &d_i, off)); M.cell_off = d_i;
+    TRYB(dev_upload(h, &d_i, cnt_int)); M.cell_nint = d_i;
+    TRYB(dev_upload(h, &d_i, e_other)); M.e_other = d_i;
+    TRYB(dev_upload(h, &d_i, e_face)); M.e_face = d_i;
+    TRYB(dev_upload(h, &d_i, e_owner)); M.e_owner = d_i;
+    TRYB(dev_upload(h, &d_d, e_geo)); M.e_geo = d_d;
+    TRYB(dev_upload(h, &d_d, std::vector<double>(mesh->V, mesh->V + nc))); M.V = d_d;
+    TRYB(dev_upload(h, &d_i, b_owner)); M.b_owner = d_i;
+    TRYB(dev_upload(h, &d_i, b_kind)); M.b_kind = d_i;
+    TRYB(dev_upload(h, &d_d, b_n)); M.b_n = d_d;
+    TRYB(dev_upload(h, &d_d, b_invdc)); M.b_invdc = d_d;
+    TRYB(dev_upload(h, &d_d, b_Sf)); M.b_Sf = d_d;
+    TRYB(dev_upload(h, &d_d, b_r)); M.b_r = d_d;
+    TRYB(dev_upload(h, &d_d, std::vector<double>(mesh->deltaCoeffs, mesh->deltaCoeffs + nif))); M.dcoef_int = d_d;
+    DevDV& V = A.dv;
+    V.L = L; V.Rs = h->Rs; V.nslab = h->nslab; V.ntab = h->ntab; V.hasH = h->hasH; V.tabw = h->tabw;
+    TRYB(dev_upload(h, &d_d, tx)); V.tx = d_d;
+    TRYB(dev_upload(h, &d_d, row_y)); V.row_y = d_d;
+    TRYB(dev_upload(h, &d_d, row_z)); V.row_z = d_d;
+    TRYB(dev_upload(h, &d_d, row_w)); V.row_w = d_d;
+    TRYB(dev_upload(h, &d_i, row_cb)); V.row_cbase = d_i;
+    TRYB(dev_upload(h, &h->d_bc, b_bc));
+    TRYB(dev_upload(h, &h->d_pres, b_pres));
+    TRYB(dev_upload(h, &h->d_mirror, mirror));
+
+    // ---- macros
+    std::vector<double> cmac((size_t)nc * MAC_N, 0.0), bmac((size_t)nbf * 5, 0.0), fmac((size_t)nf * MAC_N, 0.0);
+    for (int c = 0; c < nc; c++) {
+        cmac[(size_t)c * MAC_N] = rho[c];
+        for (int d = 0; d < 3; d++) cmac[(size_t)c * MAC_N + 1 + d] = U[(size_t)c * 3 + d];
+        cmac[(size_t)c * MAC_N + 4] = T[c];
+    }
+    for (int b = 0; b < nbf; b++) {
+        bmac[(size_t)b * 5] = rho_b[b];
+        for (int d = 0; d < 3; d++) bmac[(size_t)b * 5 + 1 + d] = U_b[(size_t)b * 3 + d];
+        bmac[(size_t)b * 5 + 4] = T_b[b];
+    }
+    // Usurf = fvc::interpolate(Uvol, "linear") for the first Courant number (fvDVM.C:1074) [OF-lib]
+    for (int f = 0; f < nif; f++) {
+        int o = mesh->owner[f], nb = mesh->neighbour[f];
+        const double *S = mesh->Sf + (size_t)f * 3, *Cf = mesh->Cf + (size_t)f * 3;
+        double sn = 0, sp = 0;
+        for (int d = 0; d < 3; d++) {
+            sn += S[d] * (mesh->C[(size_t)nb * 3 + d] - Cf[d]);
+            sp += S[d] * (Cf[d] - mesh->C[(size_t)o * 3 + d]);
+        }
+        sn = std::fabs(sn); sp = std::fabs(sp);
+        double w = sn / (sp + sn);
+        for (int d = 0; d < 3; d++) fmac[(size_t)f * MAC_N + 1 + d] = w * U[(size_t)o * 3 + d] + (1 - w) * U[(size_t)nb * 3 + d];
+    }
+    for (int b = 0; b < nbf; b++)
+        for (int d = 0; d < 3; d++) fmac[(size_t)(nif + b) * MAC_N + 1 + d] = U_b[(size_t)b * 3 + d];
+    TRYB(dev_upload(h, &A.cmac, cmac));
+    TRYB(dev_upload(h, &A.bmac, bmac));
+    TRYB(dev_upload(h, &A.fmac, fmac));
+
+    // ---- state
+    size_t free_b = 0, total_b = 0;
+    CUDAB(cudaMemGetInfo(&free_b, &total_b));
+    const size_t ncell_dv = (size_t)nc * h->nflat, nb_dv = (size_t)nbf * h->nflat;
+    const int nfld = h->hasH ? 2 : 1;
+    size_t need = (2 * ncell_dv + 3 * nb_dv + (h->has_sym ? nb_dv : 0) + (size_t)nif * L * h->Rs) * nfld * sizeof(double) +
+                  ((size_t)(2 * nif + nbf) + nc) * h->nm * sizeof(double);
+    if (need > free_b) {
+        fail(h, DUGKS_ERR_NOMEM, "state needs %.2f GB of device memory, only %.2f GB free (nCells=%d, local DVs=%d, h %s)",
+             need / 1e9, free_b / 1e9, nc, h->nvl, h->hasH ? "stored" : "elided");
+        return bail(DUGKS_ERR_NOMEM);
+    }
+    TRYB(dev_alloc(h, &A.gt, ncell_dv));
+    TRYB(dev_alloc(h, &A.gb, ncell_dv));
+    TRYB(dev_alloc(h, &A.gsb, nb_dv));
+    TRYB(dev_alloc(h, &h->gam_a_g, nb_dv));
+    TRYB(dev_alloc(h, &h->gam_b_g, nb_dv));
+    TRYB(dev_alloc(h, &A.fbuf_g, (size_t)nif * L * h->Rs));
+    if (h->hasH) {
+        TRYB(dev_alloc(h, &A.ht, ncell_dv));
+        TRYB(dev_alloc(h, &A.hb, ncell_dv));
+        TRYB(dev_alloc(h, &A.hsb, nb_dv));
+        TRYB(dev_alloc(h, &h->gam_a_h, nb_dv));
+        TRYB(dev_alloc(h, &h->gam_b_h, nb_dv));
+        TRYB(dev_alloc(h, &A.fbuf_h, (size_t)nif * L * h->Rs));
+    }
+    if (h->has_sym) {
+        TRYB(dev_alloc(h, &h->snap_g, nb_dv));
+        if (h->hasH) TRYB(dev_alloc(h, &h->snap_h, nb_dv));
+    }
+    TRYB(dev_alloc(h, &A.fslot, ((size_t)2 * nif + nbf) * h->nm));
+    TRYB(dev_alloc(h, &A.cslot, (size_t)nc * h->nm));
+    TRYB(dev_alloc(h, &h->wall_cin, (size_t)nbf * h->nm));
+    TRYB(dev_alloc(h, &h->wall_in, (size_t)nbf));
+    TRYB(dev_alloc(h, &A.wall_diag, (size_t)nbf * 12));
+    TRYB(dev_alloc(h, &h->d_co, 2));
+    A.wall_cin = h->wall_cin; A.wall_in = h->wall_in;
+    A.gam_old_g = h->gam_a_g; A.gam_old_h = h->gam_a_h; A.gam_new_g = h->gam_b_g; A.gam_new_h = h->gam_b_h;
+
+    // ---- dynamic shared memory sizes
+    h->smem_out1 = (size_t)5 * NT_MAX * 8 + (size_t)WARPS_PER_CTA * STAGE_BYTES;
+    h->smem_out2 = h->smem_out1 + (size_t)WARPS_PER_CTA * ACC_FACES * 3 * h->tabw * 8;
+    h->smem_bnd = (size_t)NT_MAX * 8 + (size_t)WARPS_PER_CTA * STAGE_BYTES;
+    h->smem_upd = h->smem_out1;
+    if (h->hasH) {
+        CUDAB(cudaFuncSetAttribute(k_cell_outgoing<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_out2));
+    } else {
+        CUDAB(cudaFuncSetAttribute(k_cell_outgoing<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_out2));
+    }
+
+    // ---- collective backend
+    if (nranks > 1 && !h->reduce) {
+        if (!par->nccl_unique_id) { fail(h, DUGKS_ERR_COMM, "nRanks = %d needs either a reduce callback or an NCCL unique id", nranks); return bail(DUGKS_ERR_COMM); }
+        std::string err;
+        if (!g_nccl.load(err)) { fail(h, DUGKS_ERR_COMM, "%s", err.c_str()); return bail(DUGKS_ERR_COMM); }
+        nccl_uid_t id;
+        memcpy(&id, par->nccl_unique_id, sizeof id);
+        int nrc = g_nccl.init_rank(&h->nccl_comm, nranks, id, h->rank);
+        if (nrc) { fail(h, DUGKS_ERR_COMM, "ncclCommInitRank failed: %s", g_nccl.errstr ? g_nccl.errstr(nrc) : "?"); return bail(DUGKS_ERR_COMM); }
+    }
+
+    TRYB(h->hasH ? init_state<true>(h) : init_state<false>(h));
+    CUDAB(cudaStreamSynchronize(h->stream));
+    CUDAB(cudaGetLastError());
+#undef TRYB
+#undef CUDAB
+    *out = h;
+    return 0;
+}
+
+extern "C" int dugks_step(dugks_handle_t* h, double dt) {
+    if (!h) return DUGKS_ERR_INVALID;
+    if (!(dt > 0.0)) return fail(h, DUGKS_ERR_INVALID, "dugks_step: dt must be positive");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    return h->hasH ? step_impl<true>(h, dt) : step_impl<false>(h, dt);
+}
+
+extern "C" int dugks_sync(dugks_handle_t* h) {
+    if (!h) return DUGKS_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
+}
+
+extern "C" void* dugks_stream(dugks_handle_t* h) { return h ? (void*)h->stream : nullptr; }
+
+static int fetch(dugks_handle* h, const double* dev, size_t n, std::vector<double>& host) {
+    host.resize(n);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaMemcpyAsync(host.data(), dev, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+static void unpack_macros(const std::vector<double>& m, size_t n, double* rho, double* U, double* T, double* q, double* tau) {
+    for (size_t k = 0; k < n; k++) {
+        const double* p = m.data() + k * MAC_N;
+        if (rho) rho[k] = p[0];
+        if (U) { U[3 * k] = p[1]; U[3 * k + 1] = p[2]; U[3 * k + 2] = p[3]; }
+        if (T) T[k] = p[4];
+        if (tau) tau[k] = p[5];
+        if (q) { q[3 * k] = p[6]; q[3 * k + 1] = p[7]; q[3 * k + 2] = p[8]; }
+    }
+}
+
+extern "C" int dugks_get_cell_macros(dugks_handle_t* h, double* rho, double* U, double* T, double* q, double* tau) {
+    if (!h) return DUGKS_ERR_INVALID;
+    std::vector<double> m;
+    int rc = fetch(h, h->A.cmac, (size_t)h->nc * MAC_N, m);
+    if (rc) return rc;
+    unpack_macros(m, h->nc, rho, U, T, q, tau);
+    return 0;
+}
+
+extern "C" int dugks_get_face_macros(dugks_handle_t* h, double* rho, double* U, double* T, double* q, double* tau) {
+    if (!h) return DUGKS_ERR_INVALID;
+    std::vector<double> m;
+    int rc = fetch(h, h->A.fmac, (size_t)h->nf * MAC_N, m);
+    if (rc) return rc;
+    unpack_macros(m, h->nf, rho, U, T, q, tau);
+    return 0;
+}
+
+extern "C" int dugks_get_boundary_macros(dugks_handle_t* h, double* rho_b, double* U_b, double* T_b) {
+    if (!h) return DUGKS_ERR_INVALID;
+    std::vector<double> m;
+    int rc = fetch(h, h->A.bmac, (size_t)h->nbf * 5, m);
+    if (rc) return rc;
+    for (int b = 0; b < h->nbf; b++) {
+        if (rho_b) rho_b[b] = m[(size_t)b * 5];
+        if (U_b) for (int d = 0; d < 3; d++) U_b[3 * b + d] = m[(size_t)b * 5 + 1 + d];
+        if (T_b) T_b[b] = m[(size_t)b * 5 + 4];
+    }
+    return 0;
+}
+
+extern "C" int dugks_set_boundary_macros(dugks_handle_t* h, const double* rho_b, const double* U_b, const double* T_b) {
+    if (!h) return DUGKS_ERR_INVALID;
+    std::vector<double> m;
+    int rc = fetch(h, h->A.bmac, (size_t)h->nbf * 5, m);
+    if (rc) return rc;
+    for (int b = 0; b < h->nbf; b++) {
+        if (rho_b) m[(size_t)b * 5] = rho_b[b];
+        if (U_b) for (int d = 0; d < 3; d++) m[(size_t)b * 5 + 1 + d] = U_b[3 * b + d];
+        if (T_b) m[(size_t)b * 5 + 4] = T_b[b];
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(h->A.bmac, m.data(), m.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return h->hasH ? compute_wall_constants<true>(h) : compute_wall_constants<false>(h);
+}
+
+extern "C" int dugks_get_wall_diag(dugks_handle_t* h, double* qWall, double* stressWall) {
+    if (!h) return DUGKS_ERR_INVALID;
+    std::vector<double> m;
+    int rc = fetch(h, h->A.wall_diag, (size_t)h->nbf * 12, m);
+    if (rc) return rc;
+    for (int b = 0; b < h->nbf; b++) {
+        if (qWall) for (int d = 0; d < 3; d++) qWall[3 * b + d] = m[(size_t)b * 12 + d];
+        if (stressWall) for (int d = 0; d < 9; d++) stressWall[9 * b + d] = m[(size_t)b * 12 + 3 + d];
+    }
+    return 0;
+}
+
+extern "C" int dugks_courant(dugks_handle_t* h, double dt, double* maxCo, double* meanCo) {
+    if (!h) return DUGKS_ERR_INVALID;
+    if (h->nif == 0) { if (maxCo) *maxCo = 0; if (meanCo) *meanCo = 0; return 0; }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    StepArgs a = h->A;
+    k_courant<<<1, 1024, 0, h->stream>>>(a, std::sqrt((double)h->D) * h->xiMax, h->d_co);
+    int rc = check_launch(h, "k_courant");
+    if (rc) return rc;
+    double out[2];
+    CUDA_TRY(h, cudaMemcpyAsync(out, h->d_co, sizeof out, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (maxCo) *maxCo = out[0] * dt;
+    if (meanCo) *meanCo = out[1] / h->nif * dt;
+    return 0;
+}
+
+extern "C" int dugks_local_dvs(dugks_handle_t* h, int32_t* ids, int32_t* n) {
+    if (!h || !n) return DUGKS_ERR_INVALID;
+    *n = h->nvl;
+    if (ids) memcpy(ids, h->local_gids.data(), sizeof(int32_t) * h->nvl);
+    return 0;
+}
+
+extern "C" int dugks_sizes(dugks_handle_t* h, int32_t* nXi, int32_t* nXiLocal, int32_t* nCells, int32_t* nFaces) {
+    if (!h) return DUGKS_ERR_INVALID;
+    if (nXi) *nXi = h->nxi;
+    if (nXiLocal) *nXiLocal = h->nvl;
+    if (nCells) *nCells = h->nc;
+    if (nFaces) *nFaces = h->nf;
+    return 0;
+}
+
+// state <-> DV-major host arrays; device layout [slab][cell][i][r]
+static int state_io(dugks_handle* h, double* dev, double* host, bool to_host) {
+    const size_t slabsz = (size_t)h->L * h->Rs;
+    std::vector<double> tmp((size_t)h->nc * slabsz);
+    for (int s = 0; s < h->nslab; s++) {
+        double* dslab = dev + (size_t)s * h->nc * slabsz;
+        // read-modify-write also when storing: padding entries keep their device values
+        CUDA_TRY(h, cudaMemcpyAsync(tmp.data(), dslab, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        for (int j = 0; j < h->nvl; j++) {
+            size_t flat = h->local_flat[j];
+            if (flat / slabsz != (size_t)s) continue;
+            size_t rem = flat % slabsz;
+            double* hj = host + (size_t)j * h->nc;
+            if (to_host) for (int c = 0; c < h->nc; c++) hj[c] = tmp[(size_t)c * slabsz + rem];
+            else for (int c = 0; c < h->nc; c++) tmp[(size_t)c * slabsz + rem] = hj[c];
+        }
+        if (!to_host) {
+            CUDA_TRY(h, cudaMemcpyAsync(dslab, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        }
+    }
+    return 0;
+}
+
+extern "C" int dugks_get_state(dugks_handle_t* h, double* g, double* h_) {
+    if (!h) return DUGKS_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc;
+    if (g && (rc = state_io(h, h->A.gt, g, true))) return rc;
+    if (h_) {
+        if (h->hasH) { if ((rc = state_io(h, h->A.ht, h_, true))) return rc; }
+        else memset(h_, 0, sizeof(double) * (size_t)h->nvl * h->nc);   // h == 0 exactly when elided
+    }
+    return 0;
+}
+
+extern "C" int dugks_set_state(dugks_handle_t* h, const double* g, const double* h_) {
+    if (!h) return DUGKS_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc;
+    if (g && (rc = state_io(h, h->A.gt, const_cast<double*>(g), false))) return rc;
+    if (h_ && h->hasH && (rc = state_io(h, h->A.ht, const_cast<double*>(h_), false))) return rc;
+    return 0;
+}
+
+extern "C" int dugks_get_df(dugks_handle_t* h, int32_t cell, double* g, double* h_) {
+    if (!h || cell < 0 || cell >= h->nc) return h ? fail(h, DUGKS_ERR_INVALID, "dugks_get_df: bad cell") : DUGKS_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    // gather this rank's slice into a zero-filled global vector on the device, then sum over
+    // ranks (an all-gather expressed with the one collective the reducer offers)
+    const size_t slabsz = (size_t)h->L * h->Rs;
+    for (int pass = 0; pass < 2; pass++) {
+        double* dst = pass == 0 ? g : h_;
+        if (!dst) continue;
+        const double* src = pass == 0 ? h->A.gt : h->A.ht;
+        std::vector<double> glob(h->nxi, 0.0);
+        if (src) {
+            std::vector<double> tmp(slabsz);
+            for (int s = 0; s < h->nslab; s++) {
+                CUDA_TRY(h, cudaMemcpyAsync(tmp.data(), src + ((size_t)s * h->nc + cell) * slabsz, slabsz * sizeof(double),
+                                            cudaMemcpyDeviceToHost, h->stream));
+                CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+                for (size_t k = 0; k < slabsz; k++) {
+                    int gid = h->flat_gid[(size_t)s * slabsz + k];
+                    if (gid >= 0) glob[gid] = tmp[k];
+                }
+            }
+        }
+        if (h->nranks > 1) {
+            double* d = nullptr;
+            CUDA_TRY(h, cudaMalloc(&d, sizeof(double) * h->nxi));
+            CUDA_TRY(h, cudaMemcpyAsync(d, glob.data(), sizeof(double) * h->nxi, cudaMemcpyHostToDevice, h->stream));
+            int rc = do_allreduce(h, d, h->nxi);
+            if (!rc) {
+                cudaMemcpyAsync(glob.data(), d, sizeof(double) * h->nxi, cudaMemcpyDeviceToHost, h->stream);
+                cudaStreamSynchronize(h->stream);
+            }
+            cudaFree(d);
+            if (rc) return rc;
+        }
+        memcpy(dst, glob.data(), sizeof(double) * h->nxi);
+    }
+    return 0;
+}
+
+extern "C" int dugks_get_stats(dugks_handle_t* h, dugks_stats_t* out) {
+    if (!h || !out) return DUGKS_ERR_INVALID;
+    out->kernel_launches = h->launches;
+    out->steps = h->steps;
+    out->device_bytes = h->dev_bytes;
+    out->h_elided = h->hasH ? 0 : 1;
+    out->n_slabs = h->nslab;
+    out->slab_dvs = h->L * h->Rs;
+    out->reserved = 0;
+    return 0;
+}
+
+extern "C" int dugks_kernel_timing(dugks_handle_t* h, int enable, int which, double* total_ms, uint64_t* launches) {
+    if (!h) return DUGKS_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (total_ms || launches) {
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        double tot = 0;
+        uint64_t n = 0;
+        for (auto& e : h->events)
+            if (e.which == which) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, e.a, e.b);
+                tot += ms;
+                n++;
+            }
+        if (total_ms) *total_ms = tot;
+        if (launches) *launches = n;
+    }
+    if (enable == 0 || enable == 2) {   // 0: stop and clear, 2: clear and keep running
+        for (auto& e : h->events) h->pool.push_back(e);
+        h->events.clear();
+    }
+    if (enable == 0) h->timing = false;
+    if (enable == 1 || enable == 2) h->timing = true;
+    return 0;
+}
+
+// debug accessor for parity tests: boundary-face values gSurf/hSurf of local DV j (sorted
+// global-id order) on all boundary faces, [nvl][nbf]
+extern "C" int dugks_get_boundary_df(dugks_handle_t* h, double* g, double* h_) {
+    if (!h) return DUGKS_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t slabsz = (size_t)h->L * h->Rs;
+    for (int pass = 0; pass < 2; pass++) {
+        double* dst = pass == 0 ? g : h_;
+        const double* src = pass == 0 ? h->A.gsb : h->A.hsb;
+        if (!dst) continue;
+        if (!src) { memset(dst, 0, sizeof(double) * (size_t)h->nvl * h->nbf); continue; }
+        std::vector<double> tmp;
+        int rc = fetch(h, src, (size_t)h->nbf * h->nflat, tmp);
+        if (rc) return rc;
+        for (int j = 0; j < h->nvl; j++) {
+            size_t flat = h->local_flat[j], s = flat / slabsz, rem = flat % slabsz;
+            for (int b = 0; b < h->nbf; b++) dst[(size_t)j * h->nbf + b] = tmp[(s * h->nbf + b) * slabsz + rem];
+        }
+    }
+    return 0;
+}

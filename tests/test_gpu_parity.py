@@ -1,0 +1,138 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle.
+
+Bar (BASELINE.json north_star): 1e-12 relative per step, 1e-9 on rho/U/T/q after
+1000 steps, FP64.  Relative = max|a-b| / max|b| per field (vector fields whose
+reference value may vanish are scaled by the thermal speed / rho c^3).
+"""
+import numpy as np
+import pytest
+
+from dugksfoam_b200 import capi
+from dugksfoam_b200 import case as cs
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare(dv, orc, case, tol, label):
+    sc = util.macro_scales(case)
+    errs = {}
+    cm_g, cm_o = dv.cell_macros(), orc.cell_macros()
+    fm_g, fm_o = dv.face_macros(), orc.face_macros()
+    for k in ("rho", "T", "tau"):
+        errs["cell_" + k] = util.rel_err(cm_g[k], cm_o[k])
+        errs["face_" + k] = util.rel_err(fm_g[k], fm_o[k])
+    for k in ("U", "q"):
+        errs["cell_" + k] = util.rel_err(cm_g[k], cm_o[k], sc[k])
+        errs["face_" + k] = util.rel_err(fm_g[k], fm_o[k], sc[k])
+    bm_g, bm_o = dv.boundary_macros(), orc.boundary_macros()
+    errs["bnd_rho"] = util.rel_err(bm_g["rho"], bm_o["rho"], sc["rho"])
+    errs["bnd_U"] = util.rel_err(bm_g["U"], bm_o["U"], sc["U"])
+    errs["bnd_T"] = util.rel_err(bm_g["T"], bm_o["T"], sc["T"])
+    wd_g, wd_o = dv.wall_diag(), orc.wall_diag()
+    errs["qWall"] = util.rel_err(wd_g["qWall"], wd_o["qWall"], sc["q"])
+    errs["stressWall"] = util.rel_err(wd_g["stressWall"], wd_o["stressWall"], sc["rho"] * sc["U"] ** 2)
+    g_g, h_g = dv.state()
+    g_o, h_o = orc.state()
+    ids = dv.local_dvs()
+    errs["gTilde"] = util.rel_err(g_g, g_o[ids])
+    errs["hTilde"] = util.rel_err(h_g, h_o[ids], max(np.abs(h_o).max(), 1e-300))
+    bad = {k: v for k, v in errs.items() if not (v <= tol)}
+    assert not bad, f"{label}: parity above {tol:g}: {bad}  (all: {errs})"
+    return errs
+
+
+@pytest.mark.parametrize("name,case,store_h", util.cases_small(), ids=[c[0] for c in util.cases_small()])
+def test_step_parity(oracle_lib, name, case, store_h):
+    dv = capi.fvDVM(case, store_h=store_h)
+    orc = oracle_lib.Oracle(case)
+    dt = case.courant_dt(0.5)
+    assert np.allclose(dv.getCoNum(dt), orc.courant(dt), rtol=1e-12)
+    # initial state (discreteVelocity::initDFtoEq)
+    _compare(dv, orc, case, util.TOL_STEP, name + " init")
+    for step in range(4):
+        dtk = dt * (1.0 + 0.1 * step)           # dt changes every step (adjustTimeStep)
+        dv.evolution(dtk)
+        orc.step(dtk)
+        _compare(dv, orc, case, util.TOL_STEP * (step + 1), f"{name} step {step + 1}")
+        assert np.allclose(dv.getCoNum(dtk), orc.courant(dtk), rtol=1e-10)
+    # boundary face DFs
+    gb, hb = dv.boundary_surf()
+    nif = case.geom.nInternalFaces
+    ids = dv.local_dvs()
+    ref = np.stack([orc.surf(int(k))[0][nif:] for k in ids])
+    assert util.rel_err(gb, ref) <= 1e-11
+    dv.close(); orc.close()
+
+
+def _bc_cases():
+    K = cs
+    out = []
+    # far field in / zero-gradient out, mixed (fixedValue rho) top, Maxwell wall bottom
+    out.append(("farfield_zg_mixed", util.channel_case(
+        10, 6, 8, kinds={"inlet": K.PATCH_FAR_FIELD, "outlet": K.PATCH_ZERO_GRADIENT, "top": K.PATCH_MIXED},
+        bc_overrides={"inlet": dict(U=(30.0, 0, 0), rho=1.2 * K.RHO0, T=290.0, U_bc=K.BC_ZERO_GRADIENT),
+                      "top": dict(U=(20.0, 0, 0), T=280.0)}, perturb=0.01)))
+    # pressure inlet / outlet
+    p0 = K.RHO0 * K.ARGON["R"] * K.T0
+    out.append(("pressure_in_out", util.channel_case(
+        10, 6, 8, kinds={"inlet": K.PATCH_PRESSURE_IN, "outlet": K.PATCH_PRESSURE_OUT},
+        bc_overrides={"inlet": dict(pressure=1.1 * p0), "outlet": dict(pressure=0.9 * p0)}, perturb=0.01)))
+    # symmetryMod (DVMsymmetry) on the left, symmetryPlane-like on the bottom
+    out.append(("dvm_symmetry", util.channel_case(
+        8, 6, 8, kinds={"inlet": K.PATCH_DVM_SYMMETRY, "bottom": K.PATCH_SYMMETRY_PLANE},
+        bc_overrides={"top": dict(U=(40.0, 0, 0))}, perturb=0.01)))
+    return out
+
+
+@pytest.mark.parametrize("name,case", _bc_cases(), ids=[c[0] for c in _bc_cases()])
+def test_boundary_kinds(oracle_lib, name, case):
+    dv = capi.fvDVM(case)
+    orc = oracle_lib.Oracle(case)
+    dt = case.courant_dt(0.5)
+    for step in range(4):
+        dv.evolution(dt)
+        orc.step(dt)
+        _compare(dv, orc, case, util.TOL_STEP * (step + 1), f"{name} step {step + 1}")
+    dv.close(); orc.close()
+
+
+def test_thousand_steps(oracle_lib):
+    """1e-9 on rho/U/T/q after 1000 steps (north_star)."""
+    case = cs.cavity2d_case(10, 8)
+    dv = capi.fvDVM(case)
+    orc = oracle_lib.Oracle(case)
+    dt = case.courant_dt(0.8)
+    for _ in range(1000):
+        dv.evolution(dt)
+        orc.step(dt)
+    sc = util.macro_scales(case)
+    a, b = dv.cell_macros(), orc.cell_macros()
+    assert util.rel_err(a["rho"], b["rho"]) <= util.TOL_LONG
+    assert util.rel_err(a["T"], b["T"]) <= util.TOL_LONG
+    assert util.rel_err(a["U"], b["U"], np.abs(b["U"]).max()) <= util.TOL_LONG
+    assert util.rel_err(a["q"], b["q"], np.abs(b["q"]).max()) <= util.TOL_LONG
+    dv.close(); orc.close()
+
+
+def test_set_get_state_roundtrip():
+    case = cs.cavity2d_case(6, 8)
+    dv = capi.fvDVM(case)
+    g, h = dv.state()
+    rng = np.random.default_rng(1)
+    g2 = g * (1 + 0.01 * rng.random(g.shape))
+    dv.set_state(g2, h)
+    g3, _ = dv.state()
+    assert np.array_equal(g2, g3)
+    gd, hd = dv.writeDFonCell(3)
+    assert np.array_equal(gd[dv.local_dvs()], g3[:, 3])
+    st = dv.stats()
+    assert st["kernel_launches"] > 0
+    dv.close()
+
+
+def test_fails_loudly_on_bad_input():
+    case = cs.cavity2d_case(4, 8)
+    case.patches[0].kind = 99
+    with pytest.raises(capi.DugksError):
+        capi.fvDVM(case)

@@ -1,0 +1,55 @@
+"""Shared helpers of the parity tests: case zoo and comparison metrics."""
+import numpy as np
+
+from dugksfoam_b200 import case as cs
+from dugksfoam_b200 import dvset
+from dugksfoam_b200.polymesh import hex_block
+
+# tolerance of BASELINE.json north_star: 1e-12 relative per step (FP64)
+TOL_STEP = 1e-12
+# 1e-9 on rho/U/T/q after 1000 steps
+TOL_LONG = 1e-9
+
+
+def rel_err(a, b, scale=None):
+    """max |a-b| / max |b| (or / scale): field-wise relative L-infinity error."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    s = np.abs(b).max() if scale is None else scale
+    if s == 0.0:
+        return float(np.abs(a - b).max())
+    return float(np.abs(a - b).max() / s)
+
+
+def macro_scales(case):
+    """Characteristic magnitudes used for the vector fields whose reference value may be ~0."""
+    R = case.gas["R"]
+    T = float(np.max(case.T))
+    rho = float(np.max(case.rho))
+    c = np.sqrt(2 * R * T)
+    return dict(U=c, q=rho * c ** 3, rho=rho, T=T)
+
+
+def channel_case(nx=10, ny=6, nDV=8, kinds=None, **kw):
+    """2-D channel: xmin = inlet patch, xmax = outlet patch, ymin/ymax walls; used for the
+    far-field / mixed / zeroGradient / pressure / symmetry boundary kinds."""
+    names = {"xmin": "inlet", "xmax": "outlet", "ymin": "bottom", "ymax": "top"}
+    mesh = hex_block(nx, ny, 1, (1.0, 0.6, 0.1), two_d=True, patch_names=names, distort=kw.pop("distort", 0.0))
+    Xis, w = cs.gh_set(nDV)
+    kinds = kinds or {}
+    c = cs._uniform_case(mesh, Xis, w, kinds, lid_patch="none", name="channel", **kw)
+    return c
+
+
+def cases_small():
+    """(name, case, store_h) tuples the oracle finishes in well under a second per step."""
+    out = []
+    out.append(("cavity2d_12_gh8", cs.cavity2d_case(12, 8, perturb=0.01), False))
+    out.append(("cavity2d_16_gh28", cs.cavity2d_case(16, 28), False))
+    out.append(("cavity2d_10_gh8_distort", cs.cavity2d_case(10, 8, distort=0.2, perturb=0.01), False))
+    out.append(("cavity2d_9_nc9_ties", cs.cavity2d_case(9, 9, quad="NC", perturb=0.01), False))
+    out.append(("cavity3d_6_gh8", cs.cavity3d_case(6, 8, perturb=0.01), False))
+    out.append(("cavity3d_5_gh8_storeh", cs.cavity3d_case(5, 8, perturb=0.01), True))
+    out.append(("cavity3d_5_gh8_distort", cs.cavity3d_case(5, 8, distort=0.15, perturb=0.01), False))
+    out.append(("tri_8_gh8", cs.tri_cavity_case(8, 8, perturb=0.01), False))
+    return out
