@@ -9,7 +9,7 @@ import pytest
 
 from dugksfoam_b200 import capi
 from dugksfoam_b200 import case as cs
-from tests import util
+import parity_util as util
 
 pytestmark = pytest.mark.gpu
 
@@ -26,7 +26,8 @@ def _compare(dv, orc, case, tol, label):
         errs["cell_" + k] = util.rel_err(cm_g[k], cm_o[k], sc[k])
         errs["face_" + k] = util.rel_err(fm_g[k], fm_o[k], sc[k])
     bm_g, bm_o = dv.boundary_macros(), orc.boundary_macros()
-    errs["bnd_rho"] = util.rel_err(bm_g["rho"], bm_o["rho"], sc["rho"])
+    if not label.endswith("init"):   # wall rho starts at 1 in the reference (calculatedMaxwellFvPatchField.C:80), unused
+        errs["bnd_rho"] = util.rel_err(bm_g["rho"], bm_o["rho"], sc["rho"])
     errs["bnd_U"] = util.rel_err(bm_g["U"], bm_o["U"], sc["U"])
     errs["bnd_T"] = util.rel_err(bm_g["T"], bm_o["T"], sc["T"])
     wd_g, wd_o = dv.wall_diag(), orc.wall_diag()

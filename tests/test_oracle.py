@@ -1,0 +1,205 @@
+"""CPU tests (no GPU): the oracle pinned against the reference's golden vector and the
+physical / numerical identities that stand in for the golden outputs the reference
+does not ship ("parity unpinned")."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import parity_util as util
+from dugksfoam_b200 import case as cs
+from dugksfoam_b200 import dvset
+from dugksfoam_b200.polymesh import compute_geometry, hex_block, tri_prism_2d
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, "golden", "demo_cavity.json")))
+REF_DEMO = "/root/reference/demo/cavity"
+
+
+# ---- golden vector: the shipped 28-point half-range Gauss-Hermite set -----------------
+def test_gh_quadrature_matches_shipped_demo_set():
+    g = GOLD["gas"]
+    Xis, w = dvset.dvGH(float(np.sqrt(2.0 * g["R"] * GOLD["T0"])), 28)      # doc/demo.tex:28
+    assert util.rel_err(Xis, GOLD["Xis"]) < 1e-10
+    assert util.rel_err(w, GOLD["weights"]) < 1e-9
+    # quadrature identities: moments of a 1-D Maxwellian at the case temperature
+    RT = g["R"] * GOLD["T0"]
+    X, W = np.array(GOLD["Xis"]), np.array(GOLD["weights"])
+    M = np.exp(-X ** 2 / (2 * RT)) / np.sqrt(2 * np.pi * RT)
+    assert abs((W * M).sum() - 1.0) < 1e-13
+    assert abs((W * M * X ** 2).sum() / RT - 1.0) < 1e-12
+    assert abs((W * M * X).sum()) < 1e-10
+
+
+def test_newton_cotes_rule():
+    X, w = dvset.dvNC(1600.0, 41)                                            # setDV.py usage example
+    assert len(X) == 41 and abs(X[0] + 1600) < 1e-12 and abs(X[-1] - 1600) < 1e-9
+    # Boole's rule integrates polynomials up to degree 5 exactly
+    for p in range(6):
+        exact = 0.0 if p % 2 else 2 * 1600.0 ** (p + 1) / (p + 1)
+        assert abs((w * X ** p).sum() - exact) <= 1e-13 * 2 * 1600.0 ** (p + 1)
+    with pytest.raises(ValueError):
+        dvset.dvNC(1600.0, 40)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_DEMO), reason="reference tree not mounted")
+def test_demo_cavity_reader_matches_golden_facts():
+    c = cs.read_case(REF_DEMO)
+    g = c.geom
+    assert (g.nCells, g.nInternalFaces, g.nBoundaryFaces, g.nSolutionD) == (3600, 7080, 240, 2)
+    assert g.patch_names == ["movingWall", "fixedWalls"] and g.patch_size == [60, 180]
+    assert [p.kind for p in c.patches] == [cs.PATCH_MAXWELL_WALL, cs.PATCH_MAXWELL_WALL]
+    assert np.allclose(c.U_b[:60], [50.0, 0, 0]) and np.allclose(c.U_b[60:], 0.0)
+    assert np.array_equal(c.Xis, GOLD["Xis"]) and np.array_equal(c.weights, GOLD["weights"])
+    assert abs(g.V.sum() - 0.1) < 1e-15
+    # the shipped mesh and the generated 60x60 block have the same geometry up to numbering
+    s = cs.cavity2d_case(60).geom
+    assert np.allclose(np.sort(g.V), np.sort(s.V), rtol=1e-12)
+    assert np.allclose(np.sort(g.deltaCoeffs), np.sort(s.deltaCoeffs), rtol=1e-10)
+
+
+def test_golden_case_facts():
+    assert GOLD["nCells"] == 3600 and GOLD["nInternalFaces"] == 7080 and GOLD["nPoints"] == 7442
+    assert GOLD["nFacesAll"] == 14520 and GOLD["patch_sizes"] == [60, 180]
+    assert abs(GOLD["gas"]["R"] - 208.244343891) < 1e-12 and GOLD["lid_U"] == [50.0, 0.0, 0.0]
+
+
+# ---- geometry identities ---------------------------------------------------------------
+@pytest.mark.parametrize("mesh", [hex_block(5, 4, 3, (1.0, 0.8, 0.6), distort=0.2),
+                                  hex_block(6, 5, 1, (1.0, 1.0, 0.1), two_d=True, distort=0.2),
+                                  tri_prism_2d(5, 4, distort=0.15)], ids=["hex3d", "hex2d", "tri2d"])
+def test_geometry_identities(mesh):
+    from dugksfoam_b200.polymesh import cell_centres_and_volumes, face_centres_and_areas
+    Cf, Sf = face_centres_and_areas(mesh)
+    C, V = cell_centres_and_volumes(mesh, Cf, Sf)
+    nif = mesh.nInternalFaces
+    closure = np.zeros((mesh.nCells, 3))
+    np.add.at(closure, mesh.owner, Sf)
+    np.add.at(closure, mesh.neighbour, -Sf[:nif])
+    assert np.abs(closure).max() < 1e-15                          # sum of Sf over a closed cell = 0
+    lens = mesh.points.max(axis=0) - mesh.points.min(axis=0)
+    assert abs(V.sum() - np.prod(lens)) < 1e-14                   # sum V = domain volume
+    g = compute_geometry(mesh)
+    # least-squares gradient is exact for linear fields, including boundary cells when the
+    # boundary value is the exact linear value (stock leastSquares with boundary faces)
+    a = np.array([0.3, -1.1, 0.7]) * (~g.empty_dirs)
+    phi = C @ a + 2.0
+    grad = np.zeros((g.nCells, 3))
+    own, nei = g.owner[:nif], g.neighbour
+    d = phi[nei] - phi[own]
+    np.add.at(grad, own, g.ownLs * d[:, None])
+    np.add.at(grad, nei, -g.neiLs * d[:, None])
+    ob = g.owner[nif:]
+    nHat = g.Sf[nif:] / np.linalg.norm(g.Sf[nif:], axis=1)[:, None]
+    delta = nHat * np.einsum("ij,ij->i", nHat, g.Cf[nif:] - g.C[ob])[:, None]
+    phib = phi[ob] + delta @ a                                     # value at C + delta
+    np.add.at(grad, ob, g.patchLs * (phib - phi[ob])[:, None])
+    assert np.abs(grad - a[None, :]).max() < 1e-10
+
+
+# ---- oracle identities -------------------------------------------------------------------
+def _run(oracle_lib, case, nsteps, co=0.5, **kw):
+    o = oracle_lib.Oracle(case, **kw)
+    dt = case.courant_dt(co)
+    for _ in range(nsteps):
+        o.step(dt)
+    return o
+
+
+def test_uniform_equilibrium_is_steady(oracle_lib):
+    """Gas at rest between isothermal walls at the gas temperature stays at rest up to the
+    quadrature error of the 28-point set."""
+    case = cs.cavity2d_case(8, 28)
+    case.U_b[:] = 0.0
+    o = _run(oracle_lib, case, 5)
+    m = o.cell_macros()
+    assert util.rel_err(m["rho"], case.rho) < 1e-11
+    assert util.rel_err(m["T"], case.T) < 1e-11
+    assert np.abs(m["U"]).max() < 1e-8 * np.sqrt(2 * case.gas["R"] * 273.0)
+    o.close()
+
+
+@pytest.mark.parametrize("D", [2, 3])
+def test_velocity_partition_independence(oracle_lib, D):
+    """serial == -dvParallel decomposition up to summation order (fvDVM.C:228-260)."""
+    case = cs.cavity2d_case(8, 8, perturb=0.01) if D == 2 else cs.cavity3d_case(4, 8, perturb=0.01)
+    ref = _run(oracle_lib, case, 3)
+    a = ref.cell_macros()
+    for P, part in ((4, 0), (3, 1)):
+        o = _run(oracle_lib, case, 3, nranks=P, partition=part)
+        b = o.cell_macros()
+        sc = util.macro_scales(case)
+        assert util.rel_err(b["rho"], a["rho"]) < 1e-13
+        assert util.rel_err(b["T"], a["T"]) < 1e-13
+        assert util.rel_err(b["U"], a["U"], sc["U"]) < 1e-13
+        assert util.rel_err(b["q"], a["q"], sc["q"]) < 1e-13
+        assert util.rel_err(o.state()[0], ref.state()[0]) < 1e-13
+        o.close()
+    ref.close()
+
+
+def test_mirror_symmetry_of_the_cavity(oracle_lib):
+    """A cavity driven by two opposite lids moving in opposite directions is point-symmetric;
+    the solution must keep that symmetry to round-off (checks owner/neighbour handling,
+    upwinding and wall treatment for both signs of every velocity component)."""
+    n = 8
+    mesh = hex_block(n, n, 1, (1.0, 1.0, 0.1), two_d=True,
+                     patch_names={"ymax": "movingWall", "ymin": "lid2", "xmin": "fixedWalls", "xmax": "fixedWalls"})
+    Xis, w = cs.gh_set(8)
+    case = cs._uniform_case(mesh, Xis, w, {}, bc_overrides={"lid2": dict(U=(-50.0, 0, 0))})
+    o = _run(oracle_lib, case, 6)
+    m = o.cell_macros()
+    rho = m["rho"].reshape(n, n)
+    Ux = m["U"][:, 0].reshape(n, n)
+    assert util.rel_err(rho[::-1, ::-1], rho) < 1e-13
+    assert util.rel_err(-Ux[::-1, ::-1], Ux) < 1e-12
+    o.close()
+
+
+def test_half_cavity_with_symmetry_patch(oracle_lib):
+    """demo/testSymmetry: a half cavity closed by a DVMsymmetry patch reproduces the flow of the
+    mirrored full cavity.  Here the full problem is the symmetric double-lid cavity (both lids move
+    in +x), whose solution is mirror-symmetric about y = 0.5."""
+    n = 8
+    Xis, w = cs.gh_set(8)
+    full_mesh = hex_block(n, n, 1, (1.0, 1.0, 0.1), two_d=True,
+                          patch_names={"ymax": "movingWall", "ymin": "lid2", "xmin": "fixedWalls", "xmax": "fixedWalls"})
+    full = cs._uniform_case(full_mesh, Xis, w, {}, bc_overrides={"lid2": dict(U=(50.0, 0, 0))})
+    half_mesh = hex_block(n, n // 2, 1, (1.0, 0.5, 0.1), two_d=True,
+                          patch_names={"ymax": "symmetryWall", "ymin": "lid2", "xmin": "fixedWalls", "xmax": "fixedWalls"})
+    half = cs._uniform_case(half_mesh, Xis, w, {"symmetryWall": cs.PATCH_DVM_SYMMETRY}, lid_patch="lid2")
+    dt = full.courant_dt(0.5)
+    of, oh = oracle_lib.Oracle(full), oracle_lib.Oracle(half)
+    for _ in range(20):
+        of.step(dt); oh.step(dt)
+    mf, mh = of.cell_macros(), oh.cell_macros()
+    # the symmetry treatment is a boundary closure, not an identity: agreement is to the
+    # truncation error of the boundary reconstruction, far below the flow signal
+    sig = np.abs(mf["U"][:, 0]).max()
+    assert np.abs(mf["U"][: n * n // 2, 0] - mh["U"][:, 0]).max() < 0.05 * sig
+    assert util.rel_err(mh["rho"], mf["rho"][: n * n // 2]) < 1e-3   # flow signal in rho is ~5e-2
+    of.close(); oh.close()
+
+
+def test_mass_change_equals_boundary_flux_only(oracle_lib):
+    """Internal-face fluxes cancel exactly: with zero-velocity walls and a symmetric start the
+    total mass changes only through the (tiny) wall-flux imbalance of the scheme."""
+    case = cs.cavity2d_case(8, 8, perturb=0.02)
+    o = oracle_lib.Oracle(case)
+    m0 = (o.cell_macros()["rho"] * case.geom.V).sum()
+    dt = case.courant_dt(0.5)
+    for _ in range(5):
+        o.step(dt)
+    m1 = (o.cell_macros()["rho"] * case.geom.V).sum()
+    assert abs(m1 - m0) / m0 < 1e-6
+    o.close()
+
+
+def test_courant_number(oracle_lib):
+    case = cs.cavity2d_case(8, 8)
+    o = oracle_lib.Oracle(case)
+    dt = case.courant_dt(0.8)
+    mx, mean = o.courant(dt)
+    assert abs(mx - 0.8) < 1e-12 and abs(mean - 0.8) < 1e-12          # uniform mesh, U = 0
+    o.close()
