@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py — cell x DV updates/s of the DUGKS discrete-velocity update on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" = one fvDVM::evolution() (all stages) over the whole mesh and all discrete
+velocities.  Workload at every N: BASELINE.json configs[2], the configuration the metric is
+quoted on — 3-D cavity 64^3 hexes x 28^3 Gauss-Hermite velocities (h == 0 in 3-D monatomic gas
+and is elided, nf = 1) — velocity space sharded over the N GPUs (strong scaling: total work fixed).
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "cell x DV updates/sec (GUPS)"
+UNIT = "GUPS"
+
+WORKLOADS = {
+    # name: (builder, args)
+    "cavity3d_64_gh28": ("cavity3d", dict(n=64, nDV=28)),            # BASELINE configs[2] (headline)
+    "cavity2d_256_nc101": ("cavity2d", dict(n=256, nDV=101, quad="NC")),  # BASELINE configs[1]
+    "cavity3d_32_gh28": ("cavity3d", dict(n=32, nDV=28)),
+    "cavity3d_16_gh16": ("cavity3d", dict(n=16, nDV=16)),
+    "cavity2d_60_gh28": ("cavity2d", dict(n=60, nDV=28)),            # demo/cavity shape
+}
+# bounded CPU sample of the same workload shape (3-D cavity, 28^3 GH velocities, same gas/BCs)
+CPU_SAMPLE = ("cavity3d", dict(n=8, nDV=28))
+
+
+def build_case(kind, kw):
+    from dugksfoam_b200 import case as cs
+    if kind == "cavity3d":
+        return cs.cavity3d_case(kw["n"], kw["nDV"])
+    return cs.cavity2d_case(kw["n"], kw["nDV"], quad=kw.get("quad", "GH"))
+
+
+def b_alg(case, nf):
+    """Algorithmic bytes per update, SURVEY.md §8(d): 8 nf (3 + 2F)."""
+    return 8.0 * nf * (3.0 + 2.0 * case.faces_per_cell())
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.device)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_cpu_reference(steps, warmup, threads=None):
+    """Times the CPU restatement of the reference (oracle/, OpenMP over discrete velocities
+    like the reference's -dvParallel ranks) on a bounded sample of the workload."""
+    from oracle import oracle as orc
+    orc.build()
+    threads = threads or os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    case = build_case(*CPU_SAMPLE)
+    o = orc.Oracle(case)
+    dt = case.courant_dt(0.8)
+    for _ in range(warmup):
+        o.step(dt)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.step(dt)
+    el = time.perf_counter() - t0
+    ups = case.nCells * o.nxi * steps / el
+    o.close()
+    sample = (f"3-D cavity {CPU_SAMPLE[1]['n']}^3 cells x {CPU_SAMPLE[1]['nDV']}^3 GH velocities "
+              f"({case.nCells * case.nXi:.3g} updates/step), {steps} steps after {warmup} warm-up")
+    return ups / 1e9, el / steps * 1e3, threads, sample
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cavity3d_64_gh28", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    kind, kw = WORKLOADS[args.workload]
+    wl_name = f"{'3-D' if kind == 'cavity3d' else '2-D'} cavity {kw['n']}^{3 if kind == 'cavity3d' else 2} hex cells x " \
+              f"{kw['nDV']}^{3 if kind == 'cavity3d' else 2} {kw.get('quad', 'GH')} velocities, Kn=0.075 argon, Maxwell walls"
+
+    if args.impl == "reference":
+        # the reference's own CPU path (restated: OpenFOAM + MPI are not available, so the oracle
+        # port stands in), rank 0 only
+        if rank != 0:
+            return
+        K = max(1, min(args.steps, 4))
+        W = max(1, min(args.warmup, 1))
+        gups, ms, cores, sample = run_cpu_reference(K, W)
+        line = {
+            "impl": "reference", "metric": METRIC, "value": gups, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+            "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl_name, "timed_on": sample, "parallelism": f"openmp{cores}"},
+            "cpu_baseline": {"value": gups, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": gups, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line), flush=True)
+        return
+
+    import torch
+    from dugksfoam_b200 import capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; dugksfoam_b200 has no CPU fallback "
+                         "(use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    nccl_id = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt = torch.frombuffer(bytearray(capi.nccl_unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(idt, 0)
+        nccl_id = bytes(idt.cpu().numpy().tobytes())
+
+    case = build_case(kind, kw)
+    dv = capi.fvDVM(case, rank=rank, nranks=world, device=local_rank, nccl_id=nccl_id)
+    st0 = dv.stats()
+    nf = 1 if st0["h_elided"] else 2
+    dt = case.courant_dt(0.8)
+    updates_per_step = case.nCells * case.nXi
+    K, W = args.steps, max(args.warmup, 3)
+    stream = torch.cuda.ExternalStream(dv.stream(), device=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        dv.evolution(dt)
+    dv.sync()
+
+    # ---- device-timed region: K steps, state resident in HBM, CUDA events on the library's stream
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = dv.stats()["kernel_launches"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(K):
+        dv.evolution(dt)
+    e1.record(stream)
+    dv.sync()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = dv.stats()["kernel_launches"] - l0
+    clocks = sampler.stop() if rank == 0 else None
+    # per-kernel-family device time: a separate pass with CUDA events around every launch of the
+    # three big kernels (kept out of the timed region above)
+    dv.kernel_timing(1)
+    for _ in range(K):
+        dv.evolution(dt)
+    dv.sync()
+    fam = {}
+    for which, name in ((0, "k_cell_outgoing"), (1, "k_cell_update"), (2, "k_cell_halfstep")):
+        ms, n = dv.kernel_timing(-1, which)
+        fam[name] = {"ms_per_step": ms / K, "launches_per_step": n / K}
+    dv.kernel_timing(0)
+    if dist is not None:
+        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / K
+    gups = updates_per_step / (ms_step * 1e-3) / 1e9
+
+    # ---- end-to-end through the host-facing API: every step the host pushes the boundary macro
+    # fields (pinned host memory) and reads back the cell macro fields + Courant number, as the
+    # reference's time loop does (dugksFoam.C:63-109, CourantNo.H:35)
+    bm = dv.boundary_macros()
+    pin = {k: torch.from_numpy(v.copy()).pin_memory() for k, v in bm.items()}
+    h2d = sum(v.numel() * 8 for v in pin.values())
+    d2h = case.nCells * 11 * 8 + 16
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        dv.set_boundary_macros(None, pin["U"].numpy(), pin["T"].numpy())
+        dv.evolution(dt)
+        cm = dv.cell_macros()
+        co = dv.getCoNum(dt)
+    dv.sync()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_gups = updates_per_step * K / e2e_s / 1e9
+    assert np.isfinite(cm["rho"]).all() and co[0] > 0
+
+    if rank != 0:
+        dv.close()
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peaks()
+    balg = b_alg(case, nf)
+    achieved = gups / world * balg   # GB/s per GPU (each GPU advances 1/world of the updates) vs one GPU's HBM peak
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic_per_update.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(args.workload)
+        except Exception:
+            traffic = None
+    dom = max(fam, key=lambda k: fam[k]["ms_per_step"])
+    line = {
+        "metric": METRIC, "value": gups, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl_name, "nCells": case.nCells, "nXi": case.nXi, "updates_per_step": updates_per_step,
+                   "h_elided": bool(st0["h_elided"]), "nf": nf, "faces_per_cell": case.faces_per_cell(),
+                   "parallelism": f"dv{world}", "dt": dt,
+                   "l2_policy": "inputs larger than L2 (state is tens of GB per GPU)",
+                   "slabs_per_step": st0["n_slabs"], "slab_dvs": st0["slab_dvs"],
+                   "device_bytes": st0["device_bytes"]},
+        "e2e": {"value": e2e_gups, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_s / K * 1e3},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src,
+                     "scope": "whole step (all kernels of one evolution()), per GPU",
+                     "algorithmic_bytes_per_update": balg,
+                     "dominant_kernel": dom, "kernels": fam},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        cg, cms, cores, sample = run_cpu_reference(args.cpu_steps, 1)
+        line["cpu_baseline"] = {"value": cg, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                                "ms_per_step": cms}
+    print(json.dumps(line), flush=True)
+    dv.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
