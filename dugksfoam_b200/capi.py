@@ -41,6 +41,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     """nvcc -gencode arch=compute_100a,code=sm_100a ... -> dugksfoam_b200/libdugks.so (in tree)."""
     src = os.path.join(_HERE, "csrc", "dugks_capi.cu")
     deps = [src, os.path.join(_HERE, "csrc", "dugks_kernels.cuh"), os.path.join(_HERE, "csrc", "dugks_device.cuh"),
+            os.path.join(_HERE, "csrc", "dugks_fast.cuh"), os.path.join(_HERE, "csrc", "dugks_tma.cuh"),
             os.path.join(_HERE, "..", "include", "dugks.h")]
     if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(d) for d in deps):
         return LIB_PATH

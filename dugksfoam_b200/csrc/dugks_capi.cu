@@ -12,7 +12,7 @@
 #include <vector>
 
 #include "../../include/dugks.h"
-#include "dugks_kernels.cuh"
+#include "dugks_tma.cuh"
 
 // ------------------------------------------------------------------------------
 // NCCL through dlopen (the library is present in every torch install and on the
@@ -104,6 +104,12 @@ struct dugks_handle {
     std::vector<Ev> events;
     std::vector<Ev> pool;
     size_t smem_out1 = 0, smem_out2 = 0, smem_bnd = 0, smem_upd = 0;
+    size_t fsmem_out1 = 0, fsmem_out2 = 0, fsmem_upd = 0;
+    int n_big = 0;          // cells with more than FAST_NE faces (generic kernels)
+    bool use_fast = true;
+    bool use_tma = true;    // bulk-async staged kernels (dugks_tma.cuh)
+    int ci = 4, max_ne_fast = 0;
+    size_t tsmem_out1 = 0, tsmem_out2 = 0, tsmem_upd = 0;
 };
 
 static int fail(dugks_handle* h, int code, const char* fmt, ...) {
@@ -204,11 +210,21 @@ static int launch_slab_kernels_phase1(dugks_handle* h, StepArgs a) {
         k_cell_halfstep<H><<<grid_for(items), WARPS_PER_CTA * 32, 0, h->stream>>>(a, 0);
     }
     if ((rc = check_launch(h, "k_cell_halfstep"))) return rc;
-    {
+    if (h->use_fast && h->use_tma) {
         Timed t(h, 0);
-        k_cell_outgoing<1, H><<<grid_for(items), WARPS_PER_CTA * 32, h->smem_out1, h->stream>>>(a);
+        k_cell_outgoing_tma<1, H><<<grid_for(items), WARPS_PER_CTA * 32, h->tsmem_out1, h->stream>>>(a, h->ci, h->max_ne_fast + 1);
+        if ((rc = check_launch(h, "k_cell_outgoing_tma<1>"))) return rc;
+    } else if (h->use_fast) {
+        Timed t(h, 0);
+        k_cell_outgoing_fast<1, H><<<grid_for(items), WARPS_PER_CTA * 32, h->fsmem_out1, h->stream>>>(a);
+        if ((rc = check_launch(h, "k_cell_outgoing_fast<1>"))) return rc;
     }
-    if ((rc = check_launch(h, "k_cell_outgoing<1>"))) return rc;
+    if (!h->use_fast || h->n_big > 0) {
+        Timed t(h, 0);
+        a.skip_small = h->use_fast ? 1 : 0;
+        k_cell_outgoing<1, H><<<grid_for(items), WARPS_PER_CTA * 32, h->smem_out1, h->stream>>>(a);
+        if ((rc = check_launch(h, "k_cell_outgoing<1>"))) return rc;
+    }
     if (h->nbf > 0) {
         long long bitems = (long long)h->nbf * (h->Rs / 32);
         k_bnd_outgoing<H><<<grid_for(bitems), WARPS_PER_CTA * 32, h->smem_bnd, h->stream>>>(a);
@@ -226,16 +242,36 @@ static int launch_slab_kernels_phase2(dugks_handle* h, StepArgs a) {
         k_bnd_relax<H><<<grid_for(bitems), WARPS_PER_CTA * 32, 0, h->stream>>>(a);
         if ((rc = check_launch(h, "k_bnd_relax"))) return rc;
     }
-    {
+    if (h->use_fast && h->use_tma) {
         Timed t(h, 0);
+        k_cell_outgoing_tma<2, H><<<grid_for(items), WARPS_PER_CTA * 32, h->tsmem_out2, h->stream>>>(a, h->ci, h->max_ne_fast + 1);
+        if ((rc = check_launch(h, "k_cell_outgoing_tma<2>"))) return rc;
+    } else if (h->use_fast) {
+        Timed t(h, 0);
+        k_cell_outgoing_fast<2, H><<<grid_for(items), WARPS_PER_CTA * 32, h->fsmem_out2, h->stream>>>(a);
+        if ((rc = check_launch(h, "k_cell_outgoing_fast<2>"))) return rc;
+    }
+    if (!h->use_fast || h->n_big > 0) {
+        Timed t(h, 0);
+        a.skip_small = h->use_fast ? 1 : 0;
         k_cell_outgoing<2, H><<<grid_for(items), WARPS_PER_CTA * 32, h->smem_out2, h->stream>>>(a);
+        if ((rc = check_launch(h, "k_cell_outgoing<2>"))) return rc;
     }
-    if ((rc = check_launch(h, "k_cell_outgoing<2>"))) return rc;
-    {
+    if (h->use_fast && h->use_tma) {
         Timed t(h, 1);
-        k_cell_update<H><<<grid_for(items), WARPS_PER_CTA * 32, h->smem_upd, h->stream>>>(a);
+        k_cell_update_tma<H><<<grid_for(items), WARPS_PER_CTA * 32, h->tsmem_upd, h->stream>>>(a, h->ci, h->max_ne_fast + 2);
+        if ((rc = check_launch(h, "k_cell_update_tma"))) return rc;
+    } else if (h->use_fast) {
+        Timed t(h, 1);
+        k_cell_update_fast<H><<<grid_for(items), WARPS_PER_CTA * 32, h->fsmem_upd, h->stream>>>(a);
+        if ((rc = check_launch(h, "k_cell_update_fast"))) return rc;
     }
-    if ((rc = check_launch(h, "k_cell_update"))) return rc;
+    if (!h->use_fast || h->n_big > 0) {
+        Timed t(h, 1);
+        a.skip_small = h->use_fast ? 1 : 0;
+        k_cell_update<H><<<grid_for(items), WARPS_PER_CTA * 32, h->smem_upd, h->stream>>>(a);
+        if ((rc = check_launch(h, "k_cell_update"))) return rc;
+    }
     return 0;
 }
 
@@ -354,7 +390,7 @@ static int choose_chunks(int n, int D, long long base_rows_local) {
         long long rows = base_rows_local * nch;
         long long padded = (rows + 31) / 32 * 32;
         double waste = 1.0 - (double)(base_rows_local * n) / (double)(padded * L);
-        if (waste < best_waste - 0.02) { best_waste = waste; best = nch; }
+        if (waste < best_waste - 0.03) { best_waste = waste; best = nch; }   // prefer long rows unless padding drops by > 3%
     }
     return best;
 }
@@ -664,6 +700,24 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
     TRYB(dev_upload(h, &d_i, e_face)); M.e_face = d_i;
     TRYB(dev_upload(h, &d_i, e_owner)); M.e_owner = d_i;
     TRYB(dev_upload(h, &d_d, e_geo)); M.e_geo = d_d;
+    {
+        std::vector<double> g12((size_t)ne * GEO12, 0.0);
+        for (int e = 0; e < ne; e++) {
+            const double* g = &e_geo[(size_t)e * 9];
+            double* o = &g12[(size_t)e * GEO12];
+            o[0] = g[0]; o[1] = g[1]; o[2] = g[2]; o[3] = g[6];
+            o[4] = g[3]; o[5] = g[4]; o[6] = g[5]; o[7] = g[7];
+            o[8] = g[8]; o[9] = (e_other[e] < 0) ? b_invdc[-1 - e_other[e]] : 0.0;
+        }
+        TRYB(dev_upload(h, &d_d, g12)); M.e_geo12 = d_d;
+    }
+    for (int c = 0; c < nc; c++) {
+        if (cnt[c] > FAST_NE) h->n_big++;
+        else h->max_ne_fast = std::max(h->max_ne_fast, cnt[c]);
+    }
+    h->use_tma = getenv("DUGKS_NO_TMA") == nullptr;            // test hook: per-element LDG kernels instead
+    if (const char* e = getenv("DUGKS_CI")) h->ci = std::max(1, std::min(32, atoi(e)));
+    h->use_fast = getenv("DUGKS_FORCE_GENERIC") == nullptr;   // test hook: run every cell through the generic kernels
     TRYB(dev_upload(h, &d_d, std::vector<double>(mesh->V, mesh->V + nc))); M.V = d_d;
     TRYB(dev_upload(h, &d_i, b_owner)); M.b_owner = d_i;
     TRYB(dev_upload(h, &d_i, b_kind)); M.b_kind = d_i;
@@ -758,10 +812,40 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
     h->smem_out2 = h->smem_out1 + (size_t)WARPS_PER_CTA * ACC_FACES * 3 * h->tabw * 8;
     h->smem_bnd = (size_t)NT_MAX * 8 + (size_t)WARPS_PER_CTA * STAGE_BYTES;
     h->smem_upd = h->smem_out1;
+    h->fsmem_out1 = (size_t)NT_MAX * 6 * 8 + (size_t)WARPS_PER_CTA * FAST_STAGE_BYTES;
+    h->fsmem_out2 = h->fsmem_out1 + (size_t)WARPS_PER_CTA * ((size_t)ACC_FACES * 3 * h->tabw + ACC_FACES * 3 * 32 + ACC_FACES * 2) * 8;
+    h->fsmem_upd = h->fsmem_out1;
+    {
+        const int nfld2 = h->hasH ? 2 : 1;
+        auto tma_bytes = [&](int nstream, size_t extra_d) {
+            return (size_t)NT_MAX * 6 * 8 + (size_t)WARPS_PER_CTA * (TMA_META_BYTES + (TMA_STAGES * tma_stage_doubles(nstream * nfld2, h->ci) + extra_d) * 8);
+        };
+        const size_t extra2 = (size_t)ACC_FACES * 3 * h->tabw + ACC_FACES * 3 * 32 + ACC_FACES * 2;
+        h->tsmem_out1 = tma_bytes(h->max_ne_fast + 1, 0);
+        h->tsmem_out2 = tma_bytes(h->max_ne_fast + 1, extra2);
+        h->tsmem_upd = tma_bytes(h->max_ne_fast + 2, 0);
+        if (std::max(h->tsmem_out2, h->tsmem_upd) > 220 * 1024) h->use_tma = false;
+    }
+    if ((double)std::max(nc, nf) * L * h->Rs >= 2147483647.0) {
+        fail(h, DUGKS_ERR_UNSUPPORTED, "mesh too large for 32-bit slab offsets (%d faces x %d slab DVs)", nf, L * h->Rs);
+        return bail(DUGKS_ERR_UNSUPPORTED);
+    }
     if (h->hasH) {
         CUDAB(cudaFuncSetAttribute(k_cell_outgoing<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_out2));
+        CUDAB(cudaFuncSetAttribute(k_cell_outgoing_fast<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fsmem_out2));
+        if (h->use_tma) {
+            CUDAB(cudaFuncSetAttribute(k_cell_outgoing_tma<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tsmem_out1));
+            CUDAB(cudaFuncSetAttribute(k_cell_outgoing_tma<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tsmem_out2));
+            CUDAB(cudaFuncSetAttribute(k_cell_update_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tsmem_upd));
+        }
     } else {
+        if (h->use_tma) {
+            CUDAB(cudaFuncSetAttribute(k_cell_outgoing_tma<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tsmem_out1));
+            CUDAB(cudaFuncSetAttribute(k_cell_outgoing_tma<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tsmem_out2));
+            CUDAB(cudaFuncSetAttribute(k_cell_update_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tsmem_upd));
+        }
         CUDAB(cudaFuncSetAttribute(k_cell_outgoing<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_out2));
+        CUDAB(cudaFuncSetAttribute(k_cell_outgoing_fast<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fsmem_out2));
     }
 
     // ---- collective backend

@@ -44,6 +44,7 @@ struct DevMesh {
     const int* e_face;       // [ne]   face index f (internal) or nif+b
     const int* e_owner;      // [ne]   1 if the cell owns the face
     const double* e_geo;     // [ne][9] G(3) LS vector, r(3) = Cf - C_cell, Sf(3) owner-oriented
+    const double* e_geo12;   // [ne][12] same data as 16-byte pairs: G0 G1 | G2 Sx | r0 r1 | r2 Sy | Sz invdc | 0 0
     const double* V;         // [nc]
     const int* b_owner;      // [nbf]
     const int* b_kind;       // [nbf]

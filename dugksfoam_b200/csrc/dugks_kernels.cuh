@@ -26,6 +26,7 @@ struct StepArgs {
     DevGas gas;
     int slab;
     int nm;            // moments per slot: 13 or 17
+    int skip_small;    // generic cell kernels: skip cells the fast kernels (dugks_fast.cuh) handle
     double dt;
     double *gt, *ht, *gb, *hb;              // [nslab][nc][L][Rs]
     double *gsb, *hsb;                      // [nslab][nbf][L][Rs]
@@ -122,6 +123,65 @@ __device__ __forceinline__ void cell_gradient(const StepArgs& a, const CellStage
         const double* G = s.geo + j * 9;
         g[0] += G[0] * dg; g[1] += G[1] * dg; g[2] += G[2] * dg;
         if (HAS_H) { h[0] += G[0] * dh; h[1] += G[1] * dh; h[2] += G[2] * dh; }
+    }
+}
+
+// ---- fast path for cells with at most FAST_NE faces: all neighbour values of one (i, r) are
+// fetched into registers with independent loads (memory-level parallelism), one iteration ahead
+#define FAST_NE 8
+template <bool HAS_H>
+struct NbrVals {
+    double v0, w0;
+    double vn[FAST_NE], wn[FAST_NE];
+};
+
+template <bool HAS_H>
+__device__ __forceinline__ void nbr_load(const StepArgs& a, const CellStage& s, int ne, size_t cbase, size_t ir,
+                                         NbrVals<HAS_H>& o) {
+    o.v0 = a.gb[cbase + ir];
+    o.w0 = HAS_H ? a.hb[cbase + ir] : 0.0;
+#pragma unroll
+    for (int j = 0; j < FAST_NE; j++) {
+        o.vn[j] = 0.0;
+        o.wn[j] = 0.0;
+        if (j < ne) {
+            int kind = s.kind[j];
+            size_t off = (size_t)s.obase[j] + ir;
+            if (kind < 0) {
+                o.vn[j] = a.gb[off];
+                if (HAS_H) o.wn[j] = a.hb[off];
+            } else if (kind != K_SYMMETRY_PLANE) {
+                o.vn[j] = a.gam_old_g[off];
+                if (HAS_H) o.wn[j] = a.gam_old_h[off];
+            }
+        }
+    }
+}
+
+template <bool HAS_H>
+__device__ __forceinline__ void nbr_gradient(const CellStage& s, int ne, const NbrVals<HAS_H>& o, double g[3],
+                                             double h[3]) {
+    g[0] = g[1] = g[2] = 0.0;
+    h[0] = h[1] = h[2] = 0.0;
+#pragma unroll
+    for (int j = 0; j < FAST_NE; j++) {
+        if (j < ne) {
+            int kind = s.kind[j];
+            double dg, dh = 0.0;
+            if (kind < 0) {
+                dg = o.vn[j] - o.v0;
+                if (HAS_H) dh = o.wn[j] - o.w0;
+            } else if (kind == K_SYMMETRY_PLANE) {
+                dg = 0.0;
+            } else {
+                double idc = s.invdc[j];
+                dg = (o.v0 + o.vn[j] * idc) - o.v0;
+                if (HAS_H) dh = (o.w0 + o.wn[j] * idc) - o.w0;
+            }
+            const double* G = s.geo + j * 9;
+            g[0] += G[0] * dg; g[1] += G[1] * dg; g[2] += G[2] * dg;
+            if (HAS_H) { h[0] += G[0] * dh; h[1] += G[1] * dh; h[2] += G[2] * dh; }
+        }
     }
 }
 
@@ -244,6 +304,7 @@ k_cell_outgoing(StepArgs a) {
         int tmin, span;
         table_range(dv, cb, tmin, span);
         int ne = stage_cell(a, c, lane, st);
+        if (a.skip_small && ne <= FAST_NE) continue;   // warp-uniform
         int nint = a.m.cell_nint[c];
         size_t base = dv_index(dv, a.slab, a.m.nc, c, 0, r);
 
@@ -280,14 +341,9 @@ k_cell_outgoing(StepArgs a) {
             }
             if (PHASE == 2) __syncwarp();
 
-            for (int i = 0; i < dv.L; i++) {
-                size_t ir = (size_t)i * dv.Rs + r;
+            auto body = [&](int i, double v0, double w0, const double* gg, const double* gh) {
                 int t = cb + i;
                 double x = txs[t];
-                double v0 = a.gb[base + (size_t)i * dv.Rs];
-                double w0 = HAS_H ? a.hb[base + (size_t)i * dv.Rs] : 0.0;
-                double gg[3], gh[3];
-                cell_gradient<HAS_H>(a, st, ne, ir, v0, w0, gg, gh);
                 // reconstruction point: Cf - C - 0.5 xi dt  (discreteVelocity.C:498-502)
                 double hd = -0.5 * a.dt;
                 double xg = (x * gg[0] + y * gg[1] + z * gg[2]) * hd;
@@ -341,6 +397,33 @@ k_cell_outgoing(StepArgs a) {
                             }
                         }
                     }
+                }
+            };
+            const bool fast = ne <= FAST_NE;
+            const size_t cellbase = base - r;   // base offset of the cell's row block (without r)
+            if (fast) {
+                NbrVals<HAS_H> A, B;
+                nbr_load<HAS_H>(a, st, ne, cellbase, (size_t)r, A);
+                for (int i = 0; i < dv.L; i += 2) {
+                    double gg[3], gh[3];
+                    bool hasB = i + 1 < dv.L;
+                    if (hasB) nbr_load<HAS_H>(a, st, ne, cellbase, (size_t)(i + 1) * dv.Rs + r, B);
+                    nbr_gradient<HAS_H>(st, ne, A, gg, gh);
+                    body(i, A.v0, A.w0, gg, gh);
+                    if (i + 2 < dv.L) nbr_load<HAS_H>(a, st, ne, cellbase, (size_t)(i + 2) * dv.Rs + r, A);
+                    if (hasB) {
+                        nbr_gradient<HAS_H>(st, ne, B, gg, gh);
+                        body(i + 1, B.v0, B.w0, gg, gh);
+                    }
+                }
+            } else {
+                for (int i = 0; i < dv.L; i++) {
+                    size_t ir = (size_t)i * dv.Rs + r;
+                    double v0 = a.gb[base + (size_t)i * dv.Rs];
+                    double w0 = HAS_H ? a.hb[base + (size_t)i * dv.Rs] : 0.0;
+                    double gg[3], gh[3];
+                    cell_gradient<HAS_H>(a, st, ne, ir, v0, w0, gg, gh);
+                    body(i, v0, w0, gg, gh);
                 }
             }
 
@@ -735,44 +818,105 @@ k_cell_update(StepArgs a) {
         double y = dv.row_y[grow], z = dv.row_z[grow], wr = dv.row_w[grow];
         int cb = dv.row_cbase[grow];
         int ne = stage_cell(a, c, lane, st);
+        if (a.skip_small && ne <= FAST_NE) continue;   // warp-uniform
         // face value source: internal -> fbuf[face], boundary -> gsb (obase already points there)
         size_t base = dv_index(dv, a.slab, a.m.nc, c, 0, r);
         double dtv = a.dt / a.m.V[c];
         double A[4] = {0, 0, 0, 0}, B[2] = {0, 0};
-        for (int i = 0; i < dv.L; i++) {
+        const size_t slabsz = (size_t)dv.L * dv.Rs;
+        auto finish = [&](int i, double g0, double gb0, double h0, double hb0, double sumg, double sumh) {
             int t = cb + i;
-            double x = txs[t];
-            size_t ir = (size_t)i * dv.Rs + r;
             size_t idx = base + (size_t)i * dv.Rs;
-            double sumg = 0.0, sumh = 0.0;
-            for (int j = 0; j < ne; j++) {
-                const double* G = st.geo + j * 9;
-                double phi = dot_exact(x, y, z, G[6], G[7], G[8]);
-                double gf, hf = 0.0;
-                if (st.kind[j] < 0) {
-                    size_t fo = (size_t)st.face[j] * dv.L * dv.Rs + ir;
-                    gf = a.fbuf_g[fo];
-                    if (HAS_H) hf = a.fbuf_h[fo];
-                } else {
-                    size_t bo = (size_t)st.obase[j] + ir;
-                    gf = a.gsb[bo];
-                    if (HAS_H) hf = a.hsb[bo];
-                }
-                double sphi = st.own[j] ? phi : -phi;       // discreteVelocity.C:952-955
-                sumg = fma(sphi, gf, sumg);
-                if (HAS_H) sumh = fma(sphi, hf, sumh);
-            }
-            double gnew = (-1.0 / 3) * a.gt[idx] + (4.0 / 3) * a.gb[idx] - sumg * dtv;   // :937,952
+            double gnew = (-1.0 / 3) * g0 + (4.0 / 3) * gb0 - sumg * dtv;   // discreteVelocity.C:937,952
             a.gt[idx] = gnew;
             A[0] = fma(txs[NT_MAX + t], gnew, A[0]);
             A[1] = fma(txs[2 * NT_MAX + t], gnew, A[1]);
             A[2] = fma(txs[3 * NT_MAX + t], gnew, A[2]);
             A[3] = fma(txs[4 * NT_MAX + t], gnew, A[3]);
             if (HAS_H) {
-                double hnew = (-1.0 / 3) * a.ht[idx] + (4.0 / 3) * a.hb[idx] - sumh * dtv;
+                double hnew = (-1.0 / 3) * h0 + (4.0 / 3) * hb0 - sumh * dtv;
                 a.ht[idx] = hnew;
                 B[0] = fma(txs[NT_MAX + t], hnew, B[0]);
                 B[1] = fma(txs[2 * NT_MAX + t], hnew, B[1]);
+            }
+        };
+        if (ne <= FAST_NE) {
+            // per-thread y*Sy, z*Sz of every face (exact product, see dot_exact)
+            double ySy[FAST_NE], zSz[FAST_NE];
+#pragma unroll
+            for (int j = 0; j < FAST_NE; j++) {
+                ySy[j] = zSz[j] = 0.0;
+                if (j < ne) { ySy[j] = __dmul_rn(y, st.geo[j * 9 + 7]); zSz[j] = __dmul_rn(z, st.geo[j * 9 + 8]); }
+            }
+            struct Vals { double g0, gb0, h0, hb0, gf[FAST_NE], hf[FAST_NE]; };
+            auto load = [&](int i, Vals& o) {
+                size_t ir = (size_t)i * dv.Rs + r;
+                size_t idx = base + (size_t)i * dv.Rs;
+                o.g0 = a.gt[idx]; o.gb0 = a.gb[idx];
+                o.h0 = HAS_H ? a.ht[idx] : 0.0; o.hb0 = HAS_H ? a.hb[idx] : 0.0;
+#pragma unroll
+                for (int j = 0; j < FAST_NE; j++) {
+                    o.gf[j] = 0.0; o.hf[j] = 0.0;
+                    if (j < ne) {
+                        if (st.kind[j] < 0) {
+                            size_t fo = (size_t)st.face[j] * slabsz + ir;
+                            o.gf[j] = a.fbuf_g[fo];
+                            if (HAS_H) o.hf[j] = a.fbuf_h[fo];
+                        } else {
+                            size_t bo = (size_t)st.obase[j] + ir;
+                            o.gf[j] = a.gsb[bo];
+                            if (HAS_H) o.hf[j] = a.hsb[bo];
+                        }
+                    }
+                }
+            };
+            auto compute = [&](int i, const Vals& o) {
+                double x = txs[cb + i];
+                double sumg = 0.0, sumh = 0.0;
+#pragma unroll
+                for (int j = 0; j < FAST_NE; j++) {
+                    if (j < ne) {
+                        double phi = __dadd_rn(__dadd_rn(__dmul_rn(x, st.geo[j * 9 + 6]), ySy[j]), zSz[j]);
+                        double sphi = st.own[j] ? phi : -phi;       // discreteVelocity.C:952-955
+                        sumg = fma(sphi, o.gf[j], sumg);
+                        if (HAS_H) sumh = fma(sphi, o.hf[j], sumh);
+                    }
+                }
+                finish(i, o.g0, o.gb0, o.h0, o.hb0, sumg, sumh);
+            };
+            Vals P, Q;
+            load(0, P);
+            for (int i = 0; i < dv.L; i += 2) {
+                bool hasQ = i + 1 < dv.L;
+                if (hasQ) load(i + 1, Q);
+                compute(i, P);
+                if (i + 2 < dv.L) load(i + 2, P);
+                if (hasQ) compute(i + 1, Q);
+            }
+        } else {
+            for (int i = 0; i < dv.L; i++) {
+                double x = txs[cb + i];
+                size_t ir = (size_t)i * dv.Rs + r;
+                size_t idx = base + (size_t)i * dv.Rs;
+                double sumg = 0.0, sumh = 0.0;
+                for (int j = 0; j < ne; j++) {
+                    const double* G = st.geo + j * 9;
+                    double phi = dot_exact(x, y, z, G[6], G[7], G[8]);
+                    double gf, hf = 0.0;
+                    if (st.kind[j] < 0) {
+                        size_t fo = (size_t)st.face[j] * slabsz + ir;
+                        gf = a.fbuf_g[fo];
+                        if (HAS_H) hf = a.fbuf_h[fo];
+                    } else {
+                        size_t bo = (size_t)st.obase[j] + ir;
+                        gf = a.gsb[bo];
+                        if (HAS_H) hf = a.hsb[bo];
+                    }
+                    double sphi = st.own[j] ? phi : -phi;
+                    sumg = fma(sphi, gf, sumg);
+                    if (HAS_H) sumh = fma(sphi, hf, sumh);
+                }
+                finish(i, a.gt[idx], a.gb[idx], HAS_H ? a.ht[idx] : 0.0, HAS_H ? a.hb[idx] : 0.0, sumg, sumh);
             }
         }
         double v[16];
