@@ -212,7 +212,7 @@ static int launch_slab_kernels_phase1(dugks_handle* h, StepArgs a) {
     if ((rc = check_launch(h, "k_cell_halfstep"))) return rc;
     if (h->use_fast && h->use_tma) {
         Timed t(h, 0);
-        k_cell_outgoing_tma<1, H><<<grid_for(items), WARPS_PER_CTA * 32, h->tsmem_out1, h->stream>>>(a, h->ci, h->max_ne_fast + 1);
+        k_cell_outgoing_tma<1, H, TMA_CI><<<grid_for(items), WARPS_PER_CTA * 32, h->tsmem_out1, h->stream>>>(a, h->max_ne_fast + 1);
         if ((rc = check_launch(h, "k_cell_outgoing_tma<1>"))) return rc;
     } else if (h->use_fast) {
         Timed t(h, 0);
@@ -244,7 +244,7 @@ static int launch_slab_kernels_phase2(dugks_handle* h, StepArgs a) {
     }
     if (h->use_fast && h->use_tma) {
         Timed t(h, 0);
-        k_cell_outgoing_tma<2, H><<<grid_for(items), WARPS_PER_CTA * 32, h->tsmem_out2, h->stream>>>(a, h->ci, h->max_ne_fast + 1);
+        k_cell_outgoing_tma<2, H, TMA_CI><<<grid_for(items), WARPS_PER_CTA * 32, h->tsmem_out2, h->stream>>>(a, h->max_ne_fast + 1);
         if ((rc = check_launch(h, "k_cell_outgoing_tma<2>"))) return rc;
     } else if (h->use_fast) {
         Timed t(h, 0);
@@ -716,7 +716,7 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
         else h->max_ne_fast = std::max(h->max_ne_fast, cnt[c]);
     }
     h->use_tma = getenv("DUGKS_NO_TMA") == nullptr;            // test hook: per-element LDG kernels instead
-    if (const char* e = getenv("DUGKS_CI")) h->ci = std::max(1, std::min(32, atoi(e)));
+    h->ci = TMA_CI;
     h->use_fast = getenv("DUGKS_FORCE_GENERIC") == nullptr;   // test hook: run every cell through the generic kernels
     TRYB(dev_upload(h, &d_d, std::vector<double>(mesh->V, mesh->V + nc))); M.V = d_d;
     TRYB(dev_upload(h, &d_i, b_owner)); M.b_owner = d_i;
@@ -834,14 +834,14 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
         CUDAB(cudaFuncSetAttribute(k_cell_outgoing<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_out2));
         CUDAB(cudaFuncSetAttribute(k_cell_outgoing_fast<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fsmem_out2));
         if (h->use_tma) {
-            CUDAB(cudaFuncSetAttribute(k_cell_outgoing_tma<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tsmem_out1));
-            CUDAB(cudaFuncSetAttribute(k_cell_outgoing_tma<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tsmem_out2));
+            CUDAB(cudaFuncSetAttribute(k_cell_outgoing_tma<1, true, TMA_CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tsmem_out1));
+            CUDAB(cudaFuncSetAttribute(k_cell_outgoing_tma<2, true, TMA_CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tsmem_out2));
             CUDAB(cudaFuncSetAttribute(k_cell_update_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tsmem_upd));
         }
     } else {
         if (h->use_tma) {
-            CUDAB(cudaFuncSetAttribute(k_cell_outgoing_tma<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tsmem_out1));
-            CUDAB(cudaFuncSetAttribute(k_cell_outgoing_tma<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tsmem_out2));
+            CUDAB(cudaFuncSetAttribute(k_cell_outgoing_tma<1, false, TMA_CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tsmem_out1));
+            CUDAB(cudaFuncSetAttribute(k_cell_outgoing_tma<2, false, TMA_CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tsmem_out2));
             CUDAB(cudaFuncSetAttribute(k_cell_update_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tsmem_upd));
         }
         CUDAB(cudaFuncSetAttribute(k_cell_outgoing<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_out2));

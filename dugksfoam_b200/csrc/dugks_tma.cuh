@@ -15,6 +15,7 @@
 #include "dugks_fast.cuh"
 
 #define TMA_STAGES 2
+#define TMA_CI 4        // velocity points per bulk copy (1 KB per stream)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -50,10 +51,257 @@ __host__ __device__ inline size_t tma_stage_doubles(int nstream, int ci) { retur
 static_assert(FAST_STAGE_BYTES <= TMA_BAR_OFFSET, "FastStage overlaps the mbarriers");
 
 // ---------------------------------------------------------------------------------
-// PHASE 1: gradient + upwind reconstruction + face moments;  PHASE 2: + relaxation, face flux store
-template <int PHASE, bool HAS_H>
+// warp reduction of 16 values per lane through shared memory (row stride 17 doubles):
+// every lane returns the warp total of value index (lane & 15).  ~50 instructions.
+__device__ __forceinline__ double warp_reduce16_smem(const double v[16], double* red, int lane) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) red[lane * 17 + k] = v[k];
+    __syncwarp();
+    const int col = lane & 15, half = lane >> 4;
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int rr = 0; rr < 16; rr += 2) {
+        s0 += red[(half * 16 + rr) * 17 + col];
+        s1 += red[(half * 16 + rr + 1) * 17 + col];
+    }
+    double s = s0 + s1;
+    s += __shfl_xor_sync(0xffffffffu, s, 16);
+    __syncwarp();
+    return s;
+}
+
+// Work of one warp on one cell for the bulk-staged outgoing kernel.
+// NE_T >= 0: all faces internal and ne == nint == NE_T (interior cell, fully unrolled,
+// no run-time face predicates); NE_T < 0: run-time ne / nint (boundary cells).
+template <int PHASE, bool HAS_H, int CI, int NE_T>
+struct OutgoingCell {
+    template <class Issue>
+    static __device__ __forceinline__ void run(const StepArgs& a, const FastStage& st, const double* txs,
+                                               double* stages, size_t stage_d, int nstream, uint64_t* bars,
+                                               uint32_t& phase, double* ftab, double* lanec, double* unic,
+                                               int ne_rt, int nint_rt, unsigned ownmask, unsigned symmask,
+                                               int c, int r, int lane, Issue&& issue) {
+        const DevDV& dv = a.dv;
+        const int L = dv.L, Rs = dv.Rs, tw = dv.tabw, nm = a.nm;
+        const int ne = NE_T >= 0 ? NE_T : ne_rt;
+        const int nint = NE_T >= 0 ? NE_T : nint_rt;
+        const double kd = (double)(a.gas.K + 3 - a.gas.D);
+        const double hstep = 0.5 * a.dt, hd = -0.5 * a.dt;
+        const int grow = a.slab * Rs + r;
+        const double y = dv.row_y[grow], z = dv.row_z[grow], wr = dv.row_w[grow];
+        const int cb = dv.row_cbase[grow];
+        int tmin = 0, span = 0;
+        if (PHASE == 2) table_range(dv, cb, tmin, span);
+        const int nchunk = (L + CI - 1) / CI;
+        // exact upwind thresholds on the OUTWARD flux phi' = +-(xi.Sf) of this cell
+        // (discreteVelocity.C:495,506: owner side full if phi >= VSMALL, neighbour side full if phi < -VSMALL)
+        const double V0 = DUGKS_VSMALL;
+        const double Vp = __longlong_as_double(__double_as_longlong(V0) + 1);   // next above VSMALL
+        const double Vm = __longlong_as_double(__double_as_longlong(V0) - 1);   // next below VSMALL
+
+        for (int p0 = 0; p0 < nint; p0 += ACC_FACES) {
+            issue(0, 0);
+            double ySy[ACC_FACES], zSz[ACC_FACES], Sx[ACC_FACES], tF[ACC_FACES], tN[ACC_FACES];
+            double accg[ACC_FACES][4], acch[ACC_FACES][2];
+#pragma unroll
+            for (int jj = 0; jj < ACC_FACES; jj++) {
+                const int j = p0 + jj;
+                ySy[jj] = zSz[jj] = Sx[jj] = tF[jj] = tN[jj] = 0.0;
+                accg[jj][0] = accg[jj][1] = accg[jj][2] = accg[jj][3] = 0.0;
+                acch[jj][0] = acch[jj][1] = 0.0;
+                if (j < nint) {
+                    const double* G = st.geo + j * GEO12;
+                    const bool isown = (ownmask >> j) & 1u;
+                    const double sgn = isown ? 1.0 : -1.0;
+                    Sx[jj] = sgn * G[3];
+                    ySy[jj] = __dmul_rn(y, sgn * G[7]);
+                    zSz[jj] = __dmul_rn(z, sgn * G[8]);
+                    tF[jj] = isown ? V0 : Vp;      // full  <=> phi' >= tF
+                    tN[jj] = isown ? -V0 : -Vm;    // none  <=> phi' <  tN
+                    if (PHASE == 2) {
+                        const double* mf = a.fmac + (size_t)st.face[j] * MAC_N;
+                        double rf = hstep / (2.0 * mf[5] + hstep);            // discreteVelocity.C:867
+                        EqCoef e = make_eq(a.gas, mf, rf);
+                        for (int tt = lane; tt < span; tt += 32) {
+                            double cx = txs[(tmin + tt) * 6] - e.Ux;
+                            double x2 = cx * cx * e.a;
+                            ftab[(jj * 3 + 0) * tw + tt] = exp(-0.5 * x2);
+                            ftab[(jj * 3 + 1) * tw + tt] = x2;
+                            ftab[(jj * 3 + 2) * tw + tt] = cx * e.qx;
+                        }
+                        double cy = y - e.Uy, cz = z - e.Uz;
+                        double yz2 = (cy * cy + cz * cz) * e.a;
+                        lanec[(jj * 3 + 0) * 32 + lane] = e.pre * exp(-0.5 * yz2);
+                        lanec[(jj * 3 + 1) * 32 + lane] = yz2 - a.gas.D - 2.0;
+                        lanec[(jj * 3 + 2) * 32 + lane] = cy * e.qy + cz * e.qz;
+                        if (lane == 0) { unic[jj * 2] = 1.0 - rf; unic[jj * 2 + 1] = e.RT; }
+                    }
+                }
+            }
+            if (PHASE == 2) __syncwarp();
+
+            for (int ch = 0; ch < nchunk; ch++) {
+                const int s = ch & 1;
+                if (ch + 1 < nchunk) issue(ch + 1, s ^ 1);
+                mbar_wait(&bars[s], (phase >> s) & 1u);
+                phase ^= (1u << s);
+                const double* sg = stages + s * stage_d;            // [stream][CI][32]
+                const double* sh = sg + (size_t)nstream * CI * 32;
+                const int ilen = min(CI, L - ch * CI);
+#pragma unroll
+                for (int ii = 0; ii < CI; ii += 2) {
+                    if (ii >= ilen) break;                          // warp-uniform
+                    const bool two = ii + 1 < ilen;
+                    const int i0 = ch * CI + ii;
+                    const int iu1 = two ? ii + 1 : ii;
+                    double vc[2], wc[2];
+                    double gg[2][3] = {{0, 0, 0}, {0, 0, 0}}, gh[2][3] = {{0, 0, 0}, {0, 0, 0}};
+                    vc[0] = sg[ii * 32 + lane]; vc[1] = sg[iu1 * 32 + lane];
+                    wc[0] = HAS_H ? sh[ii * 32 + lane] : 0.0; wc[1] = HAS_H ? sh[iu1 * 32 + lane] : 0.0;
+                    // ---- least-squares gradient (see cell_gradient in dugks_kernels.cuh)
+#pragma unroll
+                    for (int j = 0; j < FAST_NE; j++) {
+                        if (j < nint) {                              // internal face: neighbour cell value
+                            const double2 G01 = lds2(st.geo + j * GEO12), G2s = lds2(st.geo + j * GEO12 + 2);
+#pragma unroll
+                            for (int u = 0; u < 2; u++) {
+                                const int iu = u ? iu1 : ii;
+                                const double dg = sg[((1 + j) * CI + iu) * 32 + lane] - vc[u];
+                                gg[u][0] = fma(G01.x, dg, gg[u][0]); gg[u][1] = fma(G01.y, dg, gg[u][1]);
+                                gg[u][2] = fma(G2s.x, dg, gg[u][2]);
+                                if (HAS_H) {
+                                    const double dh = sh[((1 + j) * CI + iu) * 32 + lane] - wc[u];
+                                    gh[u][0] = fma(G01.x, dh, gh[u][0]); gh[u][1] = fma(G01.y, dh, gh[u][1]);
+                                    gh[u][2] = fma(G2s.x, dh, gh[u][2]);
+                                }
+                            }
+                        } else if (NE_T < 0 && j < ne) {             // boundary face: lagged normal gradient
+                            if ((symmask >> j) & 1u) continue;
+                            const double2 G01 = lds2(st.geo + j * GEO12), G2s = lds2(st.geo + j * GEO12 + 2);
+                            const double idc = st.geo[j * GEO12 + 9];
+#pragma unroll
+                            for (int u = 0; u < 2; u++) {
+                                const int iu = u ? iu1 : ii;
+                                const double dg = (vc[u] + sg[((1 + j) * CI + iu) * 32 + lane] * idc) - vc[u];
+                                gg[u][0] = fma(G01.x, dg, gg[u][0]); gg[u][1] = fma(G01.y, dg, gg[u][1]);
+                                gg[u][2] = fma(G2s.x, dg, gg[u][2]);
+                                if (HAS_H) {
+                                    const double dh = (wc[u] + sh[((1 + j) * CI + iu) * 32 + lane] * idc) - wc[u];
+                                    gh[u][0] = fma(G01.x, dh, gh[u][0]); gh[u][1] = fma(G01.y, dh, gh[u][1]);
+                                    gh[u][2] = fma(G2s.x, dh, gh[u][2]);
+                                }
+                            }
+                        }
+                    }
+                    // ---- per-point constants
+                    double x[2], W[2][4], xg[2], xh[2];
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        const int t = cb + i0 + ((u == 1 && two) ? 1 : 0);
+                        const double2 t0 = lds2(txs + t * 6), t1 = lds2(txs + t * 6 + 2), t2 = lds2(txs + t * 6 + 4);
+                        x[u] = t0.x; W[u][0] = t0.y; W[u][1] = t1.x; W[u][2] = t1.y; W[u][3] = t2.x;
+                        xg[u] = (x[u] * gg[u][0] + y * gg[u][1] + z * gg[u][2]) * hd;   // discreteVelocity.C:498-502
+                        xh[u] = HAS_H ? (x[u] * gh[u][0] + y * gh[u][1] + z * gh[u][2]) * hd : 0.0;
+                    }
+                    // ---- faces
+#pragma unroll
+                    for (int jj = 0; jj < ACC_FACES; jj++) {
+                        const int j = p0 + jj;
+                        if (j < nint) {
+                            const double* G = st.geo + j * GEO12;
+                            double phi[2];
+                            phi[0] = __dadd_rn(__dadd_rn(__dmul_rn(x[0], Sx[jj]), ySy[jj]), zSz[jj]);
+                            phi[1] = __dadd_rn(__dadd_rn(__dmul_rn(x[1], Sx[jj]), ySy[jj]), zSz[jj]);
+                            if (PHASE == 1) {
+                                const bool act0 = !(phi[0] < tN[jj]);             // this side contributes (full or tie)
+                                const bool act1 = two && !(phi[1] < tN[jj]);
+                                if (!__any_sync(0xffffffffu, act0 || act1)) continue;
+                                const double2 r01 = lds2(G + 4);
+                                const double r2 = G[6];
+#pragma unroll
+                                for (int u = 0; u < 2; u++) {
+                                    if (u ? act1 : act0) {
+                                        double val = vc[u] + (gg[u][0] * r01.x + gg[u][1] * r01.y + gg[u][2] * r2) + xg[u];
+                                        if (!(phi[u] >= tF[jj])) val *= 0.5;                         // tie :513-529
+                                        accg[jj][0] = fma(W[u][0], val, accg[jj][0]);
+                                        accg[jj][1] = fma(W[u][1], val, accg[jj][1]);
+                                        accg[jj][2] = fma(W[u][2], val, accg[jj][2]);
+                                        accg[jj][3] = fma(W[u][3], val, accg[jj][3]);
+                                        if (HAS_H) {
+                                            double vh = wc[u] + (gh[u][0] * r01.x + gh[u][1] * r01.y + gh[u][2] * r2) + xh[u];
+                                            if (!(phi[u] >= tF[jj])) vh *= 0.5;
+                                            acch[jj][0] = fma(W[u][0], vh, acch[jj][0]);
+                                            acch[jj][1] = fma(W[u][1], vh, acch[jj][1]);
+                                        }
+                                    }
+                                }
+                            } else {
+                                // exactly one side writes the face value: the owner unless phi < -VSMALL
+                                // (then the neighbour, for which that is the "full" test)
+                                const double tW = ((ownmask >> j) & 1u) ? tN[jj] : tF[jj];
+                                const bool wr0 = phi[0] >= tW;
+                                const bool wr1 = two && (phi[1] >= tW);
+                                if (!__any_sync(0xffffffffu, wr0 || wr1)) continue;
+                                const double2 r01 = lds2(G + 4);
+                                const double r2 = G[6];
+                                const double EYZ = lanec[(jj * 3 + 0) * 32 + lane], YZ2 = lanec[(jj * 3 + 1) * 32 + lane],
+                                             QYZ = lanec[(jj * 3 + 2) * 32 + lane];
+                                const double omrf = unic[jj * 2], frt = unic[jj * 2 + 1];
+                                const size_t fbase = (size_t)st.face[j] * L * Rs + r;
+#pragma unroll
+                                for (int u = 0; u < 2; u++) {
+                                    if (u ? wr1 : wr0) {
+                                        const int tt = cb + i0 + u - tmin;
+                                        double val = vc[u] + (gg[u][0] * r01.x + gg[u][1] * r01.y + gg[u][2] * r2) + xg[u];
+                                        double cc = ftab[(jj * 3 + 1) * tw + tt] + YZ2;
+                                        double cq = ftab[(jj * 3 + 2) * tw + tt] + QYZ;
+                                        double gM = ftab[(jj * 3 + 0) * tw + tt] * EYZ;
+                                        double gS = fma(cq, cc, 1.0) * gM;
+                                        const size_t fo = fbase + (size_t)(i0 + u) * Rs;
+                                        a.fbuf_g[fo] = fma(omrf, val, gS);                       // :880
+                                        if (HAS_H) {
+                                            double vh = wc[u] + (gh[u][0] * r01.x + gh[u][1] * r01.y + gh[u][2] * r2) + xh[u];
+                                            double hS = (kd + cq * ((cc + 2.0) * kd - 2.0 * a.gas.K)) * gM * frt;
+                                            a.fbuf_h[fo] = fma(omrf, vh, hS);                    // :881
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+                __syncwarp();   // all lanes are done with stage s before it is refilled
+            }
+
+            if (PHASE == 1) {
+                double* red = stages;   // both stages are idle here
+#pragma unroll
+                for (int jj = 0; jj < ACC_FACES; jj++) {
+                    const int j = p0 + jj;
+                    if (j < nint) {   // warp-uniform
+                        double v[16];
+                        expand_g(accg[jj], wr, y, z, v);
+                        double uu[NM_H] = {0, 0, 0, 0};
+                        if (HAS_H) expand_h(acch[jj], wr, y, z, uu);
+                        v[13] = uu[0]; v[14] = uu[1]; v[15] = uu[2];
+                        const double tot = warp_reduce16_smem(v, red, lane);
+                        const size_t slot = (size_t)2 * st.face[j] + (((ownmask >> j) & 1u) ? 0 : 1);
+                        if (lane < 16 && lane < nm) a.fslot[slot * nm + lane] += tot;
+                        if (HAS_H) {
+                            const double t3 = warp_sum(uu[3]);
+                            if (lane == 0) a.fslot[slot * nm + 16] += t3;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+};
+
+template <int PHASE, bool HAS_H, int CI>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2)
-k_cell_outgoing_tma(StepArgs a, int CI, int nstream /* streams per field incl. own */) {
+k_cell_outgoing_tma(StepArgs a, int nstream /* streams per field incl. own */) {
     extern __shared__ __align__(128) unsigned char dyn[];
     // layout: txs[NT_MAX][6] | per warp: meta(1 KB) | stages | (PHASE 2) ftab, lanec, unic
     double* txs = reinterpret_cast<double*>(dyn);
@@ -88,16 +336,11 @@ k_cell_outgoing_tma(StepArgs a, int CI, int nstream /* streams per field incl. o
     const int L = dv.L, Rs = dv.Rs;
     const int nwr = Rs >> 5;
     const long long nitems = (long long)a.m.nc * nwr;
-    const double kd = (double)(a.gas.K + 3 - a.gas.D);
-    const double hstep = 0.5 * a.dt;
-    const double hd = -0.5 * a.dt;
-    const int nm = a.nm;
     const size_t slab_c = (size_t)a.slab * a.m.nc * L * Rs, slab_b = (size_t)a.slab * a.m.nbf * L * Rs;
     const double* gbs = a.gb + slab_c;
     const double* hbs = HAS_H ? a.hb + slab_c : nullptr;
     const double* gam_g = a.gam_old_g + slab_b;
     const double* gam_h = HAS_H ? a.gam_old_h + slab_b : nullptr;
-    const int nchunk = (L + CI - 1) / CI;
 
     for (long long item = (long long)blockIdx.x * WARPS_PER_CTA + wib; item < nitems;
          item += (long long)gridDim.x * WARPS_PER_CTA) {
@@ -109,6 +352,7 @@ k_cell_outgoing_tma(StepArgs a, int CI, int nstream /* streams per field incl. o
         if (nint == 0) continue;
         __syncwarp();
         // ---- stream sources (per lane): lane 0 = own row block, lane 1+j = face j; lanes 16.. = h
+        // (a row block is contiguous because a slab is one warp of rows, Rs == 32)
         const int sl = lane & 15;                 // stream slot
         const bool hl = lane >= 16;               // this lane copies an h stream
         const double* src = nullptr;
@@ -132,205 +376,13 @@ k_cell_outgoing_tma(StepArgs a, int CI, int nstream /* streams per field incl. o
                 bulk_g2s(dst, src + (size_t)ch * CI * Rs, bytes, &bars[s]);
             }
         };
-        // NOTE: a row block is contiguous only when the slab is one warp of rows (Rs == 32)
-
-        const int grow = a.slab * Rs + r;
-        const double y = dv.row_y[grow], z = dv.row_z[grow], wr = dv.row_w[grow];
-        const int cb = dv.row_cbase[grow];
-        int tmin, span;
-        table_range(dv, cb, tmin, span);
-
-        for (int p0 = 0; p0 < nint; p0 += ACC_FACES) {
-            issue(0, 0);
-            double ySy[ACC_FACES], zSz[ACC_FACES];
-            double accg[ACC_FACES][4], acch[ACC_FACES][2];
-#pragma unroll
-            for (int jj = 0; jj < ACC_FACES; jj++) {
-                const int j = p0 + jj;
-                ySy[jj] = zSz[jj] = 0.0;
-                accg[jj][0] = accg[jj][1] = accg[jj][2] = accg[jj][3] = 0.0;
-                acch[jj][0] = acch[jj][1] = 0.0;
-                if (j < nint) {
-                    const double* G = st.geo + j * GEO12;
-                    ySy[jj] = __dmul_rn(y, G[7]);
-                    zSz[jj] = __dmul_rn(z, G[8]);
-                    if (PHASE == 2) {
-                        const double* mf = a.fmac + (size_t)st.face[j] * MAC_N;
-                        double rf = hstep / (2.0 * mf[5] + hstep);            // discreteVelocity.C:867
-                        EqCoef e = make_eq(a.gas, mf, rf);
-                        for (int tt = lane; tt < span; tt += 32) {
-                            double cx = txs[(tmin + tt) * 6] - e.Ux;
-                            double x2 = cx * cx * e.a;
-                            ftab[(jj * 3 + 0) * tw + tt] = exp(-0.5 * x2);
-                            ftab[(jj * 3 + 1) * tw + tt] = x2;
-                            ftab[(jj * 3 + 2) * tw + tt] = cx * e.qx;
-                        }
-                        double cy = y - e.Uy, cz = z - e.Uz;
-                        double yz2 = (cy * cy + cz * cz) * e.a;
-                        lanec[(jj * 3 + 0) * 32 + lane] = e.pre * exp(-0.5 * yz2);
-                        lanec[(jj * 3 + 1) * 32 + lane] = yz2 - a.gas.D - 2.0;
-                        lanec[(jj * 3 + 2) * 32 + lane] = cy * e.qy + cz * e.qz;
-                        if (lane == 0) { unic[jj * 2] = 1.0 - rf; unic[jj * 2 + 1] = e.RT; }
-                    }
-                }
-            }
-            if (PHASE == 2) __syncwarp();
-
-            for (int ch = 0; ch < nchunk; ch++) {
-                const int s = ch & 1;
-                if (ch + 1 < nchunk) issue(ch + 1, s ^ 1);
-                mbar_wait(&bars[s], (phase >> s) & 1u);
-                phase ^= (1u << s);
-                const double* sg = stages + s * stage_d;            // [stream][CI][32]
-                const double* sh = sg + (size_t)nstream * CI * 32;
-                const int ilen = min(CI, L - ch * CI);
-                for (int ii = 0; ii < ilen; ii += 2) {
-                    const bool two = ii + 1 < ilen;                 // warp-uniform
-                    const int i0 = ch * CI + ii;
-                    double vc[2], wc[2];
-                    double gg[2][3] = {{0, 0, 0}, {0, 0, 0}}, gh[2][3] = {{0, 0, 0}, {0, 0, 0}};
-#pragma unroll
-                    for (int u = 0; u < 2; u++) {
-                        const int iu = ii + ((u == 1 && !two) ? 0 : u);
-                        vc[u] = sg[iu * 32 + lane];
-                        wc[u] = HAS_H ? sh[iu * 32 + lane] : 0.0;
-                    }
-                    // ---- least-squares gradient (see cell_gradient in dugks_kernels.cuh)
-#pragma unroll
-                    for (int j = 0; j < FAST_NE; j++) {
-                        if (j < ne) {
-                            const bool isint = (intmask >> j) & 1u, issym = (symmask >> j) & 1u;
-                            if (issym) continue;
-                            const double2 G01 = lds2(st.geo + j * GEO12), G2s = lds2(st.geo + j * GEO12 + 2);
-                            const double idc = isint ? 0.0 : st.geo[j * GEO12 + 9];
-#pragma unroll
-                            for (int u = 0; u < 2; u++) {
-                                const int iu = ii + ((u == 1 && !two) ? 0 : u);
-                                const double vn = sg[((1 + j) * CI + iu) * 32 + lane];
-                                double dg, dh = 0.0;
-                                if (isint) dg = vn - vc[u];
-                                else dg = (vc[u] + vn * idc) - vc[u];
-                                gg[u][0] = fma(G01.x, dg, gg[u][0]); gg[u][1] = fma(G01.y, dg, gg[u][1]);
-                                gg[u][2] = fma(G2s.x, dg, gg[u][2]);
-                                if (HAS_H) {
-                                    const double wn = sh[((1 + j) * CI + iu) * 32 + lane];
-                                    if (isint) dh = wn - wc[u];
-                                    else dh = (wc[u] + wn * idc) - wc[u];
-                                    gh[u][0] = fma(G01.x, dh, gh[u][0]); gh[u][1] = fma(G01.y, dh, gh[u][1]);
-                                    gh[u][2] = fma(G2s.x, dh, gh[u][2]);
-                                }
-                            }
-                        }
-                    }
-                    // ---- per-point constants
-                    double x[2], W[2][4], xg[2], xh[2];
-#pragma unroll
-                    for (int u = 0; u < 2; u++) {
-                        const int t = cb + i0 + ((u == 1 && !two) ? 0 : u);
-                        const double2 t0 = lds2(txs + t * 6), t1 = lds2(txs + t * 6 + 2), t2 = lds2(txs + t * 6 + 4);
-                        x[u] = t0.x; W[u][0] = t0.y; W[u][1] = t1.x; W[u][2] = t1.y; W[u][3] = t2.x;
-                        if (u == 1 && !two) { W[u][0] = W[u][1] = W[u][2] = W[u][3] = 0.0; }
-                        xg[u] = (x[u] * gg[u][0] + y * gg[u][1] + z * gg[u][2]) * hd;   // discreteVelocity.C:498-502
-                        xh[u] = HAS_H ? (x[u] * gh[u][0] + y * gh[u][1] + z * gh[u][2]) * hd : 0.0;
-                    }
-                    // ---- faces
-#pragma unroll
-                    for (int jj = 0; jj < ACC_FACES; jj++) {
-                        const int j = p0 + jj;
-                        if (j < nint) {
-                            const double* G = st.geo + j * GEO12;
-                            const double Sx = G[3];
-                            const bool isown = (ownmask >> j) & 1u;
-                            bool full[2], none[2], neg[2];
-#pragma unroll
-                            for (int u = 0; u < 2; u++) {
-                                const double phi = __dadd_rn(__dadd_rn(__dmul_rn(x[u], Sx), ySy[jj]), zSz[jj]);
-                                neg[u] = phi < -DUGKS_VSMALL;                    // discreteVelocity.C:506
-                                const bool pos = phi >= DUGKS_VSMALL;            // :495
-                                full[u] = isown ? pos : neg[u];
-                                none[u] = isown ? neg[u] : pos;
-                            }
-                            if (PHASE == 1) {
-                                if (__all_sync(0xffffffffu, none[0] && none[1])) continue;
-                                const double2 r01 = lds2(G + 4);
-                                const double r2 = G[6];
-#pragma unroll
-                                for (int u = 0; u < 2; u++) {
-                                    double val = vc[u] + (gg[u][0] * r01.x + gg[u][1] * r01.y + gg[u][2] * r2) + xg[u];
-                                    val = none[u] ? 0.0 : (full[u] ? val : 0.5 * val);          // :513-529
-                                    accg[jj][0] = fma(W[u][0], val, accg[jj][0]);
-                                    accg[jj][1] = fma(W[u][1], val, accg[jj][1]);
-                                    accg[jj][2] = fma(W[u][2], val, accg[jj][2]);
-                                    accg[jj][3] = fma(W[u][3], val, accg[jj][3]);
-                                    if (HAS_H) {
-                                        double vh = wc[u] + (gh[u][0] * r01.x + gh[u][1] * r01.y + gh[u][2] * r2) + xh[u];
-                                        vh = none[u] ? 0.0 : (full[u] ? vh : 0.5 * vh);
-                                        acch[jj][0] = fma(W[u][0], vh, acch[jj][0]);
-                                        acch[jj][1] = fma(W[u][1], vh, acch[jj][1]);
-                                    }
-                                }
-                            } else {
-                                // exactly one side writes the face value (ties: the owner)
-                                bool wr_[2];
-                                wr_[0] = isown ? !neg[0] : neg[0];
-                                wr_[1] = two && (isown ? !neg[1] : neg[1]);
-                                if (!__any_sync(0xffffffffu, wr_[0] || wr_[1])) continue;
-                                const double2 r01 = lds2(G + 4);
-                                const double r2 = G[6];
-                                const double EYZ = lanec[(jj * 3 + 0) * 32 + lane], YZ2 = lanec[(jj * 3 + 1) * 32 + lane],
-                                             QYZ = lanec[(jj * 3 + 2) * 32 + lane];
-                                const double omrf = unic[jj * 2], frt = unic[jj * 2 + 1];
-                                const size_t fbase = (size_t)st.face[j] * L * Rs + r;
-#pragma unroll
-                                for (int u = 0; u < 2; u++) {
-                                    if (wr_[u]) {
-                                        const int tt = cb + i0 + u - tmin;
-                                        double val = vc[u] + (gg[u][0] * r01.x + gg[u][1] * r01.y + gg[u][2] * r2) + xg[u];
-                                        double cc = ftab[(jj * 3 + 1) * tw + tt] + YZ2;
-                                        double cq = ftab[(jj * 3 + 2) * tw + tt] + QYZ;
-                                        double gM = ftab[(jj * 3 + 0) * tw + tt] * EYZ;
-                                        double gS = fma(cq, cc, 1.0) * gM;
-                                        const size_t fo = fbase + (size_t)(i0 + u) * Rs;
-                                        a.fbuf_g[fo] = fma(omrf, val, gS);                       // :880
-                                        if (HAS_H) {
-                                            double vh = wc[u] + (gh[u][0] * r01.x + gh[u][1] * r01.y + gh[u][2] * r2) + xh[u];
-                                            double hS = (kd + cq * ((cc + 2.0) * kd - 2.0 * a.gas.K)) * gM * frt;
-                                            a.fbuf_h[fo] = fma(omrf, vh, hS);                    // :881
-                                        }
-                                    }
-                                }
-                            }
-                        }
-                    }
-                }
-                __syncwarp();   // all lanes are done with stage s before it is refilled
-            }
-
-            if (PHASE == 1) {
-#pragma unroll
-                for (int jj = 0; jj < ACC_FACES; jj++) {
-                    const int j = p0 + jj;
-                    if (j < nint) {   // warp-uniform
-                        double v[16];
-                        expand_g(accg[jj], wr, y, z, v);
-                        v[13] = v[14] = v[15] = 0.0;
-                        double tot = warp_reduce16(v, lane);
-                        const size_t slot = (size_t)2 * st.face[j] + (((ownmask >> j) & 1u) ? 0 : 1);
-                        const int idx = reduce16_index(lane);
-                        if ((lane & 1) == 0 && idx < NM_G) a.fslot[slot * nm + idx] += tot;
-                        if (HAS_H) {
-                            double uu[16];
-                            expand_h(acch[jj], wr, y, z, uu);
-#pragma unroll
-                            for (int k = NM_H; k < 16; k++) uu[k] = 0.0;
-                            double toth = warp_reduce16(uu, lane);
-                            if ((lane & 1) == 0 && idx < NM_H) a.fslot[slot * nm + NM_G + idx] += toth;
-                        }
-                    }
-                }
-            }
-            __syncwarp();
-        }
+#define DUGKS_RUN(NE_T)                                                                                      \
+    OutgoingCell<PHASE, HAS_H, CI, NE_T>::run(a, st, txs, stages, stage_d, nstream, bars, phase, ftab, lanec, \
+                                               unic, ne, nint, ownmask, symmask, c, r, lane, issue)
+        if (nint == ne && ne == 6) DUGKS_RUN(6);        // interior hexahedron
+        else if (nint == ne && ne == 4) DUGKS_RUN(4);   // interior 2-D quad
+        else DUGKS_RUN(-1);
+#undef DUGKS_RUN
         __syncwarp();
     }
 }
