@@ -108,7 +108,7 @@ struct dugks_handle {
     int n_big = 0;          // cells with more than FAST_NE faces (generic kernels)
     bool use_fast = true;
     bool use_tma = true;    // bulk-async staged kernels (dugks_tma.cuh)
-    int ci = 4, max_ne_fast = 0;
+    int ci = 4, max_ne_fast = 0, tma_tw = 32;
     size_t tsmem_out1 = 0, tsmem_out2 = 0, tsmem_upd = 0;
 };
 
@@ -212,7 +212,7 @@ static int launch_slab_kernels_phase1(dugks_handle* h, StepArgs a) {
     if ((rc = check_launch(h, "k_cell_halfstep"))) return rc;
     if (h->use_fast && h->use_tma) {
         Timed t(h, 0);
-        k_cell_outgoing_tma<1, H, TMA_CI><<<grid_for(items), WARPS_PER_CTA * 32, h->tsmem_out1, h->stream>>>(a, h->max_ne_fast + 1);
+        k_cell_outgoing_tma<1, H, TMA_CI, 32><<<grid_for(items), WARPS_PER_CTA * 32, h->tsmem_out1, h->stream>>>(a, h->max_ne_fast + 1);
         if ((rc = check_launch(h, "k_cell_outgoing_tma<1>"))) return rc;
     } else if (h->use_fast) {
         Timed t(h, 0);
@@ -244,7 +244,10 @@ static int launch_slab_kernels_phase2(dugks_handle* h, StepArgs a) {
     }
     if (h->use_fast && h->use_tma) {
         Timed t(h, 0);
-        k_cell_outgoing_tma<2, H, TMA_CI><<<grid_for(items), WARPS_PER_CTA * 32, h->tsmem_out2, h->stream>>>(a, h->max_ne_fast + 1);
+        if (h->tma_tw == 32)
+            k_cell_outgoing_tma<2, H, TMA_CI, 32><<<grid_for(items), WARPS_PER_CTA * 32, h->tsmem_out2, h->stream>>>(a, h->max_ne_fast + 1);
+        else
+            k_cell_outgoing_tma<2, H, TMA_CI, 64><<<grid_for(items), WARPS_PER_CTA * 32, h->tsmem_out2, h->stream>>>(a, h->max_ne_fast + 1);
         if ((rc = check_launch(h, "k_cell_outgoing_tma<2>"))) return rc;
     } else if (h->use_fast) {
         Timed t(h, 0);
@@ -820,7 +823,9 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
         auto tma_bytes = [&](int nstream, size_t extra_d) {
             return (size_t)NT_MAX * 6 * 8 + (size_t)WARPS_PER_CTA * (TMA_META_BYTES + (TMA_STAGES * tma_stage_doubles(nstream * nfld2, h->ci) + extra_d) * 8);
         };
-        const size_t extra2 = (size_t)ACC_FACES * 3 * h->tabw + ACC_FACES * 3 * 32 + ACC_FACES * 2;
+        h->tma_tw = h->tabw <= 32 ? 32 : 64;
+        const size_t extra2 = (size_t)ACC_FACES * 3 * h->tma_tw + ACC_FACES * 3 * 32 + ACC_FACES * 2;
+        if (h->tabw > 64) h->use_tma = false;
         h->tsmem_out1 = tma_bytes(h->max_ne_fast + 1, 0);
         h->tsmem_out2 = tma_bytes(h->max_ne_fast + 1, extra2);
         h->tsmem_upd = tma_bytes(h->max_ne_fast + 2, 0);
@@ -834,14 +839,16 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
         CUDAB(cudaFuncSetAttribute(k_cell_outgoing<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_out2));
         CUDAB(cudaFuncSetAttribute(k_cell_outgoing_fast<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fsmem_out2));
         if (h->use_tma) {
-            CUDAB(cudaFuncSetAttribute(k_cell_outgoing_tma<1, true, TMA_CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tsmem_out1));
-            CUDAB(cudaFuncSetAttribute(k_cell_outgoing_tma<2, true, TMA_CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tsmem_out2));
+            CUDAB(cudaFuncSetAttribute(k_cell_outgoing_tma<1, true, TMA_CI, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tsmem_out1));
+            CUDAB(cudaFuncSetAttribute(k_cell_outgoing_tma<2, true, TMA_CI, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tsmem_out2));
+            CUDAB(cudaFuncSetAttribute(k_cell_outgoing_tma<2, true, TMA_CI, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tsmem_out2));
             CUDAB(cudaFuncSetAttribute(k_cell_update_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tsmem_upd));
         }
     } else {
         if (h->use_tma) {
-            CUDAB(cudaFuncSetAttribute(k_cell_outgoing_tma<1, false, TMA_CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tsmem_out1));
-            CUDAB(cudaFuncSetAttribute(k_cell_outgoing_tma<2, false, TMA_CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tsmem_out2));
+            CUDAB(cudaFuncSetAttribute(k_cell_outgoing_tma<1, false, TMA_CI, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tsmem_out1));
+            CUDAB(cudaFuncSetAttribute(k_cell_outgoing_tma<2, false, TMA_CI, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tsmem_out2));
+            CUDAB(cudaFuncSetAttribute(k_cell_outgoing_tma<2, false, TMA_CI, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tsmem_out2));
             CUDAB(cudaFuncSetAttribute(k_cell_update_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tsmem_upd));
         }
         CUDAB(cudaFuncSetAttribute(k_cell_outgoing<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_out2));

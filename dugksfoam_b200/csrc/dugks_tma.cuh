@@ -73,7 +73,7 @@ __device__ __forceinline__ double warp_reduce16_smem(const double v[16], double*
 // Work of one warp on one cell for the bulk-staged outgoing kernel.
 // NE_T >= 0: all faces internal and ne == nint == NE_T (interior cell, fully unrolled,
 // no run-time face predicates); NE_T < 0: run-time ne / nint (boundary cells).
-template <int PHASE, bool HAS_H, int CI, int NE_T>
+template <int PHASE, bool HAS_H, int CI, int TW, int NE_T>
 struct OutgoingCell {
     template <class Issue>
     static __device__ __forceinline__ void run(const StepArgs& a, const FastStage& st, const double* txs,
@@ -82,7 +82,8 @@ struct OutgoingCell {
                                                int ne_rt, int nint_rt, unsigned ownmask, unsigned symmask,
                                                int c, int r, int lane, Issue&& issue) {
         const DevDV& dv = a.dv;
-        const int L = dv.L, Rs = dv.Rs, tw = dv.tabw, nm = a.nm;
+        const int L = dv.L, Rs = dv.Rs, nm = a.nm;
+        constexpr int tw = TW;
         const int ne = NE_T >= 0 ? NE_T : ne_rt;
         const int nint = NE_T >= 0 ? NE_T : nint_rt;
         const double kd = (double)(a.gas.K + 3 - a.gas.D);
@@ -101,23 +102,20 @@ struct OutgoingCell {
 
         for (int p0 = 0; p0 < nint; p0 += ACC_FACES) {
             issue(0, 0);
-            double ySy[ACC_FACES], zSz[ACC_FACES], Sx[ACC_FACES], tF[ACC_FACES], tN[ACC_FACES];
+            double ySy[ACC_FACES], zSz[ACC_FACES];
             double accg[ACC_FACES][4], acch[ACC_FACES][2];
 #pragma unroll
             for (int jj = 0; jj < ACC_FACES; jj++) {
                 const int j = p0 + jj;
-                ySy[jj] = zSz[jj] = Sx[jj] = tF[jj] = tN[jj] = 0.0;
+                ySy[jj] = zSz[jj] = 0.0;
                 accg[jj][0] = accg[jj][1] = accg[jj][2] = accg[jj][3] = 0.0;
                 acch[jj][0] = acch[jj][1] = 0.0;
                 if (j < nint) {
                     const double* G = st.geo + j * GEO12;
                     const bool isown = (ownmask >> j) & 1u;
                     const double sgn = isown ? 1.0 : -1.0;
-                    Sx[jj] = sgn * G[3];
                     ySy[jj] = __dmul_rn(y, sgn * G[7]);
                     zSz[jj] = __dmul_rn(z, sgn * G[8]);
-                    tF[jj] = isown ? V0 : Vp;      // full  <=> phi' >= tF
-                    tN[jj] = isown ? -V0 : -Vm;    // none  <=> phi' <  tN
                     if (PHASE == 2) {
                         const double* mf = a.fmac + (size_t)st.face[j] * MAC_N;
                         double rf = hstep / (2.0 * mf[5] + hstep);            // discreteVelocity.C:867
@@ -209,12 +207,16 @@ struct OutgoingCell {
                         const int j = p0 + jj;
                         if (j < nint) {
                             const double* G = st.geo + j * GEO12;
+                            const bool isown = (ownmask >> j) & 1u;
+                            const double Sxj = isown ? G[3] : -G[3];
+                            const double tFj = isown ? V0 : Vp;      // full  <=> phi' >= tF
+                            const double tNj = isown ? -V0 : -Vm;    // none  <=> phi' <  tN
                             double phi[2];
-                            phi[0] = __dadd_rn(__dadd_rn(__dmul_rn(x[0], Sx[jj]), ySy[jj]), zSz[jj]);
-                            phi[1] = __dadd_rn(__dadd_rn(__dmul_rn(x[1], Sx[jj]), ySy[jj]), zSz[jj]);
+                            phi[0] = __dadd_rn(__dadd_rn(__dmul_rn(x[0], Sxj), ySy[jj]), zSz[jj]);
+                            phi[1] = __dadd_rn(__dadd_rn(__dmul_rn(x[1], Sxj), ySy[jj]), zSz[jj]);
                             if (PHASE == 1) {
-                                const bool act0 = !(phi[0] < tN[jj]);             // this side contributes (full or tie)
-                                const bool act1 = two && !(phi[1] < tN[jj]);
+                                const bool act0 = !(phi[0] < tNj);             // this side contributes (full or tie)
+                                const bool act1 = two && !(phi[1] < tNj);
                                 if (!__any_sync(0xffffffffu, act0 || act1)) continue;
                                 const double2 r01 = lds2(G + 4);
                                 const double r2 = G[6];
@@ -222,14 +224,14 @@ struct OutgoingCell {
                                 for (int u = 0; u < 2; u++) {
                                     if (u ? act1 : act0) {
                                         double val = vc[u] + (gg[u][0] * r01.x + gg[u][1] * r01.y + gg[u][2] * r2) + xg[u];
-                                        if (!(phi[u] >= tF[jj])) val *= 0.5;                         // tie :513-529
+                                        if (!(phi[u] >= tFj)) val *= 0.5;                         // tie :513-529
                                         accg[jj][0] = fma(W[u][0], val, accg[jj][0]);
                                         accg[jj][1] = fma(W[u][1], val, accg[jj][1]);
                                         accg[jj][2] = fma(W[u][2], val, accg[jj][2]);
                                         accg[jj][3] = fma(W[u][3], val, accg[jj][3]);
                                         if (HAS_H) {
                                             double vh = wc[u] + (gh[u][0] * r01.x + gh[u][1] * r01.y + gh[u][2] * r2) + xh[u];
-                                            if (!(phi[u] >= tF[jj])) vh *= 0.5;
+                                            if (!(phi[u] >= tFj)) vh *= 0.5;
                                             acch[jj][0] = fma(W[u][0], vh, acch[jj][0]);
                                             acch[jj][1] = fma(W[u][1], vh, acch[jj][1]);
                                         }
@@ -238,7 +240,7 @@ struct OutgoingCell {
                             } else {
                                 // exactly one side writes the face value: the owner unless phi < -VSMALL
                                 // (then the neighbour, for which that is the "full" test)
-                                const double tW = ((ownmask >> j) & 1u) ? tN[jj] : tF[jj];
+                                const double tW = isown ? tNj : tFj;
                                 const bool wr0 = phi[0] >= tW;
                                 const bool wr1 = two && (phi[1] >= tW);
                                 if (!__any_sync(0xffffffffu, wr0 || wr1)) continue;
@@ -247,7 +249,7 @@ struct OutgoingCell {
                                 const double EYZ = lanec[(jj * 3 + 0) * 32 + lane], YZ2 = lanec[(jj * 3 + 1) * 32 + lane],
                                              QYZ = lanec[(jj * 3 + 2) * 32 + lane];
                                 const double omrf = unic[jj * 2], frt = unic[jj * 2 + 1];
-                                const size_t fbase = (size_t)st.face[j] * L * Rs + r;
+                                const int fbase = st.face[j] * L * Rs + r;
 #pragma unroll
                                 for (int u = 0; u < 2; u++) {
                                     if (u ? wr1 : wr0) {
@@ -257,7 +259,7 @@ struct OutgoingCell {
                                         double cq = ftab[(jj * 3 + 2) * tw + tt] + QYZ;
                                         double gM = ftab[(jj * 3 + 0) * tw + tt] * EYZ;
                                         double gS = fma(cq, cc, 1.0) * gM;
-                                        const size_t fo = fbase + (size_t)(i0 + u) * Rs;
+                                        const int fo = fbase + (i0 + u) * Rs;
                                         a.fbuf_g[fo] = fma(omrf, val, gS);                       // :880
                                         if (HAS_H) {
                                             double vh = wc[u] + (gh[u][0] * r01.x + gh[u][1] * r01.y + gh[u][2] * r2) + xh[u];
@@ -299,8 +301,9 @@ struct OutgoingCell {
     }
 };
 
-template <int PHASE, bool HAS_H, int CI>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2)
+// TW: stride of the per-face equilibrium tables (>= dv.tabw; 32 or 64)
+template <int PHASE, bool HAS_H, int CI, int TW>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, HAS_H ? 2 : 3)
 k_cell_outgoing_tma(StepArgs a, int nstream /* streams per field incl. own */) {
     extern __shared__ __align__(128) unsigned char dyn[];
     // layout: txs[NT_MAX][6] | per warp: meta(1 KB) | stages | (PHASE 2) ftab, lanec, unic
@@ -315,7 +318,7 @@ k_cell_outgoing_tma(StepArgs a, int nstream /* streams per field incl. own */) {
         txs[k * 6 + 5] = 0.0;
     }
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int tw = dv.tabw;
+    constexpr int tw = TW;
     const int nfld = HAS_H ? 2 : 1;
     const size_t stage_d = tma_stage_doubles(nstream * nfld, CI);
     const size_t extra_d = (PHASE == 2) ? ((size_t)ACC_FACES * 3 * tw + ACC_FACES * 3 * 32 + ACC_FACES * 2) : 0;
@@ -377,7 +380,7 @@ k_cell_outgoing_tma(StepArgs a, int nstream /* streams per field incl. own */) {
             }
         };
 #define DUGKS_RUN(NE_T)                                                                                      \
-    OutgoingCell<PHASE, HAS_H, CI, NE_T>::run(a, st, txs, stages, stage_d, nstream, bars, phase, ftab, lanec, \
+    OutgoingCell<PHASE, HAS_H, CI, TW, NE_T>::run(a, st, txs, stages, stage_d, nstream, bars, phase, ftab, lanec, \
                                                unic, ne, nint, ownmask, symmask, c, r, lane, issue)
         if (nint == ne && ne == 6) DUGKS_RUN(6);        // interior hexahedron
         else if (nint == ne && ne == 4) DUGKS_RUN(4);   // interior 2-D quad
