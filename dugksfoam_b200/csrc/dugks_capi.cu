@@ -393,7 +393,7 @@ static int choose_chunks(int n, int D, long long base_rows_local) {
         long long rows = base_rows_local * nch;
         long long padded = (rows + 31) / 32 * 32;
         double waste = 1.0 - (double)(base_rows_local * n) / (double)(padded * L);
-        if (waste < best_waste - 0.03) { best_waste = waste; best = nch; }   // prefer long rows unless padding drops by > 3%
+        if (waste < best_waste - 0.08) { best_waste = waste; best = nch; }   // prefer long rows unless padding drops by > 8%
     }
     return best;
 }
