@@ -18,7 +18,7 @@ from .abi import (ALLREDUCE_FN, DvsetT, GasT, Marshalled, MeshT, ParT, PatchT, S
 from .case import Case
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdugks.so")
+LIB_PATH = os.environ.get("DUGKS_LIB", os.path.join(_HERE, "libdugks.so"))   # DUGKS_LIB: A/B builds
 _LIB = None
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

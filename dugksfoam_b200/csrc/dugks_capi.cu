@@ -12,7 +12,7 @@
 #include <vector>
 
 #include "../../include/dugks.h"
-#include "dugks_tma.cuh"
+#include "dugks_hot.cuh"
 
 // ------------------------------------------------------------------------------
 // NCCL through dlopen (the library is present in every torch install and on the
@@ -110,6 +110,10 @@ struct dugks_handle {
     bool use_tma = true;    // bulk-async staged kernels (dugks_tma.cuh)
     int ci = 4, max_ne_fast = 0, tma_tw = 32;
     size_t tsmem_out1 = 0, tsmem_out2 = 0, tsmem_upd = 0;
+    // second-generation kernels (dugks_hot.cuh)
+    bool use_hot = true, has_far = false;
+    int hot_ne = 6, hot_grid_out1 = 148, hot_grid_out2 = 148, hot_grid_upd = 148;
+    size_t hsmem_out1 = 0, hsmem_out2 = 0, hsmem_upd = 0;
 };
 
 static int fail(dugks_handle* h, int code, const char* fmt, ...) {
@@ -201,6 +205,66 @@ static int do_allreduce(dugks_handle* h, double* buf, size_t n) {
     return 0;
 }
 
+// ---- second-generation kernels: NE (faces staged per cell) and TW (equilibrium table stride)
+// are compile-time; create() picks the smallest that fits the mesh / velocity layout
+template <int PHASE, bool H>
+static void launch_hot_outgoing(dugks_handle* h, const StepArgs& a) {
+    const size_t sm = PHASE == 1 ? h->hsmem_out1 : h->hsmem_out2;
+    const int tw = PHASE == 1 ? 32 : h->tma_tw;
+    const int grid = PHASE == 1 ? h->hot_grid_out1 : h->hot_grid_out2;
+#define DUGKS_HOT_OUT(NE_, TW_) k_hot_outgoing<PHASE, H, NE_, TW_><<<grid, HOT_WARPS * 32, sm, h->stream>>>(a)
+    if (h->hot_ne == 4) { if (tw == 32) DUGKS_HOT_OUT(4, 32); else DUGKS_HOT_OUT(4, 64); }
+    else if (h->hot_ne == 6) { if (tw == 32) DUGKS_HOT_OUT(6, 32); else DUGKS_HOT_OUT(6, 64); }
+    else { if (tw == 32) DUGKS_HOT_OUT(8, 32); else DUGKS_HOT_OUT(8, 64); }
+#undef DUGKS_HOT_OUT
+}
+template <bool H>
+static void launch_hot_update(dugks_handle* h, const StepArgs& a) {
+    if (h->hot_ne == 4) k_hot_update<H, 4><<<h->hot_grid_upd, HOT_WARPS * 32, h->hsmem_upd, h->stream>>>(a);
+    else if (h->hot_ne == 6) k_hot_update<H, 6><<<h->hot_grid_upd, HOT_WARPS * 32, h->hsmem_upd, h->stream>>>(a);
+    else k_hot_update<H, 8><<<h->hot_grid_upd, HOT_WARPS * 32, h->hsmem_upd, h->stream>>>(a);
+}
+template <int PHASE, bool H, int NE, int TW>
+static cudaError_t hot_attr_out(size_t bytes) {
+    return cudaFuncSetAttribute(k_hot_outgoing<PHASE, H, NE, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+template <bool H>
+static int hot_configure(dugks_handle* h) {
+    const int ntab = h->ntab, tw = h->tma_tw;
+    cudaError_t e = cudaSuccess;
+    int occ[3] = {1, 1, 1};
+#define DUGKS_HOT_CFG(NE_)                                                                                   \
+    do {                                                                                                     \
+        h->hsmem_out1 = HotPlan<1, H, NE_, 32>::total(ntab);                                                 \
+        h->hsmem_out2 = tw == 32 ? HotPlan<2, H, NE_, 32>::total(ntab) : HotPlan<2, H, NE_, 64>::total(ntab); \
+        h->hsmem_upd = HotUpdPlan<H, NE_>::total(ntab);                                                      \
+        if (std::max(std::max(h->hsmem_out1, h->hsmem_out2), h->hsmem_upd) > 220 * 1024) { h->use_hot = false; return 0; } \
+        e = hot_attr_out<1, H, NE_, 32>(h->hsmem_out1);                                                      \
+        if (e == cudaSuccess) e = tw == 32 ? hot_attr_out<2, H, NE_, 32>(h->hsmem_out2) : hot_attr_out<2, H, NE_, 64>(h->hsmem_out2); \
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_hot_update<H, NE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->hsmem_upd); \
+        /* persistent grids: CTAs the SM can hold (registers and shared memory) times the SM count */    \
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], k_hot_outgoing<1, H, NE_, 32>, HOT_WARPS * 32, h->hsmem_out1); \
+        if (e == cudaSuccess) e = tw == 32 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], k_hot_outgoing<2, H, NE_, 32>, HOT_WARPS * 32, h->hsmem_out2) \
+                                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], k_hot_outgoing<2, H, NE_, 64>, HOT_WARPS * 32, h->hsmem_out2); \
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], k_hot_update<H, NE_>, HOT_WARPS * 32, h->hsmem_upd); \
+    } while (0)
+    if (h->hot_ne == 4) DUGKS_HOT_CFG(4);
+    else if (h->hot_ne == 6) DUGKS_HOT_CFG(6);
+    else DUGKS_HOT_CFG(8);
+#undef DUGKS_HOT_CFG
+    if (e != cudaSuccess) return fail(h, DUGKS_ERR_CUDA, "cudaFuncSetAttribute (hot kernels): %s", cudaGetErrorString(e));
+    int dev_sms = 148;
+    cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->device);
+    const int max_ctas = (h->nc + HOT_WARPS - 1) / HOT_WARPS;
+    h->hot_grid_out1 = std::max(1, std::min(dev_sms * std::max(occ[0], 1), max_ctas));
+    h->hot_grid_out2 = std::max(1, std::min(dev_sms * std::max(occ[1], 1), max_ctas));
+    h->hot_grid_upd = std::max(1, std::min(dev_sms * std::max(occ[2], 1), max_ctas));
+    if (getenv("DUGKS_VERBOSE"))
+        fprintf(stderr, "dugks: hot kernels NE=%d smem %zu/%zu/%zu B, CTAs per SM %d/%d/%d\n", h->hot_ne, h->hsmem_out1,
+                h->hsmem_out2, h->hsmem_upd, occ[0], occ[1], occ[2]);
+    return 0;
+}
+
 template <bool H>
 static int launch_slab_kernels_phase1(dugks_handle* h, StepArgs a) {
     int rc;
@@ -210,6 +274,26 @@ static int launch_slab_kernels_phase1(dugks_handle* h, StepArgs a) {
         k_cell_halfstep<H><<<grid_for(items), WARPS_PER_CTA * 32, 0, h->stream>>>(a, 0);
     }
     if ((rc = check_launch(h, "k_cell_halfstep"))) return rc;
+    if (h->use_hot) {
+        {
+            Timed t(h, 0);
+            launch_hot_outgoing<1, H>(h, a);
+        }
+        if ((rc = check_launch(h, "k_hot_outgoing<1>"))) return rc;
+        if (h->n_big > 0) {
+            Timed t(h, 0);
+            a.skip_small = 1;
+            k_cell_outgoing<1, H><<<grid_for(items), WARPS_PER_CTA * 32, h->smem_out1, h->stream>>>(a);
+            if ((rc = check_launch(h, "k_cell_outgoing<1>"))) return rc;
+        }
+        if (h->nbf > 0 && (h->has_far || h->n_big > 0)) {
+            // incoming half of far-field patches; every boundary face of cells the generic kernel took
+            long long bitems = (long long)h->nbf * (h->Rs / 32);
+            k_bnd_outgoing<H><<<grid_for(bitems), WARPS_PER_CTA * 32, h->smem_bnd, h->stream>>>(a, h->n_big > 0 ? 0 : 1);
+            if ((rc = check_launch(h, "k_bnd_outgoing"))) return rc;
+        }
+        return 0;
+    }
     if (h->use_fast && h->use_tma) {
         Timed t(h, 0);
         k_cell_outgoing_tma<1, H, TMA_CI, 32><<<grid_for(items), WARPS_PER_CTA * 32, h->tsmem_out1, h->stream>>>(a, h->max_ne_fast + 1);
@@ -227,7 +311,7 @@ static int launch_slab_kernels_phase1(dugks_handle* h, StepArgs a) {
     }
     if (h->nbf > 0) {
         long long bitems = (long long)h->nbf * (h->Rs / 32);
-        k_bnd_outgoing<H><<<grid_for(bitems), WARPS_PER_CTA * 32, h->smem_bnd, h->stream>>>(a);
+        k_bnd_outgoing<H><<<grid_for(bitems), WARPS_PER_CTA * 32, h->smem_bnd, h->stream>>>(a, 0);
         if ((rc = check_launch(h, "k_bnd_outgoing"))) return rc;
     }
     return 0;
@@ -241,6 +325,31 @@ static int launch_slab_kernels_phase2(dugks_handle* h, StepArgs a) {
         long long bitems = (long long)h->nbf * (h->Rs / 32);
         k_bnd_relax<H><<<grid_for(bitems), WARPS_PER_CTA * 32, 0, h->stream>>>(a);
         if ((rc = check_launch(h, "k_bnd_relax"))) return rc;
+    }
+    if (h->use_hot) {
+        {
+            Timed t(h, 0);
+            launch_hot_outgoing<2, H>(h, a);
+        }
+        if ((rc = check_launch(h, "k_hot_outgoing<2>"))) return rc;
+        if (h->n_big > 0) {
+            Timed t(h, 0);
+            a.skip_small = 1;
+            k_cell_outgoing<2, H><<<grid_for(items), WARPS_PER_CTA * 32, h->smem_out2, h->stream>>>(a);
+            if ((rc = check_launch(h, "k_cell_outgoing<2>"))) return rc;
+        }
+        {
+            Timed t(h, 1);
+            launch_hot_update<H>(h, a);
+        }
+        if ((rc = check_launch(h, "k_hot_update"))) return rc;
+        if (h->n_big > 0) {
+            Timed t(h, 1);
+            a.skip_small = 1;
+            k_cell_update<H><<<grid_for(items), WARPS_PER_CTA * 32, h->smem_upd, h->stream>>>(a);
+            if ((rc = check_launch(h, "k_cell_update"))) return rc;
+        }
+        return 0;
     }
     if (h->use_fast && h->use_tma) {
         Timed t(h, 0);
@@ -714,10 +823,39 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
         }
         TRYB(dev_upload(h, &d_d, g12)); M.e_geo12 = d_d;
     }
+    {
+        // records of the second-generation kernels (dugks_hot.cuh): branch-free gradient coefficients
+        std::vector<double> geo6((size_t)(ne + nc) * 6, 0.0), geoS((size_t)ne * 4, 0.0);
+        for (int c = 0; c < nc; c++) {
+            double* rec = &geo6[(size_t)(off[c] + c) * 6];
+            for (int j = 0; j < cnt[c]; j++) {
+                const int e = off[c] + j;
+                const double* g = &e_geo[(size_t)e * 9];
+                double* o = rec + 6 * (1 + j);
+                double scale = 1.0;
+                if (e_other[e] < 0) {
+                    const int b = -1 - e_other[e];
+                    // boundary value = cell + gamma/deltaCoeffs (fixedGradient); symmetryPlane adds nothing
+                    scale = (b_kind[b] == K_SYMMETRY_PLANE) ? 0.0 : b_invdc[b];
+                } else {
+                    for (int d = 0; d < 3; d++) rec[d] -= g[d];
+                }
+                for (int d = 0; d < 3; d++) { o[d] = g[d] * scale; o[3 + d] = g[3 + d]; }
+                const double sgn = e_owner[e] ? 1.0 : -1.0;
+                for (int d = 0; d < 3; d++) geoS[(size_t)e * 4 + d] = sgn * g[6 + d];
+            }
+        }
+        TRYB(dev_upload(h, &d_d, geo6)); A.geo6 = d_d;
+        TRYB(dev_upload(h, &d_d, geoS)); A.geoS = d_d;
+    }
     for (int c = 0; c < nc; c++) {
         if (cnt[c] > FAST_NE) h->n_big++;
         else h->max_ne_fast = std::max(h->max_ne_fast, cnt[c]);
     }
+    for (int b = 0; b < nbf; b++)
+        if (b_kind[b] == K_FAR_FIELD || b_kind[b] == K_PRESSURE_IN || b_kind[b] == K_PRESSURE_OUT) h->has_far = true;
+    h->use_hot = getenv("DUGKS_NO_HOT") == nullptr;           // test hook: first-generation kernels
+    h->hot_ne = h->max_ne_fast <= 4 ? 4 : (h->max_ne_fast <= 6 ? 6 : 8);
     h->use_tma = getenv("DUGKS_NO_TMA") == nullptr;            // test hook: per-element LDG kernels instead
     h->ci = TMA_CI;
     h->use_fast = getenv("DUGKS_FORCE_GENERIC") == nullptr;   // test hook: run every cell through the generic kernels
@@ -783,20 +921,22 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
              need / 1e9, free_b / 1e9, nc, h->nvl, h->hasH ? "stored" : "elided");
         return bail(DUGKS_ERR_NOMEM);
     }
-    TRYB(dev_alloc(h, &A.gt, ncell_dv));
-    TRYB(dev_alloc(h, &A.gb, ncell_dv));
-    TRYB(dev_alloc(h, &A.gsb, nb_dv));
-    TRYB(dev_alloc(h, &h->gam_a_g, nb_dv));
-    TRYB(dev_alloc(h, &h->gam_b_g, nb_dv));
-    TRYB(dev_alloc(h, &A.fbuf_g, (size_t)nif * L * h->Rs));
+    // HOT_PAD: the bulk copies of a tail chunk always fetch HOT_CI velocity points
+    TRYB(dev_alloc(h, &A.gt, ncell_dv + HOT_PAD));
+    TRYB(dev_alloc(h, &A.gb, ncell_dv + HOT_PAD));
+    TRYB(dev_alloc(h, &A.gsb, nb_dv + HOT_PAD));
+    TRYB(dev_alloc(h, &h->gam_a_g, nb_dv + HOT_PAD));
+    TRYB(dev_alloc(h, &h->gam_b_g, nb_dv + HOT_PAD));
+    TRYB(dev_alloc(h, &A.fbuf_g, (size_t)nif * L * h->Rs + HOT_PAD));
     if (h->hasH) {
-        TRYB(dev_alloc(h, &A.ht, ncell_dv));
-        TRYB(dev_alloc(h, &A.hb, ncell_dv));
-        TRYB(dev_alloc(h, &A.hsb, nb_dv));
-        TRYB(dev_alloc(h, &h->gam_a_h, nb_dv));
-        TRYB(dev_alloc(h, &h->gam_b_h, nb_dv));
-        TRYB(dev_alloc(h, &A.fbuf_h, (size_t)nif * L * h->Rs));
+        TRYB(dev_alloc(h, &A.ht, ncell_dv + HOT_PAD));
+        TRYB(dev_alloc(h, &A.hb, ncell_dv + HOT_PAD));
+        TRYB(dev_alloc(h, &A.hsb, nb_dv + HOT_PAD));
+        TRYB(dev_alloc(h, &h->gam_a_h, nb_dv + HOT_PAD));
+        TRYB(dev_alloc(h, &h->gam_b_h, nb_dv + HOT_PAD));
+        TRYB(dev_alloc(h, &A.fbuf_h, (size_t)nif * L * h->Rs + HOT_PAD));
     }
+    TRYB(dev_alloc(h, &A.fcoef, (size_t)nf * FCOEF_N));
     if (h->has_sym) {
         TRYB(dev_alloc(h, &h->snap_g, nb_dv));
         if (h->hasH) TRYB(dev_alloc(h, &h->snap_h, nb_dv));
@@ -853,6 +993,26 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
         }
         CUDAB(cudaFuncSetAttribute(k_cell_outgoing<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_out2));
         CUDAB(cudaFuncSetAttribute(k_cell_outgoing_fast<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fsmem_out2));
+    }
+
+    // ---- second-generation kernels: shared-memory plan, static upwind range codes
+    if (h->tabw > 64 || L > 32) h->use_hot = false;
+    if (h->use_hot) TRYB(h->hasH ? hot_configure<true>(h) : hot_configure<false>(h));
+    if (h->use_hot) {
+        uint4* d_upw = nullptr;
+        int* d_bad = nullptr;
+        TRYB(dev_alloc(h, &d_upw, (size_t)h->nslab * nc * 32, false));
+        TRYB(dev_alloc(h, &d_bad, 1));
+        long long total = (long long)h->nslab * nc * 32;
+        int grid = (int)std::min<long long>((total + 255) / 256, 148LL * 64);
+        k_build_upwind<<<grid, 256, 0, h->stream>>>(A, d_upw, d_bad);
+        TRYB(check_launch(h, "k_build_upwind"));
+        int bad = 0;
+        CUDAB(cudaMemcpyAsync(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost, h->stream));
+        CUDAB(cudaStreamSynchronize(h->stream));
+        // abscissae that are not ascending give upwind sets that are not ranges: first-generation kernels
+        if (bad) h->use_hot = false;
+        A.upw = d_upw;
     }
 
     // ---- collective backend

@@ -1,0 +1,756 @@
+// dugks_hot.cuh — second-generation cell kernels (the ones the step spends its time in).
+//
+// Same mapping as dugks_tma.cuh (a warp advances one cell, a lane owns one velocity row and walks
+// the ix points serially, all inputs arrive as bulk-async copies into a per-warp shared-memory
+// ring), rebuilt around the instruction count per (cell, velocity) update:
+//   * upwind sets are STATIC (they depend on xi and Sf only): create() evaluates the reference's
+//     exact tests once (k_build_upwind) and stores, per (slab, cell, lane), eight 13-bit range codes;
+//     the step kernels decode them to bit masks — no FP64 dot products or compares per face and DV;
+//   * the least-squares gradient is branch-free: grad = G0*v_c + sum_j G'_j * s_j, where s_j is the
+//     j-th staged stream (neighbour gBarP or the lagged boundary gradient), G'_j has the boundary
+//     1/deltaCoeffs folded in, G0 = -sum of the internal G_j, symmetry planes carry G' = 0;
+//   * four velocity points are advanced together (independent FP64 chains, geometry reads amortised);
+//   * boundary faces of a cell are finished in the same pass (lagged normal gradient, outgoing face
+//     values), so k_bnd_outgoing only remains for the incoming half of far-field patches;
+//   * warps are persistent and prefetch the first chunk (and the geometry record) of their NEXT
+//     cell while they finish the current one, so the copy engine never idles at cell boundaries;
+//   * face equilibria of phase 2 come from per-face coefficient records written by k_face_macros.
+#pragma once
+#include "dugks_tma.cuh"
+
+#define HOT_WARPS 4
+#define HOT_CI 4          // velocity points per chunk (= per bulk copy and per unrolled group)
+#define HOT_STAGES 2
+#define HOT_PAD (HOT_CI * 32)   // doubles of slack behind every streamed array (tail chunks copy full size)
+#define FCOEF_N 12        // per-face equilibrium record: Ux Uy Uz a pre qx qy qz omrf RT 0 0
+
+// ---- upwind range codes -----------------------------------------------------------------------
+// bits 0-5: a, bits 6-11: b, bit 12: dir.   dir = 0: [0,a) none, [a,b) tie, [b,L) full
+//                                           dir = 1: [0,a) full, [a,b) tie, [b,L) none
+__host__ __device__ __forceinline__ unsigned hot_lowmask(unsigned n) {
+#ifdef __CUDA_ARCH__
+    return __funnelshift_lc(0xffffffffu, 0u, n);   // low n bits set, n <= 32 (one SHF)
+#else
+    return n >= 32u ? 0xffffffffu : ((1u << n) - 1u);
+#endif
+}
+__host__ __device__ __forceinline__ void hot_decode(unsigned code, int L, unsigned& full, unsigned& tie) {
+    const unsigned la = hot_lowmask(code & 63u), lb = hot_lowmask((code >> 6) & 63u);
+    tie = lb & ~la;
+    full = (code & 0x1000u) ? la : (hot_lowmask((unsigned)L) & ~lb);
+}
+__host__ __device__ __forceinline__ bool hot_encode(unsigned full, unsigned tie, int L, unsigned& code) {
+    // try both directions; the masks must be (prefix | run | suffix) shaped
+    const int nfull = __builtin_popcount(full), ntie = __builtin_popcount(tie);
+    for (unsigned dir = 0; dir < 2; dir++) {
+        unsigned a, b;
+        if (dir == 0) { b = (unsigned)(L - nfull); a = b - (unsigned)ntie; }
+        else { a = (unsigned)nfull; b = a + (unsigned)ntie; }
+        unsigned c = a | (b << 6) | (dir << 12), f2, t2;
+        hot_decode(c, L, f2, t2);
+        if (f2 == full && t2 == tie) { code = c; return true; }
+    }
+    return false;
+}
+
+// One thread per (slab, cell, lane): evaluates xi.Sf with the reference's operation order for every
+// face entry and every ix, classifies (discreteVelocity.C:495,506 internal; :562,580,614,675 boundary)
+// and stores the range codes.  *bad is raised if a set is not range shaped (unsorted abscissae).
+__global__ void k_build_upwind(StepArgs a, uint4* out, int* bad) {
+    const DevDV& dv = a.dv;
+    const long long total = (long long)dv.nslab * a.m.nc * 32;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int lane = (int)(t & 31);
+        const long long sc = t >> 5;
+        const int c = (int)(sc % a.m.nc), slab = (int)(sc / a.m.nc);
+        const int grow = slab * 32 + lane;
+        const double y = dv.row_y[grow], z = dv.row_z[grow];
+        const int cb = dv.row_cbase[grow];
+        const int e0 = a.m.cell_off[c], ne = a.m.cell_off[c + 1] - e0;
+        unsigned short codes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int j = 0; j < ne && j < 8; j++) {
+            const double* g = a.m.e_geo + (size_t)(e0 + j) * 9;
+            const int o = a.m.e_other[e0 + j];
+            const bool isown = a.m.e_owner[e0 + j] != 0;
+            unsigned full = 0, tie = 0;
+            for (int i = 0; i < dv.L; i++) {
+                const double phi = dot_exact(dv.tx[cb + i], y, z, g[6], g[7], g[8]);
+                if (o >= 0) {
+                    const bool neg = phi < -DUGKS_VSMALL, pos = phi >= DUGKS_VSMALL;
+                    const bool f = isown ? pos : neg, none = isown ? neg : pos;
+                    if (f) full |= 1u << i;
+                    else if (!none) tie |= 1u << i;
+                } else {
+                    const int kind = a.m.b_kind[-1 - o];
+                    bool outgoing;
+                    if (kind == K_ZERO_GRADIENT) outgoing = true;
+                    else if (kind == K_DVM_SYMMETRY || kind == K_SYMMETRY_PLANE) outgoing = phi > -DUGKS_VSMALL;
+                    else outgoing = phi > 0;
+                    if (outgoing) full |= 1u << i;
+                }
+            }
+            unsigned code = 0;
+            if (!hot_encode(full, tie, dv.L, code)) atomicOr(bad, 1);
+            codes[j] = (unsigned short)code;
+        }
+        uint4 w;
+        w.x = codes[0] | ((unsigned)codes[1] << 16);
+        w.y = codes[2] | ((unsigned)codes[3] << 16);
+        w.z = codes[4] | ((unsigned)codes[5] << 16);
+        w.w = codes[6] | ((unsigned)codes[7] << 16);
+        out[t] = w;
+    }
+}
+
+// ---- asynchronous staging (LDGSTS: 16 bytes per lane and instruction, L2 -> shared, bypassing L1) ----
+// Seven-plus streams of 1 KB per chunk are cheaper to launch as 2 warp-wide cp.async per stream (one
+// address add each) than as one bulk copy per stream issued by a single elected lane (uniform-register
+// set-up + mbarrier bookkeeping per copy), see profiles/r01_ncu_summary_r2a.txt.
+__device__ __forceinline__ void cp_async16(uint32_t sdst, const void* gsrc) {
+    // no "memory" clobber: the stage is only read after cp_async_wait + __syncwarp, and refilled after
+    // the __syncwarp that ends the chunk which read it
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// ---- per-warp item bookkeeping ------------------------------------------------------------------
+struct HotMeta {
+    int c, e0, ne, nint;
+    int other, face, own, kind;   // lane j < ne: entry j (kind: -1 internal, else patch kind)
+    uint4 mw;                     // upwind range codes of this (cell, lane)
+};
+
+#ifndef HOT_MINB
+#define HOT_MINB 2      // CTAs per SM the outgoing kernel is compiled for (register budget 65536 / (128 * HOT_MINB))
+#endif
+#define HOT_PTRS 20   // stream pointer table entries per buffer (>= 2 * (2 + 8))
+
+// Reads the CSR entries of cell c; writes the stream sources of phase-1/2 into the pointer table `sp`
+// (slot 0 = own cell, 1+j = entry j; + NSLOT for the h field).
+template <bool HAS_H>
+__device__ __forceinline__ void hot_load_meta(const StepArgs& a, int c, int lane, const double* gbs,
+                                              const double* hbs, const double* gam_g, const double* gam_h,
+                                              int NE, unsigned long long* sp, HotMeta& M) {
+    const DevMesh& m = a.m;
+    const int blk = a.dv.L * 32;
+    const int NSLOT = 1 + NE;
+    M.c = c;
+    M.e0 = m.cell_off[c];
+    M.ne = m.cell_off[c + 1] - M.e0;
+    M.nint = m.cell_nint[c];
+    M.other = 0; M.face = 0; M.own = 0; M.kind = -1;
+    M.mw = a.upw[((size_t)a.slab * m.nc + c) * 32 + lane];
+    if (M.ne <= NE) {
+        if (lane < M.ne) {
+            M.other = m.e_other[M.e0 + lane];
+            M.face = m.e_face[M.e0 + lane];
+            M.own = m.e_owner[M.e0 + lane];
+            if (M.other < 0) M.kind = m.b_kind[-1 - M.other];
+        }
+        // lane j+1 <- entry j
+        const int o = __shfl_up_sync(0xffffffffu, M.other, 1), k = __shfl_up_sync(0xffffffffu, M.kind, 1);
+        if (lane <= M.ne) {
+#pragma unroll
+            for (int fld = 0; fld < (HAS_H ? 2 : 1); fld++) {
+                const double* cellsrc = fld ? hbs : gbs;
+                const double* src;
+                if (lane == 0) src = cellsrc + (size_t)c * blk;
+                else if (o >= 0) src = cellsrc + (size_t)o * blk;
+                else if (k == K_SYMMETRY_PLANE) src = cellsrc + (size_t)c * blk;   // G' = 0: any finite data
+                else src = (fld ? gam_h : gam_g) + (size_t)(-1 - o) * blk;
+                sp[fld * NSLOT + lane] = (unsigned long long)src;
+            }
+        }
+    }
+}
+
+// chunk `ch` of the item whose pointers are in `sp` into `stage`; one commit group (all lanes call)
+template <int NTOT, int NSLOT, bool ALL>
+__device__ __forceinline__ void hot_stage(const unsigned long long* sp, int ne, int ch, double* stage, int lane) {
+    const uint32_t loff = (uint32_t)lane * 16u + (uint32_t)ch * (HOT_CI * 256u);
+    const uint32_t sdst = smem_u32(stage) + (uint32_t)lane * 16u;
+#pragma unroll
+    for (int k = 0; k < NTOT; k++) {
+        if (ALL || (k % NSLOT) <= ne) {
+            const char* p = reinterpret_cast<const char*>(sp[k]) + loff;
+#pragma unroll
+            for (int part = 0; part < HOT_CI * 256 / 512; part++)
+                cp_async16(sdst + k * (HOT_CI * 256) + part * 512, p + part * 512);
+        }
+    }
+}
+
+// interior cells: every stream lives in the same slab array, so 32-bit byte offsets (already including
+// the lane's 16 bytes) in registers replace the pointer table: one 64-bit add + two LDGSTS per stream
+template <int NFLD, int NSLOT>
+__device__ __forceinline__ void hot_stage_off(const double* gbs, const double* hbs, const uint32_t (&soff)[NSLOT],
+                                              int ch, double* stage, int lane) {
+    const uint32_t sdst = smem_u32(stage) + (uint32_t)lane * 16u;
+    const uint32_t coff = (uint32_t)ch * (HOT_CI * 256u);
+#pragma unroll
+    for (int fld = 0; fld < NFLD; fld++) {
+        const char* base = reinterpret_cast<const char*>(fld ? hbs : gbs) + coff;
+#pragma unroll
+        for (int k = 0; k < NSLOT; k++) {
+            const char* p = base + soff[k];
+#pragma unroll
+            for (int part = 0; part < HOT_CI * 256 / 512; part++)
+                cp_async16(sdst + (fld * NSLOT + k) * (HOT_CI * 256) + part * 512, p + part * 512);
+        }
+    }
+}
+
+// geometry record of a cell ((1 + ne) * 48 bytes) into `dst`, same commit group as the chunk that follows
+__device__ __forceinline__ void hot_stage_geo(const double* src, int ne, double* dst, int lane) {
+    if (lane < (1 + ne) * 3) cp_async16(smem_u32(dst) + lane * 16, reinterpret_cast<const char*>(src) + lane * 16);
+}
+
+// shared-memory plan of one warp
+template <int PHASE, bool HAS_H, int NE, int TW>
+struct HotPlan {
+    static constexpr int NFLD = HAS_H ? 2 : 1;
+    static constexpr int NSLOT = 1 + NE;
+    static constexpr int STAGE_D = NFLD * NSLOT * HOT_CI * 32;
+    static constexpr int GEO_D = NSLOT * 6;
+    // PHASE 1 reduces its moments through the stage that was consumed last (STAGE_D >= 32 * 17)
+    static constexpr int EXTRA_D = (PHASE == 1) ? 0 : (NE * 4 * TW + NE * 2);
+    static_assert(STAGE_D >= 32 * 17, "stage too small for the moment reduction");
+    static constexpr int PER_WARP_D = 2 * HOT_PTRS + 2 * GEO_D + HOT_STAGES * STAGE_D + EXTRA_D;
+    static constexpr size_t PER_WARP = ((size_t)PER_WARP_D * 8 + 127) / 128 * 128;
+    static __host__ __device__ size_t txs_bytes(int ntab) { return ((size_t)(ntab + HOT_CI) * 48 + 127) / 128 * 128; }
+    static __host__ size_t total(int ntab) { return txs_bytes(ntab) + HOT_WARPS * PER_WARP; }
+};
+
+// txs[t] = { -0.5 dt x, W0, W1, W2, W3, x }, zero weights past the table
+__device__ __forceinline__ void hot_fill_txs(const DevDV& dv, double hd, double* txs) {
+    for (int k = threadIdx.x; k < dv.ntab + HOT_CI; k += blockDim.x) {
+        const int kk = min(k, dv.ntab - 1);
+        const bool real = k < dv.ntab;
+        txs[k * 6 + 0] = hd * dv.tx[kk];
+        txs[k * 6 + 1] = real ? dv.tx[dv.ntab + kk] : 0.0;
+        txs[k * 6 + 2] = real ? dv.tx[2 * dv.ntab + kk] : 0.0;
+        txs[k * 6 + 3] = real ? dv.tx[3 * dv.ntab + kk] : 0.0;
+        txs[k * 6 + 4] = real ? dv.tx[4 * dv.ntab + kk] : 0.0;
+        txs[k * 6 + 5] = dv.tx[kk];
+    }
+}
+
+// bit 4*ch of the result: some / every point of chunk ch is set in m
+__device__ __forceinline__ unsigned hot_spread_any(unsigned m) { return (m | (m >> 1) | (m >> 2) | (m >> 3)) & 0x11111111u; }
+__device__ __forceinline__ unsigned hot_spread_all(unsigned m) { return (m & (m >> 1) & (m >> 2) & (m >> 3)) & 0x11111111u; }
+
+// per-warp constants of the outgoing kernel
+struct HotCtx {
+    const double* txs;
+    const double* geo;     // geometry record of the current cell
+    double* red;           // PHASE 1 reduction scratch
+    double* xtab;          // PHASE 2 [NE][TW][4]
+    double* unic;          // PHASE 2 [NE][2]
+    double y, z, wr, yh, zh, kd;
+    int cb, tmin, span, lane, L, blk, nm, nchunk;
+    size_t slab_b;
+};
+
+// One cell of the outgoing kernel.  INTERIOR: every one of the NE entries is an internal face, so all
+// face predicates are compile-time.  `prefetch(ch)` stages the chunk that follows chunk ch.
+template <int PHASE, bool HAS_H, int NE, int TW, bool INTERIOR, class Prefetch>
+__device__ __forceinline__ void hot_out_item(const StepArgs& a, const HotCtx& x, const HotMeta& cur,
+                                             double* stages, int stage_d, uint32_t& q, Prefetch&& prefetch) {
+    constexpr int CI = HOT_CI, NSLOT = 1 + NE, NFLD = HAS_H ? 2 : 1;
+    const int lane = x.lane, L = x.L, blk = x.blk;
+    const int ne = INTERIOR ? NE : cur.ne, nint = INTERIOR ? NE : cur.nint;
+    const double* gb_ = x.geo;
+    const double* txs = x.txs;
+    // ---- upwind masks of this (cell, lane) and their warp-uniform per-chunk summaries
+    unsigned full[NE], tie[NE], anyc[NE], allc[NE];
+    const unsigned ownmask = __ballot_sync(0xffffffffu, cur.own != 0);
+    int fbase[NE];
+    {
+        const unsigned w4[4] = {cur.mw.x, cur.mw.y, cur.mw.z, cur.mw.w};
+#pragma unroll
+        for (int j = 0; j < NE; j++) {
+            full[j] = 0; tie[j] = 0; anyc[j] = 0; allc[j] = 0;
+            fbase[j] = __shfl_sync(0xffffffffu, cur.face, j);
+            if (j < ne) {
+                hot_decode((w4[j >> 1] >> ((j & 1) * 16)) & 0xffffu, L, full[j], tie[j]);
+                if (PHASE == 2 && j < nint) {
+                    // exactly one side writes the face value: the owner unless phi < -VSMALL (ties: the
+                    // owner; their flux is zero).  From here on full[] holds the write mask.
+                    if ((ownmask >> j) & 1u) full[j] |= tie[j];
+                    tie[j] = 0;
+                }
+                anyc[j] = __reduce_or_sync(0xffffffffu, hot_spread_any(full[j] | tie[j]));
+                allc[j] = __reduce_and_sync(0xffffffffu, hot_spread_all(full[j]));
+            }
+        }
+    }
+    // ---- accumulators (PHASE 1) / face equilibrium tables (PHASE 2)
+    double accg[NE][4], acch[NE][2];
+    double EYZ[NE], YZ2[NE], QYZ[NE];
+#pragma unroll
+    for (int j = 0; j < NE; j++) {
+        accg[j][0] = accg[j][1] = accg[j][2] = accg[j][3] = 0.0;
+        acch[j][0] = acch[j][1] = 0.0;
+        EYZ[j] = YZ2[j] = QYZ[j] = 0.0;
+        if (PHASE == 2 && j < nint && anyc[j] != 0) {
+            const double* fc = a.fcoef + (size_t)fbase[j] * FCOEF_N;
+            const double Ux = fc[0], Uy = fc[1], Uz = fc[2], ia = fc[3], pre = fc[4];
+            const double qx = fc[5], qy = fc[6], qz = fc[7];
+            for (int tt = lane; tt < x.span; tt += 32) {
+                const double cx = txs[(x.tmin + tt) * 6 + 5] - Ux;
+                const double x2 = cx * cx * ia;
+                double* xt = x.xtab + ((size_t)j * TW + tt) * 4;
+                xt[0] = exp(-0.5 * x2); xt[1] = x2; xt[2] = cx * qx; xt[3] = 0.0;
+            }
+            const double cy = x.y - Uy, cz = x.z - Uz;
+            const double yz2 = (cy * cy + cz * cz) * ia;
+            EYZ[j] = pre * exp(-0.5 * yz2);
+            YZ2[j] = yz2 - a.gas.D - 2.0;
+            QYZ[j] = cy * qy + cz * qz;
+            if (lane == 0) { x.unic[j * 2] = fc[8]; x.unic[j * 2 + 1] = fc[9]; }
+        }
+    }
+    if (PHASE == 2) __syncwarp();
+
+    for (int ch = 0; ch < x.nchunk; ch++) {
+        prefetch(ch);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncwarp();
+        const double* sg = stages + (q & 1) * stage_d;
+        const int i0 = ch * CI;
+        const int tb = x.cb + i0;
+
+#pragma unroll
+        for (int fld = 0; fld < NFLD; fld++) {
+            const double* sf = sg + fld * NSLOT * CI * 32 + lane;
+            // ---- gradient (stock leastSquaresGrad, zeroBoundaryGrad.C:90-99,126-133)
+            double v[CI], gx[CI], gy[CI], gz[CI], base[CI];
+            {
+                const double2 G01 = lds2(gb_);
+                const double G2 = gb_[2];
+#pragma unroll
+                for (int u = 0; u < CI; u++) {
+                    v[u] = sf[u * 32];
+                    gx[u] = G01.x * v[u]; gy[u] = G01.y * v[u]; gz[u] = G2 * v[u];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < NE; j++) {
+                if (j < ne) {
+                    const double2 G01 = lds2(gb_ + 6 * (1 + j));
+                    const double G2 = gb_[6 * (1 + j) + 2];
+#pragma unroll
+                    for (int u = 0; u < CI; u++) {
+                        const double sv = sf[((1 + j) * CI + u) * 32];
+                        gx[u] = fma(G01.x, sv, gx[u]); gy[u] = fma(G01.y, sv, gy[u]); gz[u] = fma(G2, sv, gz[u]);
+                    }
+                }
+            }
+            // ---- value at the cell centre moved back by half a step: v - 0.5 dt xi.grad (:498-502)
+            double W[CI][4];
+#pragma unroll
+            for (int u = 0; u < CI; u++) {
+                const double2 t0 = lds2(txs + (tb + u) * 6);
+                base[u] = fma(t0.x, gx[u], fma(x.yh, gy[u], fma(x.zh, gz[u], v[u])));
+                if (PHASE == 1) {
+                    const double2 t1 = lds2(txs + (tb + u) * 6 + 2);
+                    W[u][0] = t0.y; W[u][1] = t1.x; W[u][2] = t1.y; W[u][3] = txs[(tb + u) * 6 + 4];
+                }
+            }
+            // ---- internal faces
+#pragma unroll
+            for (int j = 0; j < NE; j++) {
+                if (j >= nint) continue;
+                if (!((anyc[j] >> i0) & 1u)) continue;                      // warp-uniform
+                const double2 Gr = lds2(gb_ + 6 * (1 + j) + 2), r12 = lds2(gb_ + 6 * (1 + j) + 4);
+                const double r0 = Gr.y, r1 = r12.x, r2 = r12.y;
+                const bool allfull = (allc[j] >> i0) & 1u;                  // warp-uniform
+                if (PHASE == 1) {
+                    if (allfull) {
+#pragma unroll
+                        for (int u = 0; u < CI; u++) {
+                            const double val = fma(r0, gx[u], fma(r1, gy[u], fma(r2, gz[u], base[u])));
+                            if (fld == 0) {
+                                accg[j][0] = fma(W[u][0], val, accg[j][0]); accg[j][1] = fma(W[u][1], val, accg[j][1]);
+                                accg[j][2] = fma(W[u][2], val, accg[j][2]); accg[j][3] = fma(W[u][3], val, accg[j][3]);
+                            } else {
+                                acch[j][0] = fma(W[u][0], val, acch[j][0]); acch[j][1] = fma(W[u][1], val, acch[j][1]);
+                            }
+                        }
+                    } else {
+                        const unsigned fb = full[j] >> i0, tbits = tie[j] >> i0;
+#pragma unroll
+                        for (int u = 0; u < CI; u++) {
+                            double val = fma(r0, gx[u], fma(r1, gy[u], fma(r2, gz[u], base[u])));
+                            // this side's share: all of it, half of it on a tie (:513-529), or none
+                            const int hi = ((fb >> u) & 1u) ? 0x3ff00000 : (((tbits >> u) & 1u) ? 0x3fe00000 : 0);
+                            val *= __hiloint2double(hi, 0);
+                            if (fld == 0) {
+                                accg[j][0] = fma(W[u][0], val, accg[j][0]); accg[j][1] = fma(W[u][1], val, accg[j][1]);
+                                accg[j][2] = fma(W[u][2], val, accg[j][2]); accg[j][3] = fma(W[u][3], val, accg[j][3]);
+                            } else {
+                                acch[j][0] = fma(W[u][0], val, acch[j][0]); acch[j][1] = fma(W[u][1], val, acch[j][1]);
+                            }
+                        }
+                    }
+                } else {
+                    const double omrf = x.unic[j * 2], frt = x.unic[j * 2 + 1];
+                    double* dst = (fld == 0 ? a.fbuf_g : a.fbuf_h) + (size_t)fbase[j] * blk + i0 * 32 + lane;
+                    const unsigned wb = full[j] >> i0;
+#pragma unroll
+                    for (int u = 0; u < CI; u++) {
+                        const double val = fma(r0, gx[u], fma(r1, gy[u], fma(r2, gz[u], base[u])));
+                        const double* xt = x.xtab + ((size_t)j * TW + (tb + u - x.tmin)) * 4;
+                        const double2 x01 = lds2(xt);
+                        const double cc = x01.y + YZ2[j];
+                        const double cq = xt[2] + QYZ[j];
+                        const double gM = x01.x * EYZ[j];
+                        double eq;
+                        if (fld == 0) eq = fma(cq, cc, 1.0) * gM;                                      // :1042
+                        else eq = (x.kd + cq * ((cc + 2.0) * x.kd - 2.0 * a.gas.K)) * gM * frt;        // :1043
+                        if (allfull || ((wb >> u) & 1u)) dst[u * 32] = fma(omrf, val, eq);             // :880-881
+                    }
+                }
+            }
+            // ---- boundary faces of this cell (PHASE 1): lagged normal gradient (:436-470) and the
+            // outgoing half of the patch rules (:533-690)
+            if (!INTERIOR && PHASE == 1 && nint < ne) {
+                for (int j = nint; j < ne; j++) {
+                    const int kind = __shfl_sync(0xffffffffu, cur.kind, j);
+                    const int b = -1 - __shfl_sync(0xffffffffu, cur.other, j);
+                    const double r0 = gb_[6 * (1 + j) + 3], r1 = gb_[6 * (1 + j) + 4], r2 = gb_[6 * (1 + j) + 5];
+                    const size_t bo = x.slab_b + (size_t)b * blk + i0 * 32 + lane;
+                    double* gam_new = fld == 0 ? a.gam_new_g : a.gam_new_h;
+                    double* gsb = fld == 0 ? a.gsb : a.hsb;
+                    unsigned fj = 0;
+#pragma unroll
+                    for (int jj = 0; jj < NE; jj++) if (jj == j) fj = full[jj];
+                    const unsigned ob = fj >> i0;
+                    if (kind != K_SYMMETRY_PLANE) {
+                        const double n0 = a.m.b_n[(size_t)b * 3], n1 = a.m.b_n[(size_t)b * 3 + 1], n2 = a.m.b_n[(size_t)b * 3 + 2];
+#pragma unroll
+                        for (int u = 0; u < CI; u++)
+                            if (i0 + u < L) gam_new[bo + u * 32] = gx[u] * n0 + gy[u] * n1 + gz[u] * n2;
+                    }
+#pragma unroll
+                    for (int u = 0; u < CI; u++) {
+                        if ((ob >> u) & 1u) {
+                            const double val = (kind == K_ZERO_GRADIENT)
+                                                   ? v[u]
+                                                   : fma(r0, gx[u], fma(r1, gy[u], fma(r2, gz[u], base[u])));
+                            gsb[bo + u * 32] = val;
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();   // every lane is done with this stage before it is refilled
+        q++;
+    }
+
+    if (PHASE == 1) {
+#pragma unroll
+        for (int j = 0; j < NE; j++) {
+            if (j < nint && anyc[j] != 0) {   // warp-uniform; a side that is nowhere upwind adds nothing
+                double vv[16];
+                expand_g(accg[j], x.wr, x.y, x.z, vv);
+                double uu[NM_H] = {0, 0, 0, 0};
+                if (HAS_H) expand_h(acch[j], x.wr, x.y, x.z, uu);
+                vv[13] = uu[0]; vv[14] = uu[1]; vv[15] = uu[2];
+                const double tot = warp_reduce16_smem(vv, stages + ((q & 1) ^ 1) * stage_d, lane);
+                const size_t slot = (size_t)2 * fbase[j] + (((ownmask >> j) & 1u) ? 0 : 1);
+                // one warp owns a slot per launch: the fire-and-forget add keeps the sum deterministic
+                if (lane < 16 && lane < x.nm) atomicAdd(a.fslot + slot * x.nm + lane, tot);
+                if (HAS_H) {
+                    const double t3 = warp_sum(uu[3]);
+                    if (lane == 0) atomicAdd(a.fslot + slot * x.nm + 16, t3);
+                }
+            }
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// stages 2.1 + 3 (PHASE 1: face moments, boundary-face values, lagged boundary gradient) and
+// stage 4 (PHASE 2: relaxed internal-face values into the slab flux buffer).
+// discreteVelocity.C:412-691 / fvDVM.C:473-516 / discreteVelocity.C:867-881
+template <int PHASE, bool HAS_H, int NE, int TW>
+__global__ void __launch_bounds__(HOT_WARPS * 32, HOT_MINB)
+k_hot_outgoing(StepArgs a) {
+    using P = HotPlan<PHASE, HAS_H, NE, TW>;
+    constexpr int NSLOT = P::NSLOT, NTOT = P::NFLD * P::NSLOT;
+    extern __shared__ __align__(128) unsigned char dyn[];
+    const DevDV& dv = a.dv;
+    const int L = dv.L, nc = a.m.nc, blk = L * 32;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const double hd = -0.5 * a.dt;
+    double* txs = reinterpret_cast<double*>(dyn);
+    hot_fill_txs(dv, hd, txs);
+    unsigned char* wbase = dyn + P::txs_bytes(dv.ntab) + wib * P::PER_WARP;
+    unsigned long long* sptr = reinterpret_cast<unsigned long long*>(wbase);   // [2][HOT_PTRS]
+    double* geo = reinterpret_cast<double*>(wbase) + 2 * HOT_PTRS;             // [2][GEO_D]
+    double* stages = geo + 2 * P::GEO_D;                                       // [HOT_STAGES][STAGE_D]
+    double* extra = stages + HOT_STAGES * P::STAGE_D;
+    __syncthreads();
+
+    const size_t slab_c = (size_t)a.slab * nc * blk, slab_b = (size_t)a.slab * a.m.nbf * blk;
+    const double* gbs = a.gb + slab_c;
+    const double* hbs = HAS_H ? a.hb + slab_c : nullptr;
+    const double* gam_g = a.gam_old_g + slab_b;
+    const double* gam_h = HAS_H ? a.gam_old_h + slab_b : nullptr;
+    const int grow = a.slab * 32 + lane;
+    HotCtx x;
+    x.txs = txs;
+    x.red = extra; x.xtab = extra; x.unic = extra + NE * 4 * TW;
+    x.y = dv.row_y[grow]; x.z = dv.row_z[grow]; x.wr = dv.row_w[grow];
+    x.yh = hd * x.y; x.zh = hd * x.z;
+    x.kd = (double)(a.gas.K + 3 - a.gas.D);
+    x.cb = dv.row_cbase[grow];
+    x.tmin = 0; x.span = 0;
+    if (PHASE == 2) table_range(dv, x.cb, x.tmin, x.span);
+    x.lane = lane; x.L = L; x.blk = blk; x.nm = a.nm;
+    x.nchunk = (L + HOT_CI - 1) / HOT_CI;
+    x.slab_b = slab_b;
+
+    const int nw = gridDim.x * HOT_WARPS;
+    int item = blockIdx.x * HOT_WARPS + wib;
+    uint32_t q = 0;        // flat chunk counter of this warp: stage = q & 1
+    int gsel = 0;          // pointer / geometry buffer of the current item
+    HotMeta cur{}, nxt{};
+    if (item < nc) {
+        hot_load_meta<HAS_H>(a, item, lane, gbs, hbs, gam_g, gam_h, NE, sptr, cur);
+        __syncwarp();
+        if (cur.ne <= NE) {
+            hot_stage<NTOT, NSLOT, false>(sptr, cur.ne, 0, stages, lane);
+            hot_stage_geo(a.geo6 + (size_t)(cur.e0 + cur.c) * 6, cur.ne, geo, lane);
+        }
+        cp_async_commit();
+    }
+    while (item < nc) {
+        const int nitem = item + nw;
+        const bool has_next = nitem < nc;
+        unsigned long long* sp_cur = sptr + gsel * HOT_PTRS;
+        unsigned long long* sp_nxt = sptr + (gsel ^ 1) * HOT_PTRS;
+        if (has_next) hot_load_meta<HAS_H>(a, nitem, lane, gbs, hbs, gam_g, gam_h, NE, sp_nxt, nxt);
+        __syncwarp();
+        const bool next_ok = has_next && nxt.ne <= NE;
+        auto stage_next_item = [&](double* stage) {
+            if (next_ok) {
+                hot_stage<NTOT, NSLOT, false>(sp_nxt, nxt.ne, 0, stage, lane);
+                hot_stage_geo(a.geo6 + (size_t)(nxt.e0 + nxt.c) * 6, nxt.ne, geo + (gsel ^ 1) * P::GEO_D, lane);
+            }
+        };
+        if (cur.ne > NE) {      // cell with too many faces: the generic kernels take it
+            __syncwarp();
+            stage_next_item(stages + (q & 1) * P::STAGE_D);
+            cp_async_commit();
+        } else {
+            x.geo = geo + gsel * P::GEO_D;
+            const bool interior = cur.ne == NE && cur.nint == NE;
+            if (interior) {
+                uint32_t soff[NSLOT];
+                soff[0] = (uint32_t)cur.c * (uint32_t)(blk * 8) + (uint32_t)lane * 16u;
+#pragma unroll
+                for (int j = 0; j < NE; j++)
+                    soff[1 + j] = (uint32_t)__shfl_sync(0xffffffffu, cur.other, j) * (uint32_t)(blk * 8) + (uint32_t)lane * 16u;
+                auto prefetch = [&](int ch) {
+                    double* st = stages + ((q & 1) ^ 1) * P::STAGE_D;
+                    if (ch + 1 < x.nchunk) hot_stage_off<P::NFLD, NSLOT>(gbs, hbs, soff, ch + 1, st, lane);
+                    else stage_next_item(st);
+                };
+                hot_out_item<PHASE, HAS_H, NE, TW, true>(a, x, cur, stages, P::STAGE_D, q, prefetch);
+            } else {
+                auto prefetch = [&](int ch) {
+                    double* st = stages + ((q & 1) ^ 1) * P::STAGE_D;
+                    if (ch + 1 < x.nchunk) hot_stage<NTOT, NSLOT, false>(sp_cur, cur.ne, ch + 1, st, lane);
+                    else stage_next_item(st);
+                };
+                hot_out_item<PHASE, HAS_H, NE, TW, false>(a, x, cur, stages, P::STAGE_D, q, prefetch);
+            }
+        }
+        cur = nxt; item = nitem; gsel ^= 1;
+    }
+    cp_async_wait<0>();
+}
+
+// -------------------------------------------------------------------------------------------------
+// stage 5 + the cell moments of stage 6: gTilde <- -1/3 gTilde + 4/3 gBarP - dt/V sum_f +-(xi.Sf) g_f
+// (discreteVelocity.C:934-978, fvDVM.C:612-622,712-721).  Streams: gTilde, gBarP, one per face.
+template <bool HAS_H, int NE>
+struct HotUpdPlan {
+    static constexpr int NFLD = HAS_H ? 2 : 1;
+    static constexpr int NSLOT = 2 + NE;
+    static constexpr int STAGE_D = NFLD * NSLOT * HOT_CI * 32;
+    static constexpr int PER_WARP_D = 2 * HOT_PTRS + HOT_STAGES * STAGE_D + 32 * 17;
+    static constexpr size_t PER_WARP = ((size_t)PER_WARP_D * 8 + 127) / 128 * 128;
+    static __host__ __device__ size_t txs_bytes(int ntab) { return ((size_t)(ntab + HOT_CI) * 48 + 127) / 128 * 128; }
+    static __host__ size_t total(int ntab) { return txs_bytes(ntab) + HOT_WARPS * PER_WARP; }
+};
+
+struct HotUpdMeta {
+    int c, e0, ne;
+};
+
+template <bool HAS_H>
+__device__ __forceinline__ void hot_upd_meta(const StepArgs& a, int c, int lane, const double* gts, const double* hts,
+                                             const double* gbs, const double* hbs, const double* gsbs,
+                                             const double* hsbs, int NE, unsigned long long* sp, HotUpdMeta& M) {
+    const DevMesh& m = a.m;
+    const int blk = a.dv.L * 32;
+    const int NSLOT = 2 + NE;
+    M.c = c;
+    M.e0 = m.cell_off[c];
+    M.ne = m.cell_off[c + 1] - M.e0;
+    if (M.ne <= NE && lane < 2 + M.ne) {
+        int o = 0, f = 0;
+        if (lane >= 2) { o = m.e_other[M.e0 + lane - 2]; f = m.e_face[M.e0 + lane - 2]; }
+#pragma unroll
+        for (int fld = 0; fld < (HAS_H ? 2 : 1); fld++) {
+            const double* src;
+            if (lane == 0) src = (fld ? hts : gts) + (size_t)c * blk;
+            else if (lane == 1) src = (fld ? hbs : gbs) + (size_t)c * blk;
+            else if (o >= 0) src = (fld ? a.fbuf_h : a.fbuf_g) + (size_t)f * blk;
+            else src = (fld ? hsbs : gsbs) + (size_t)(-1 - o) * blk;
+            sp[fld * NSLOT + lane] = (unsigned long long)src;
+        }
+    }
+}
+
+template <bool HAS_H, int NE>
+__global__ void __launch_bounds__(HOT_WARPS * 32, 3)
+k_hot_update(StepArgs a) {
+    using P = HotUpdPlan<HAS_H, NE>;
+    constexpr int NSLOT = P::NSLOT, NTOT = P::NFLD * P::NSLOT, CI = HOT_CI;
+    extern __shared__ __align__(128) unsigned char dyn[];
+    const DevDV& dv = a.dv;
+    const int L = dv.L, nc = a.m.nc, blk = L * 32;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double* txs = reinterpret_cast<double*>(dyn);
+    hot_fill_txs(dv, 1.0, txs);
+    unsigned char* wbase = dyn + P::txs_bytes(dv.ntab) + wib * P::PER_WARP;
+    unsigned long long* sptr = reinterpret_cast<unsigned long long*>(wbase);
+    double* stages = reinterpret_cast<double*>(wbase) + 2 * HOT_PTRS;
+    double* red = stages + HOT_STAGES * P::STAGE_D;
+    __syncthreads();
+
+    const size_t slab_c = (size_t)a.slab * nc * blk, slab_b = (size_t)a.slab * a.m.nbf * blk;
+    double* gts = a.gt + slab_c;
+    double* hts = HAS_H ? a.ht + slab_c : nullptr;
+    const double* gbs = a.gb + slab_c;
+    const double* hbs = HAS_H ? a.hb + slab_c : nullptr;
+    const double* gsbs = a.gsb + slab_b;
+    const double* hsbs = HAS_H ? a.hsb + slab_b : nullptr;
+    const int grow = a.slab * 32 + lane;
+    const double y = dv.row_y[grow], z = dv.row_z[grow], wr = dv.row_w[grow];
+    const int cb = dv.row_cbase[grow];
+    const int nchunk = (L + CI - 1) / CI;
+    const int nm = a.nm;
+
+    const int nw = gridDim.x * HOT_WARPS;
+    int item = blockIdx.x * HOT_WARPS + wib;
+    uint32_t q = 0;
+    int gsel = 0;
+    HotUpdMeta cur{}, nxt{};
+    if (item < nc) {
+        hot_upd_meta<HAS_H>(a, item, lane, gts, hts, gbs, hbs, gsbs, hsbs, NE, sptr, cur);
+        __syncwarp();
+        if (cur.ne <= NE) hot_stage<NTOT, NSLOT, false>(sptr, cur.ne + 1, 0, stages, lane);
+        cp_async_commit();
+    }
+    while (item < nc) {
+        const int nitem = item + nw;
+        const bool has_next = nitem < nc;
+        unsigned long long* sp_cur = sptr + gsel * HOT_PTRS;
+        unsigned long long* sp_nxt = sptr + (gsel ^ 1) * HOT_PTRS;
+        if (has_next) hot_upd_meta<HAS_H>(a, nitem, lane, gts, hts, gbs, hbs, gsbs, hsbs, NE, sp_nxt, nxt);
+        __syncwarp();
+        const bool next_ok = has_next && nxt.ne <= NE;
+        if (cur.ne > NE) {
+            __syncwarp();
+            if (next_ok) hot_stage<NTOT, NSLOT, false>(sp_nxt, nxt.ne + 1, 0, stages + (q & 1) * P::STAGE_D, lane);
+            cp_async_commit();
+            cur = nxt; item = nitem; gsel ^= 1;
+            continue;
+        }
+        const int ne = cur.ne, c = cur.c;
+        // outward area vectors of the cell's faces (sign folded in), flux = x*Sx + (y*Sy + z*Sz)
+        double Sx[NE], cyz[NE];
+#pragma unroll
+        for (int j = 0; j < NE; j++) {
+            Sx[j] = 0.0; cyz[j] = 0.0;
+            if (j < ne) {
+                const double* S = a.geoS + (size_t)(cur.e0 + j) * 4;
+                Sx[j] = S[0];
+                cyz[j] = fma(y, S[1], z * S[2]);
+            }
+        }
+        const double dtv = a.dt / a.m.V[c];
+        double A[4] = {0, 0, 0, 0}, B[2] = {0, 0};
+        double* gdst = gts + (size_t)c * blk + lane;
+        double* hdst = HAS_H ? hts + (size_t)c * blk + lane : nullptr;
+        for (int ch = 0; ch < nchunk; ch++) {
+            {
+                double* st = stages + ((q & 1) ^ 1) * P::STAGE_D;
+                if (ch + 1 < nchunk) hot_stage<NTOT, NSLOT, false>(sp_cur, ne + 1, ch + 1, st, lane);
+                else if (next_ok) hot_stage<NTOT, NSLOT, false>(sp_nxt, nxt.ne + 1, 0, st, lane);
+            }
+            cp_async_commit();
+            cp_async_wait<1>();
+            __syncwarp();
+            const double* sg = stages + (q & 1) * P::STAGE_D + lane;
+            const int i0 = ch * CI, tb = cb + i0;
+            double xx[CI], W[CI][4];
+#pragma unroll
+            for (int u = 0; u < CI; u++) {
+                const double2 t0 = lds2(txs + (tb + u) * 6), t1 = lds2(txs + (tb + u) * 6 + 2), t2 = lds2(txs + (tb + u) * 6 + 4);
+                W[u][0] = t0.y; W[u][1] = t1.x; W[u][2] = t1.y; W[u][3] = t2.x; xx[u] = t2.y;
+            }
+#pragma unroll
+            for (int fld = 0; fld < P::NFLD; fld++) {
+                const double* sf = sg + fld * NSLOT * CI * 32;
+                double sum[CI];
+#pragma unroll
+                for (int u = 0; u < CI; u++) sum[u] = 0.0;
+#pragma unroll
+                for (int j = 0; j < NE; j++) {
+                    if (j < ne) {
+#pragma unroll
+                        for (int u = 0; u < CI; u++)
+                            sum[u] = fma(fma(xx[u], Sx[j], cyz[j]), sf[((2 + j) * CI + u) * 32], sum[u]);   // :952-955
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < CI; u++) {
+                    const double vnew = (-1.0 / 3) * sf[u * 32] + (4.0 / 3) * sf[(CI + u) * 32] - sum[u] * dtv;   // :937,952
+                    if (i0 + u >= L) continue;   // tail chunk (warp-uniform)
+                    (fld == 0 ? gdst : hdst)[(i0 + u) * 32] = vnew;
+                    if (fld == 0) {
+                        A[0] = fma(W[u][0], vnew, A[0]); A[1] = fma(W[u][1], vnew, A[1]);
+                        A[2] = fma(W[u][2], vnew, A[2]); A[3] = fma(W[u][3], vnew, A[3]);
+                    } else {
+                        B[0] = fma(W[u][0], vnew, B[0]); B[1] = fma(W[u][1], vnew, B[1]);
+                    }
+                }
+            }
+            __syncwarp();
+            q++;
+        }
+        double vv[16];
+        expand_g(A, wr, y, z, vv);
+        double uu[NM_H] = {0, 0, 0, 0};
+        if (HAS_H) expand_h(B, wr, y, z, uu);
+        vv[13] = uu[0]; vv[14] = uu[1]; vv[15] = uu[2];
+        const double tot = warp_reduce16_smem(vv, red, lane);
+        if (lane < 16 && lane < nm) atomicAdd(a.cslot + (size_t)c * nm + lane, tot);
+        if (HAS_H) {
+            const double t3 = warp_sum(uu[3]);
+            if (lane == 0) atomicAdd(a.cslot + (size_t)c * nm + 16, t3);
+        }
+        cur = nxt; item = nitem; gsel ^= 1;
+    }
+    cp_async_wait<0>();
+}

@@ -41,6 +41,11 @@ struct StepArgs {
     const double *wall_cin;                 // [nbf][nm] incoming-half-space constants per unit rho_w
     const double *wall_in;                  // [nbf] inComingByRho
     double *wall_diag;                      // [nbf][12] qWall(3), stressWall(9)
+    // second-generation kernels (dugks_hot.cuh)
+    const double *geo6;                     // per cell (cell_off[c]+c)*6: [G0(3) 0 0 0] then per face [G'(3) r(3)]
+    const double *geoS;                     // [ne][4] outward-oriented Sf of every (cell, face) entry
+    const uint4 *upw;                       // [nslab][nc][32] upwind range codes (k_build_upwind)
+    double *fcoef;                          // [nf][12] face equilibrium records (k_face_macros)
 };
 
 __device__ __forceinline__ size_t dv_index(const DevDV& dv, int slab, int n_outer, int outer, int i, int r) {
@@ -461,7 +466,7 @@ k_cell_outgoing(StepArgs a) {
 // item = (boundary face, row-warp)
 template <bool HAS_H>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-k_bnd_outgoing(StepArgs a) {
+k_bnd_outgoing(StepArgs a, int far_only) {
     extern __shared__ __align__(16) unsigned char dyn[];
     double* txs = reinterpret_cast<double*>(dyn);
     const DevDV& dv = a.dv;
@@ -479,6 +484,8 @@ k_bnd_outgoing(StepArgs a) {
         int cb = dv.row_cbase[grow];
         int c = a.m.b_owner[b];
         int kind = a.m.b_kind[b];
+        // with the fused cell kernels (dugks_hot.cuh) only the incoming half of far-field patches is left
+        if (far_only && kind != K_FAR_FIELD && kind != K_PRESSURE_IN && kind != K_PRESSURE_OUT) continue;
         int ne = stage_cell(a, c, lane, st);
         const double* Sf = a.m.b_Sf + (size_t)b * 3;
         const double* rr = a.m.b_r + (size_t)b * 3;
@@ -717,6 +724,15 @@ __global__ void k_face_macros(StepArgs a) {
     double out[MAC_N];
     macros_from_moments(a.gas, M, 0.5 * a.dt, out);     // fvDVM.C:493-522
     for (int k = 0; k < MAC_N; k++) a.fmac[(size_t)f * MAC_N + k] = out[k];
+    if (a.fcoef) {
+        // relaxation factor and Shakhov coefficients of updateGHsurf (discreteVelocity.C:867-870)
+        const double hstep = 0.5 * a.dt;
+        const double rf = hstep / (2.0 * out[5] + hstep);
+        const EqCoef e = make_eq(a.gas, out, rf);
+        double* fc = a.fcoef + (size_t)f * 12;
+        fc[0] = e.Ux; fc[1] = e.Uy; fc[2] = e.Uz; fc[3] = e.a; fc[4] = e.pre;
+        fc[5] = e.qx; fc[6] = e.qy; fc[7] = e.qz; fc[8] = 1.0 - rf; fc[9] = e.RT; fc[10] = 0.0; fc[11] = 0.0;
+    }
     if (f >= a.m.nif) {
         int b = f - a.m.nif;
         double* wd = a.wall_diag + (size_t)b * 12;
