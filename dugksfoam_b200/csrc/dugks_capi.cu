@@ -112,7 +112,12 @@ struct dugks_handle {
     size_t tsmem_out1 = 0, tsmem_out2 = 0, tsmem_upd = 0;
     // second-generation kernels (dugks_hot.cuh)
     bool use_hot = true, has_far = false;
-    int hot_ne = 6, hot_grid_out1 = 148, hot_grid_out2 = 148, hot_grid_upd = 148;
+    int hot_ne = 6, hot_grid_out1 = 148, hot_grid_out2 = 148, hot_grid_upd = 148, hot_grid_rlx = 148;
+    size_t hsmem_rlx = 0;
+    // face-storage slabs: phase 1 keeps the reconstructed face values of slabs [0, n_keep) so that
+    // phase 2 is ONE fused relax+update pass for them (no second gradient, no flux-buffer round trip)
+    int n_keep = 0;
+    double *fkeep_g = nullptr, *fkeep_h = nullptr;
     size_t hsmem_out1 = 0, hsmem_out2 = 0, hsmem_upd = 0;
 };
 
@@ -224,6 +229,22 @@ static void launch_hot_update(dugks_handle* h, const StepArgs& a) {
     else if (h->hot_ne == 6) k_hot_update<H, 6><<<h->hot_grid_upd, HOT_WARPS * 32, h->hsmem_upd, h->stream>>>(a);
     else k_hot_update<H, 8><<<h->hot_grid_upd, HOT_WARPS * 32, h->hsmem_upd, h->stream>>>(a);
 }
+template <bool H>
+static void launch_hot_relax(dugks_handle* h, const StepArgs& a) {
+    const int tw = h->tma_tw;
+#define DUGKS_HOT_RLX(NE_, TW_) k_hot_relax_update<H, NE_, TW_><<<h->hot_grid_rlx, HOT_WARPS * 32, h->hsmem_rlx, h->stream>>>(a)
+    if (h->hot_ne == 4) { if (tw == 32) DUGKS_HOT_RLX(4, 32); else DUGKS_HOT_RLX(4, 64); }
+    else if (h->hot_ne == 6) { if (tw == 32) DUGKS_HOT_RLX(6, 32); else DUGKS_HOT_RLX(6, 64); }
+    else { if (tw == 32) DUGKS_HOT_RLX(8, 32); else DUGKS_HOT_RLX(8, 64); }
+#undef DUGKS_HOT_RLX
+}
+template <bool H, int NE, int TW>
+static cudaError_t hot_cfg_rlx(dugks_handle* h, int* occ) {
+    h->hsmem_rlx = HotRelaxPlan<H, NE, TW>::total(h->ntab);
+    cudaError_t e = cudaFuncSetAttribute(k_hot_relax_update<H, NE, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->hsmem_rlx);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_hot_relax_update<H, NE, TW>, HOT_WARPS * 32, h->hsmem_rlx);
+    return e;
+}
 template <int PHASE, bool H, int NE, int TW>
 static cudaError_t hot_attr_out(size_t bytes) {
     return cudaFuncSetAttribute(k_hot_outgoing<PHASE, H, NE, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -232,7 +253,7 @@ template <bool H>
 static int hot_configure(dugks_handle* h) {
     const int ntab = h->ntab, tw = h->tma_tw;
     cudaError_t e = cudaSuccess;
-    int occ[3] = {1, 1, 1};
+    int occ[4] = {1, 1, 1, 1};
 #define DUGKS_HOT_CFG(NE_)                                                                                   \
     do {                                                                                                     \
         h->hsmem_out1 = HotPlan<1, H, NE_, 32>::total(ntab);                                                 \
@@ -247,6 +268,7 @@ static int hot_configure(dugks_handle* h) {
         if (e == cudaSuccess) e = tw == 32 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], k_hot_outgoing<2, H, NE_, 32>, HOT_WARPS * 32, h->hsmem_out2) \
                                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], k_hot_outgoing<2, H, NE_, 64>, HOT_WARPS * 32, h->hsmem_out2); \
         if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], k_hot_update<H, NE_>, HOT_WARPS * 32, h->hsmem_upd); \
+        if (e == cudaSuccess) e = tw == 32 ? hot_cfg_rlx<H, NE_, 32>(h, &occ[3]) : hot_cfg_rlx<H, NE_, 64>(h, &occ[3]); \
     } while (0)
     if (h->hot_ne == 4) DUGKS_HOT_CFG(4);
     else if (h->hot_ne == 6) DUGKS_HOT_CFG(6);
@@ -259,9 +281,10 @@ static int hot_configure(dugks_handle* h) {
     h->hot_grid_out1 = std::max(1, std::min(dev_sms * std::max(occ[0], 1), max_ctas));
     h->hot_grid_out2 = std::max(1, std::min(dev_sms * std::max(occ[1], 1), max_ctas));
     h->hot_grid_upd = std::max(1, std::min(dev_sms * std::max(occ[2], 1), max_ctas));
+    h->hot_grid_rlx = std::max(1, std::min(dev_sms * std::max(occ[3], 1), max_ctas));
     if (getenv("DUGKS_VERBOSE"))
-        fprintf(stderr, "dugks: hot kernels NE=%d smem %zu/%zu/%zu B, CTAs per SM %d/%d/%d\n", h->hot_ne, h->hsmem_out1,
-                h->hsmem_out2, h->hsmem_upd, occ[0], occ[1], occ[2]);
+        fprintf(stderr, "dugks: hot kernels NE=%d smem %zu/%zu/%zu/%zu B, CTAs per SM %d/%d/%d/%d\n", h->hot_ne, h->hsmem_out1,
+                h->hsmem_out2, h->hsmem_upd, h->hsmem_rlx, occ[0], occ[1], occ[2], occ[3]);
     return 0;
 }
 
@@ -277,6 +300,9 @@ static int launch_slab_kernels_phase1(dugks_handle* h, StepArgs a) {
     if (h->use_hot) {
         {
             Timed t(h, 0);
+            const bool keep = a.slab < h->n_keep;
+            a.fkeep_g = keep ? h->fkeep_g : nullptr;
+            a.fkeep_h = keep ? h->fkeep_h : nullptr;
             launch_hot_outgoing<1, H>(h, a);
         }
         if ((rc = check_launch(h, "k_hot_outgoing<1>"))) return rc;
@@ -325,6 +351,15 @@ static int launch_slab_kernels_phase2(dugks_handle* h, StepArgs a) {
         long long bitems = (long long)h->nbf * (h->Rs / 32);
         k_bnd_relax<H><<<grid_for(bitems), WARPS_PER_CTA * 32, 0, h->stream>>>(a);
         if ((rc = check_launch(h, "k_bnd_relax"))) return rc;
+    }
+    if (h->use_hot && a.slab < h->n_keep) {
+        {
+            Timed t(h, 1);
+            a.fkeep_g = h->fkeep_g; a.fkeep_h = h->fkeep_h;
+            launch_hot_relax<H>(h, a);
+        }
+        if ((rc = check_launch(h, "k_hot_relax_update"))) return rc;
+        return 0;
     }
     if (h->use_hot) {
         {
@@ -1015,6 +1050,25 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
         A.upw = d_upw;
     }
 
+    // ---- face-storage slabs: as many as device memory allows (all of them from 2 GPUs up at the
+    // 64^3 x 28^3 size; about half on one GPU).  Cells with too many faces need the flux-buffer path.
+    if (h->use_hot && h->n_big == 0 && nif > 0) {
+        size_t free2 = 0, total2 = 0;
+        CUDAB(cudaMemGetInfo(&free2, &total2));
+        const size_t per_slab = (size_t)nif * L * h->Rs * sizeof(double) * nfld;
+        const size_t reserve = (size_t)3 << 30;   // NCCL buffers, CUDA context growth, caller's own allocations
+        long long fit = free2 > reserve ? (long long)((free2 - reserve) / per_slab) : 0;
+        if (const char* e = getenv("DUGKS_KEEP_SLABS")) fit = std::min<long long>(fit, atoll(e));   // test hook
+        h->n_keep = (int)std::max<long long>(0, std::min<long long>(fit, h->nslab));
+        if (h->n_keep > 0) {
+            TRYB(dev_alloc(h, &h->fkeep_g, (size_t)h->n_keep * nif * L * h->Rs + HOT_PAD, false));
+            if (h->hasH) TRYB(dev_alloc(h, &h->fkeep_h, (size_t)h->n_keep * nif * L * h->Rs + HOT_PAD, false));
+            // tie points are written by one side only and padding rows by nobody: start from zeros
+            CUDAB(cudaMemsetAsync(h->fkeep_g, 0, ((size_t)h->n_keep * nif * L * h->Rs + HOT_PAD) * sizeof(double), h->stream));
+            if (h->hasH) CUDAB(cudaMemsetAsync(h->fkeep_h, 0, ((size_t)h->n_keep * nif * L * h->Rs + HOT_PAD) * sizeof(double), h->stream));
+        }
+    }
+
     // ---- collective backend
     if (nranks > 1 && !h->reduce) {
         if (!par->nccl_unique_id) { fail(h, DUGKS_ERR_COMM, "nRanks = %d needs either a reduce callback or an NCCL unique id", nranks); return bail(DUGKS_ERR_COMM); }
@@ -1255,7 +1309,7 @@ extern "C" int dugks_get_stats(dugks_handle_t* h, dugks_stats_t* out) {
     out->h_elided = h->hasH ? 0 : 1;
     out->n_slabs = h->nslab;
     out->slab_dvs = h->L * h->Rs;
-    out->reserved = 0;
+    out->keep_slabs = h->n_keep;
     return 0;
 }
 

@@ -287,6 +287,8 @@ __device__ __forceinline__ void hot_out_item(const StepArgs& a, const HotCtx& x,
             }
         }
     }
+    double* const fkeep_g = (PHASE == 1 && a.fkeep_g) ? a.fkeep_g + (size_t)a.slab * a.m.nif * blk : nullptr;
+    double* const fkeep_h = (PHASE == 1 && HAS_H && a.fkeep_h) ? a.fkeep_h + (size_t)a.slab * a.m.nif * blk : nullptr;
     // ---- accumulators (PHASE 1) / face equilibrium tables (PHASE 2)
     double accg[NE][4], acch[NE][2];
     double EYZ[NE], YZ2[NE], QYZ[NE];
@@ -370,10 +372,15 @@ __device__ __forceinline__ void hot_out_item(const StepArgs& a, const HotCtx& x,
                 const double r0 = Gr.y, r1 = r12.x, r2 = r12.y;
                 const bool allfull = (allc[j] >> i0) & 1u;                  // warp-uniform
                 if (PHASE == 1) {
+                    // slabs in face-storage mode keep the reconstructed value for the fused relax+update
+                    // kernel: the owner writes unless phi < -VSMALL, then the neighbour does
+                    double* keep = (fld == 0 ? fkeep_g : fkeep_h);
+                    if (keep) keep += (size_t)fbase[j] * blk + i0 * 32 + lane;
                     if (allfull) {
 #pragma unroll
                         for (int u = 0; u < CI; u++) {
                             const double val = fma(r0, gx[u], fma(r1, gy[u], fma(r2, gz[u], base[u])));
+                            if (keep) keep[u * 32] = val;
                             if (fld == 0) {
                                 accg[j][0] = fma(W[u][0], val, accg[j][0]); accg[j][1] = fma(W[u][1], val, accg[j][1]);
                                 accg[j][2] = fma(W[u][2], val, accg[j][2]); accg[j][3] = fma(W[u][3], val, accg[j][3]);
@@ -383,9 +390,11 @@ __device__ __forceinline__ void hot_out_item(const StepArgs& a, const HotCtx& x,
                         }
                     } else {
                         const unsigned fb = full[j] >> i0, tbits = tie[j] >> i0;
+                        const unsigned wbk = ((ownmask >> j) & 1u) ? (fb | tbits) : fb;
 #pragma unroll
                         for (int u = 0; u < CI; u++) {
                             double val = fma(r0, gx[u], fma(r1, gy[u], fma(r2, gz[u], base[u])));
+                            if (keep && ((wbk >> u) & 1u)) keep[u * 32] = val;
                             // this side's share: all of it, half of it on a tie (:513-529), or none
                             const int hi = ((fb >> u) & 1u) ? 0x3ff00000 : (((tbits >> u) & 1u) ? 0x3fe00000 : 0);
                             val *= __hiloint2double(hi, 0);
@@ -745,6 +754,233 @@ k_hot_update(StepArgs a) {
         if (HAS_H) expand_h(B, wr, y, z, uu);
         vv[13] = uu[0]; vv[14] = uu[1]; vv[15] = uu[2];
         const double tot = warp_reduce16_smem(vv, red, lane);
+        if (lane < 16 && lane < nm) atomicAdd(a.cslot + (size_t)c * nm + lane, tot);
+        if (HAS_H) {
+            const double t3 = warp_sum(uu[3]);
+            if (lane == 0) atomicAdd(a.cslot + (size_t)c * nm + 16, t3);
+        }
+        cur = nxt; item = nitem; gsel ^= 1;
+    }
+    cp_async_wait<0>();
+}
+
+// -------------------------------------------------------------------------------------------------
+// Face-storage slabs: stage 4 and stage 5 in one pass.  Every face value gBar_f kept by phase 1 is read
+// by the two cells that share the face; each relaxes it to g_f with the face equilibrium
+// (discreteVelocity.C:867-881) and adds its flux (:934-978).  Boundary-face values come relaxed from
+// k_bnd_relax.  Replaces k_hot_outgoing<2> + k_hot_update and their flux buffer round trip.
+template <bool HAS_H, int NE, int TW>
+struct HotRelaxPlan {
+    static constexpr int NFLD = HAS_H ? 2 : 1;
+    static constexpr int NSLOT = 2 + NE;
+    static constexpr int STAGE_D = NFLD * NSLOT * HOT_CI * 32;
+    static constexpr int PER_WARP_D = 2 * HOT_PTRS + HOT_STAGES * STAGE_D + NE * 4 * TW + NE * 2;
+    static constexpr size_t PER_WARP = ((size_t)PER_WARP_D * 8 + 127) / 128 * 128;
+    static_assert(STAGE_D >= 32 * 17, "stage too small for the moment reduction");
+    static __host__ __device__ size_t txs_bytes(int ntab) { return ((size_t)(ntab + HOT_CI) * 48 + 127) / 128 * 128; }
+    static __host__ size_t total(int ntab) { return txs_bytes(ntab) + HOT_WARPS * PER_WARP; }
+};
+
+struct HotRelaxMeta {
+    int c, e0, ne, nint, face;
+};
+
+template <bool HAS_H>
+__device__ __forceinline__ void hot_relax_meta(const StepArgs& a, int c, int lane, const double* gts, const double* hts,
+                                               const double* gbs, const double* hbs, const double* gsbs,
+                                               const double* hsbs, const double* fk_g, const double* fk_h, int NE,
+                                               unsigned long long* sp, HotRelaxMeta& M) {
+    const DevMesh& m = a.m;
+    const int blk = a.dv.L * 32;
+    const int NSLOT = 2 + NE;
+    M.c = c;
+    M.e0 = m.cell_off[c];
+    M.ne = m.cell_off[c + 1] - M.e0;
+    M.nint = m.cell_nint[c];
+    M.face = 0;
+    if (M.ne <= NE) {
+        if (lane < M.ne) M.face = m.e_face[M.e0 + lane];
+        if (lane < 2 + M.ne) {
+            int o = 0, f = 0;
+            if (lane >= 2) { o = m.e_other[M.e0 + lane - 2]; f = m.e_face[M.e0 + lane - 2]; }
+#pragma unroll
+            for (int fld = 0; fld < (HAS_H ? 2 : 1); fld++) {
+                const double* src;
+                if (lane == 0) src = (fld ? hts : gts) + (size_t)c * blk;
+                else if (lane == 1) src = (fld ? hbs : gbs) + (size_t)c * blk;
+                else if (o >= 0) src = (fld ? fk_h : fk_g) + (size_t)f * blk;
+                else src = (fld ? hsbs : gsbs) + (size_t)(-1 - o) * blk;
+                sp[fld * NSLOT + lane] = (unsigned long long)src;
+            }
+        }
+    }
+}
+
+template <bool HAS_H, int NE, int TW>
+__global__ void __launch_bounds__(HOT_WARPS * 32, 2)
+k_hot_relax_update(StepArgs a) {
+    using P = HotRelaxPlan<HAS_H, NE, TW>;
+    constexpr int NSLOT = P::NSLOT, NTOT = P::NFLD * P::NSLOT, CI = HOT_CI;
+    extern __shared__ __align__(128) unsigned char dyn[];
+    const DevDV& dv = a.dv;
+    const int L = dv.L, nc = a.m.nc, blk = L * 32;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double* txs = reinterpret_cast<double*>(dyn);
+    hot_fill_txs(dv, 1.0, txs);
+    unsigned char* wbase = dyn + P::txs_bytes(dv.ntab) + wib * P::PER_WARP;
+    unsigned long long* sptr = reinterpret_cast<unsigned long long*>(wbase);
+    double* stages = reinterpret_cast<double*>(wbase) + 2 * HOT_PTRS;
+    double* xtab = stages + HOT_STAGES * P::STAGE_D;       // [NE][TW][4]
+    double* unic = xtab + NE * 4 * TW;                     // [NE][2] omrf, RT
+    __syncthreads();
+
+    const size_t slab_c = (size_t)a.slab * nc * blk, slab_b = (size_t)a.slab * a.m.nbf * blk;
+    const size_t slab_f = (size_t)a.slab * a.m.nif * blk;
+    double* gts = a.gt + slab_c;
+    double* hts = HAS_H ? a.ht + slab_c : nullptr;
+    const double* gbs = a.gb + slab_c;
+    const double* hbs = HAS_H ? a.hb + slab_c : nullptr;
+    const double* gsbs = a.gsb + slab_b;
+    const double* hsbs = HAS_H ? a.hsb + slab_b : nullptr;
+    const double* fk_g = a.fkeep_g + slab_f;
+    const double* fk_h = HAS_H ? a.fkeep_h + slab_f : nullptr;
+    const int grow = a.slab * 32 + lane;
+    const double y = dv.row_y[grow], z = dv.row_z[grow], wr = dv.row_w[grow];
+    const int cb = dv.row_cbase[grow];
+    int tmin, span;
+    table_range(dv, cb, tmin, span);
+    const int nchunk = (L + CI - 1) / CI;
+    const int nm = a.nm;
+    const double kd = (double)(a.gas.K + 3 - a.gas.D);
+
+    const int nw = gridDim.x * HOT_WARPS;
+    int item = blockIdx.x * HOT_WARPS + wib;
+    uint32_t q = 0;
+    int gsel = 0;
+    HotRelaxMeta cur{}, nxt{};
+    if (item < nc) {
+        hot_relax_meta<HAS_H>(a, item, lane, gts, hts, gbs, hbs, gsbs, hsbs, fk_g, fk_h, NE, sptr, cur);
+        __syncwarp();
+        if (cur.ne <= NE) hot_stage<NTOT, NSLOT, false>(sptr, cur.ne + 1, 0, stages, lane);
+        cp_async_commit();
+    }
+    while (item < nc) {
+        const int nitem = item + nw;
+        const bool has_next = nitem < nc;
+        unsigned long long* sp_cur = sptr + gsel * HOT_PTRS;
+        unsigned long long* sp_nxt = sptr + (gsel ^ 1) * HOT_PTRS;
+        if (has_next) hot_relax_meta<HAS_H>(a, nitem, lane, gts, hts, gbs, hbs, gsbs, hsbs, fk_g, fk_h, NE, sp_nxt, nxt);
+        __syncwarp();
+        const bool next_ok = has_next && nxt.ne <= NE;
+        if (cur.ne > NE) {
+            if (next_ok) hot_stage<NTOT, NSLOT, false>(sp_nxt, nxt.ne + 1, 0, stages + (q & 1) * P::STAGE_D, lane);
+            cp_async_commit();
+            cur = nxt; item = nitem; gsel ^= 1;
+            continue;
+        }
+        const int ne = cur.ne, nint = cur.nint, c = cur.c;
+        // outward area vectors (sign folded in) and the face equilibria of the internal faces
+        double Sx[NE], cyz[NE], EYZ[NE], YZ2[NE], QYZ[NE];
+#pragma unroll
+        for (int j = 0; j < NE; j++) {
+            Sx[j] = 0.0; cyz[j] = 0.0; EYZ[j] = YZ2[j] = QYZ[j] = 0.0;
+            if (j < ne) {
+                const double* S = a.geoS + (size_t)(cur.e0 + j) * 4;
+                Sx[j] = S[0];
+                cyz[j] = fma(y, S[1], z * S[2]);
+            }
+            if (j < nint) {
+                const int f = __shfl_sync(0xffffffffu, cur.face, j);
+                const double* fc = a.fcoef + (size_t)f * FCOEF_N;
+                const double Ux = fc[0], Uy = fc[1], Uz = fc[2], ia = fc[3], pre = fc[4];
+                const double qx = fc[5], qy = fc[6], qz = fc[7];
+                for (int tt = lane; tt < span; tt += 32) {
+                    const double cx = txs[(tmin + tt) * 6 + 5] - Ux;
+                    const double x2 = cx * cx * ia;
+                    double* xt = xtab + ((size_t)j * TW + tt) * 4;
+                    xt[0] = exp(-0.5 * x2); xt[1] = x2; xt[2] = cx * qx; xt[3] = 0.0;
+                }
+                const double cy = y - Uy, cz = z - Uz;
+                const double yz2 = (cy * cy + cz * cz) * ia;
+                EYZ[j] = pre * exp(-0.5 * yz2);
+                YZ2[j] = yz2 - a.gas.D - 2.0;
+                QYZ[j] = cy * qy + cz * qz;
+                if (lane == 0) { unic[j * 2] = fc[8]; unic[j * 2 + 1] = fc[9]; }
+            }
+        }
+        __syncwarp();
+        const double dtv = a.dt / a.m.V[c];
+        double A[4] = {0, 0, 0, 0}, B[2] = {0, 0};
+        double* gdst = gts + (size_t)c * blk + lane;
+        double* hdst = HAS_H ? hts + (size_t)c * blk + lane : nullptr;
+        for (int ch = 0; ch < nchunk; ch++) {
+            {
+                double* st = stages + ((q & 1) ^ 1) * P::STAGE_D;
+                if (ch + 1 < nchunk) hot_stage<NTOT, NSLOT, false>(sp_cur, ne + 1, ch + 1, st, lane);
+                else if (next_ok) hot_stage<NTOT, NSLOT, false>(sp_nxt, nxt.ne + 1, 0, st, lane);
+            }
+            cp_async_commit();
+            cp_async_wait<1>();
+            __syncwarp();
+            const double* sg = stages + (q & 1) * P::STAGE_D + lane;
+            const int i0 = ch * CI, tb = cb + i0;
+            double xx[CI], W[CI][4];
+#pragma unroll
+            for (int u = 0; u < CI; u++) {
+                const double2 t0 = lds2(txs + (tb + u) * 6), t1 = lds2(txs + (tb + u) * 6 + 2), t2 = lds2(txs + (tb + u) * 6 + 4);
+                W[u][0] = t0.y; W[u][1] = t1.x; W[u][2] = t1.y; W[u][3] = t2.x; xx[u] = t2.y;
+            }
+#pragma unroll
+            for (int fld = 0; fld < P::NFLD; fld++) {
+                const double* sf = sg + fld * NSLOT * CI * 32;
+                double sum[CI];
+#pragma unroll
+                for (int u = 0; u < CI; u++) sum[u] = 0.0;
+#pragma unroll
+                for (int j = 0; j < NE; j++) {
+                    if (j < nint) {
+                        const double omrf = unic[j * 2], frt = unic[j * 2 + 1];
+#pragma unroll
+                        for (int u = 0; u < CI; u++) {
+                            const double* xt = xtab + ((size_t)j * TW + (tb + u - tmin)) * 4;
+                            const double2 x01 = lds2(xt);
+                            const double cc = x01.y + YZ2[j];
+                            const double cq = xt[2] + QYZ[j];
+                            const double gM = x01.x * EYZ[j];
+                            double eq;
+                            if (fld == 0) eq = fma(cq, cc, 1.0) * gM;                                  // :1042
+                            else eq = (kd + cq * ((cc + 2.0) * kd - 2.0 * a.gas.K)) * gM * frt;        // :1043
+                            const double gf = fma(omrf, sf[((2 + j) * CI + u) * 32], eq);             // :880-881
+                            sum[u] = fma(fma(xx[u], Sx[j], cyz[j]), gf, sum[u]);                       // :952-955
+                        }
+                    } else if (j < ne) {
+#pragma unroll
+                        for (int u = 0; u < CI; u++)
+                            sum[u] = fma(fma(xx[u], Sx[j], cyz[j]), sf[((2 + j) * CI + u) * 32], sum[u]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < CI; u++) {
+                    const double vnew = (-1.0 / 3) * sf[u * 32] + (4.0 / 3) * sf[(CI + u) * 32] - sum[u] * dtv;   // :937,952
+                    if (i0 + u >= L) continue;   // tail chunk (warp-uniform)
+                    (fld == 0 ? gdst : hdst)[(i0 + u) * 32] = vnew;
+                    if (fld == 0) {
+                        A[0] = fma(W[u][0], vnew, A[0]); A[1] = fma(W[u][1], vnew, A[1]);
+                        A[2] = fma(W[u][2], vnew, A[2]); A[3] = fma(W[u][3], vnew, A[3]);
+                    } else {
+                        B[0] = fma(W[u][0], vnew, B[0]); B[1] = fma(W[u][1], vnew, B[1]);
+                    }
+                }
+            }
+            __syncwarp();
+            q++;
+        }
+        double vv[16];
+        expand_g(A, wr, y, z, vv);
+        double uu[NM_H] = {0, 0, 0, 0};
+        if (HAS_H) expand_h(B, wr, y, z, uu);
+        vv[13] = uu[0]; vv[14] = uu[1]; vv[15] = uu[2];
+        const double tot = warp_reduce16_smem(vv, stages + ((q & 1) ^ 1) * P::STAGE_D, lane);
         if (lane < 16 && lane < nm) atomicAdd(a.cslot + (size_t)c * nm + lane, tot);
         if (HAS_H) {
             const double t3 = warp_sum(uu[3]);

@@ -46,6 +46,7 @@ struct StepArgs {
     const double *geoS;                     // [ne][4] outward-oriented Sf of every (cell, face) entry
     const uint4 *upw;                       // [nslab][nc][32] upwind range codes (k_build_upwind)
     double *fcoef;                          // [nf][12] face equilibrium records (k_face_macros)
+    double *fkeep_g, *fkeep_h;              // [n_keep_slabs][nif][L][32] reconstructed face values (face-storage slabs) or null
 };
 
 __device__ __forceinline__ size_t dv_index(const DevDV& dv, int slab, int n_outer, int outer, int i, int r) {

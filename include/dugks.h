@@ -284,7 +284,8 @@ typedef struct dugks_stats_t {
     int32_t  h_elided;          /* 1 when h is identically zero and elided  */
     int32_t  n_slabs;           /* DV slabs per phase                       */
     int32_t  slab_dvs;          /* DVs per slab                             */
-    int32_t  reserved;
+    int32_t  keep_slabs;        /* slabs whose face values are kept between the two phases
+                                   (fused relax+update; limited by device memory) */
 } dugks_stats_t;
 
 int dugks_get_stats(dugks_handle_t* h, dugks_stats_t* out);

@@ -98,6 +98,44 @@ def test_boundary_kinds(oracle_lib, name, case):
     dv.close(); orc.close()
 
 
+_PATHS = [
+    ("keep_all", {}),                                   # face-storage slabs: fused relax+update
+    ("keep_none", {"DUGKS_KEEP_SLABS": "0"}),           # flux-buffer path (what one GPU uses when memory is short)
+    ("keep_one", {"DUGKS_KEEP_SLABS": "1"}),            # both kinds of slab in one step
+    ("gen1_tma", {"DUGKS_NO_HOT": "1"}),                # first-generation bulk-copy kernels
+    ("gen1_ldg", {"DUGKS_NO_HOT": "1", "DUGKS_NO_TMA": "1"}),
+    ("generic", {"DUGKS_NO_HOT": "1", "DUGKS_FORCE_GENERIC": "1"}),   # cells with many faces
+]
+
+
+@pytest.mark.parametrize("path,env", _PATHS, ids=[p[0] for p in _PATHS])
+def test_every_kernel_path(oracle_lib, monkeypatch, path, env):
+    """Every device code path that can carry the step gives the oracle's answer."""
+    for k in ("DUGKS_KEEP_SLABS", "DUGKS_NO_HOT", "DUGKS_NO_TMA", "DUGKS_FORCE_GENERIC"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    zoo = [("cavity3d_5_gh8_distort", cs.cavity3d_case(5, 8, distort=0.15, perturb=0.01), False),
+           ("cavity3d_6_gh28", cs.cavity3d_case(6, 28, perturb=0.01), False),      # two slabs
+           ("cavity2d_9_nc9_ties", cs.cavity2d_case(9, 9, quad="NC", perturb=0.01), False),
+           ("tri_8_gh8", cs.tri_cavity_case(8, 8, perturb=0.01), False),
+           ("cavity3d_4_gh8_storeh", cs.cavity3d_case(4, 8, perturb=0.01), True)]
+    for name, case, store_h in zoo:
+        dv = capi.fvDVM(case, store_h=store_h)
+        st = dv.stats()
+        if path == "keep_all":
+            assert st["keep_slabs"] == st["n_slabs"]
+        if path in ("keep_none", "gen1_tma", "gen1_ldg", "generic"):
+            assert st["keep_slabs"] == 0
+        orc = oracle_lib.Oracle(case)
+        dt = case.courant_dt(0.5)
+        for step in range(3):
+            dv.evolution(dt * (1.0 + 0.1 * step))
+            orc.step(dt * (1.0 + 0.1 * step))
+            _compare(dv, orc, case, util.TOL_STEP * (step + 1), f"{path}/{name} step {step + 1}")
+        dv.close(); orc.close()
+
+
 def test_thousand_steps(oracle_lib):
     """1e-9 on rho/U/T/q after 1000 steps (north_star)."""
     case = cs.cavity2d_case(10, 8)
