@@ -42,6 +42,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     src = os.path.join(_HERE, "csrc", "dugks_capi.cu")
     deps = [src, os.path.join(_HERE, "csrc", "dugks_kernels.cuh"), os.path.join(_HERE, "csrc", "dugks_device.cuh"),
             os.path.join(_HERE, "csrc", "dugks_fast.cuh"), os.path.join(_HERE, "csrc", "dugks_tma.cuh"),
+            os.path.join(_HERE, "csrc", "dugks_hot.cuh"),
             os.path.join(_HERE, "..", "include", "dugks.h")]
     if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(d) for d in deps):
         return LIB_PATH
