@@ -211,13 +211,16 @@ static int do_allreduce(dugks_handle* h, double* buf, size_t n) {
 }
 
 // ---- second-generation kernels: NE (faces staged per cell) and TW (equilibrium table stride)
-// are compile-time; create() picks the smallest that fits the mesh / velocity layout
+// are compile-time; create() picks the smallest that fits the mesh / velocity layout.
+// Points per chunk: 4 where the moment accumulators set the register count anyway (2 CTAs/SM),
+// 2 for the table-heavy phase-2 kernels so that they run 3 CTAs/SM (profiles/r01_occupancy_ab.txt)
+constexpr int CI_OUT1 = 4, CI_OUT2 = 2, CI_UPD = 4, CI_RLX = 2;
 template <int PHASE, bool H>
 static void launch_hot_outgoing(dugks_handle* h, const StepArgs& a) {
     const size_t sm = PHASE == 1 ? h->hsmem_out1 : h->hsmem_out2;
     const int tw = PHASE == 1 ? 32 : h->tma_tw;
     const int grid = PHASE == 1 ? h->hot_grid_out1 : h->hot_grid_out2;
-#define DUGKS_HOT_OUT(NE_, TW_) k_hot_outgoing<PHASE, H, NE_, TW_><<<grid, HOT_WARPS * 32, sm, h->stream>>>(a)
+#define DUGKS_HOT_OUT(NE_, TW_) k_hot_outgoing<PHASE, H, NE_, TW_, (PHASE == 1 ? CI_OUT1 : CI_OUT2)><<<grid, HOT_WARPS * 32, sm, h->stream>>>(a)
     if (h->hot_ne == 4) { if (tw == 32) DUGKS_HOT_OUT(4, 32); else DUGKS_HOT_OUT(4, 64); }
     else if (h->hot_ne == 6) { if (tw == 32) DUGKS_HOT_OUT(6, 32); else DUGKS_HOT_OUT(6, 64); }
     else { if (tw == 32) DUGKS_HOT_OUT(8, 32); else DUGKS_HOT_OUT(8, 64); }
@@ -225,14 +228,14 @@ static void launch_hot_outgoing(dugks_handle* h, const StepArgs& a) {
 }
 template <bool H>
 static void launch_hot_update(dugks_handle* h, const StepArgs& a) {
-    if (h->hot_ne == 4) k_hot_update<H, 4><<<h->hot_grid_upd, HOT_WARPS * 32, h->hsmem_upd, h->stream>>>(a);
-    else if (h->hot_ne == 6) k_hot_update<H, 6><<<h->hot_grid_upd, HOT_WARPS * 32, h->hsmem_upd, h->stream>>>(a);
-    else k_hot_update<H, 8><<<h->hot_grid_upd, HOT_WARPS * 32, h->hsmem_upd, h->stream>>>(a);
+    if (h->hot_ne == 4) k_hot_update<H, 4, CI_UPD><<<h->hot_grid_upd, HOT_WARPS * 32, h->hsmem_upd, h->stream>>>(a);
+    else if (h->hot_ne == 6) k_hot_update<H, 6, CI_UPD><<<h->hot_grid_upd, HOT_WARPS * 32, h->hsmem_upd, h->stream>>>(a);
+    else k_hot_update<H, 8, CI_UPD><<<h->hot_grid_upd, HOT_WARPS * 32, h->hsmem_upd, h->stream>>>(a);
 }
 template <bool H>
 static void launch_hot_relax(dugks_handle* h, const StepArgs& a) {
     const int tw = h->tma_tw;
-#define DUGKS_HOT_RLX(NE_, TW_) k_hot_relax_update<H, NE_, TW_><<<h->hot_grid_rlx, HOT_WARPS * 32, h->hsmem_rlx, h->stream>>>(a)
+#define DUGKS_HOT_RLX(NE_, TW_) k_hot_relax_update<H, NE_, TW_, CI_RLX><<<h->hot_grid_rlx, HOT_WARPS * 32, h->hsmem_rlx, h->stream>>>(a)
     if (h->hot_ne == 4) { if (tw == 32) DUGKS_HOT_RLX(4, 32); else DUGKS_HOT_RLX(4, 64); }
     else if (h->hot_ne == 6) { if (tw == 32) DUGKS_HOT_RLX(6, 32); else DUGKS_HOT_RLX(6, 64); }
     else { if (tw == 32) DUGKS_HOT_RLX(8, 32); else DUGKS_HOT_RLX(8, 64); }
@@ -240,14 +243,14 @@ static void launch_hot_relax(dugks_handle* h, const StepArgs& a) {
 }
 template <bool H, int NE, int TW>
 static cudaError_t hot_cfg_rlx(dugks_handle* h, int* occ) {
-    h->hsmem_rlx = HotRelaxPlan<H, NE, TW>::total(h->ntab);
-    cudaError_t e = cudaFuncSetAttribute(k_hot_relax_update<H, NE, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->hsmem_rlx);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_hot_relax_update<H, NE, TW>, HOT_WARPS * 32, h->hsmem_rlx);
+    h->hsmem_rlx = HotRelaxPlan<H, NE, TW, CI_RLX>::total(h->ntab);
+    cudaError_t e = cudaFuncSetAttribute(k_hot_relax_update<H, NE, TW, CI_RLX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->hsmem_rlx);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_hot_relax_update<H, NE, TW, CI_RLX>, HOT_WARPS * 32, h->hsmem_rlx);
     return e;
 }
 template <int PHASE, bool H, int NE, int TW>
 static cudaError_t hot_attr_out(size_t bytes) {
-    return cudaFuncSetAttribute(k_hot_outgoing<PHASE, H, NE, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    return cudaFuncSetAttribute(k_hot_outgoing<PHASE, H, NE, TW, (PHASE == 1 ? CI_OUT1 : CI_OUT2)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 template <bool H>
 static int hot_configure(dugks_handle* h) {
@@ -256,18 +259,18 @@ static int hot_configure(dugks_handle* h) {
     int occ[4] = {1, 1, 1, 1};
 #define DUGKS_HOT_CFG(NE_)                                                                                   \
     do {                                                                                                     \
-        h->hsmem_out1 = HotPlan<1, H, NE_, 32>::total(ntab);                                                 \
-        h->hsmem_out2 = tw == 32 ? HotPlan<2, H, NE_, 32>::total(ntab) : HotPlan<2, H, NE_, 64>::total(ntab); \
-        h->hsmem_upd = HotUpdPlan<H, NE_>::total(ntab);                                                      \
+        h->hsmem_out1 = HotPlan<1, H, NE_, 32, CI_OUT1>::total(ntab);                                                 \
+        h->hsmem_out2 = tw == 32 ? HotPlan<2, H, NE_, 32, CI_OUT2>::total(ntab) : HotPlan<2, H, NE_, 64, CI_OUT2>::total(ntab); \
+        h->hsmem_upd = HotUpdPlan<H, NE_, CI_UPD>::total(ntab);                                                      \
         if (std::max(std::max(h->hsmem_out1, h->hsmem_out2), h->hsmem_upd) > 220 * 1024) { h->use_hot = false; return 0; } \
         e = hot_attr_out<1, H, NE_, 32>(h->hsmem_out1);                                                      \
         if (e == cudaSuccess) e = tw == 32 ? hot_attr_out<2, H, NE_, 32>(h->hsmem_out2) : hot_attr_out<2, H, NE_, 64>(h->hsmem_out2); \
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_hot_update<H, NE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->hsmem_upd); \
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_hot_update<H, NE_, CI_UPD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->hsmem_upd); \
         /* persistent grids: CTAs the SM can hold (registers and shared memory) times the SM count */    \
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], k_hot_outgoing<1, H, NE_, 32>, HOT_WARPS * 32, h->hsmem_out1); \
-        if (e == cudaSuccess) e = tw == 32 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], k_hot_outgoing<2, H, NE_, 32>, HOT_WARPS * 32, h->hsmem_out2) \
-                                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], k_hot_outgoing<2, H, NE_, 64>, HOT_WARPS * 32, h->hsmem_out2); \
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], k_hot_update<H, NE_>, HOT_WARPS * 32, h->hsmem_upd); \
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], k_hot_outgoing<1, H, NE_, 32, CI_OUT1>, HOT_WARPS * 32, h->hsmem_out1); \
+        if (e == cudaSuccess) e = tw == 32 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], k_hot_outgoing<2, H, NE_, 32, CI_OUT2>, HOT_WARPS * 32, h->hsmem_out2) \
+                                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], k_hot_outgoing<2, H, NE_, 64, CI_OUT2>, HOT_WARPS * 32, h->hsmem_out2); \
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], k_hot_update<H, NE_, CI_UPD>, HOT_WARPS * 32, h->hsmem_upd); \
         if (e == cudaSuccess) e = tw == 32 ? hot_cfg_rlx<H, NE_, 32>(h, &occ[3]) : hot_cfg_rlx<H, NE_, 64>(h, &occ[3]); \
     } while (0)
     if (h->hot_ne == 4) DUGKS_HOT_CFG(4);

@@ -18,10 +18,15 @@
 #pragma once
 #include "dugks_tma.cuh"
 
+#ifndef HOT_WARPS
 #define HOT_WARPS 4
-#define HOT_CI 4          // velocity points per chunk (= per bulk copy and per unrolled group)
+#endif
+// velocity points per chunk (= per copy and per unrolled group) are a template parameter CI (2 or 4):
+// 4 amortises the geometry reads best (phase 1, 2 CTAs/SM at ~240 registers); 2 halves the stages
+// and the working set so that the table-heavy phase-2 kernels run 3 CTAs/SM (12 warps)
+#define HOT_CI_MAX 4
 #define HOT_STAGES 2
-#define HOT_PAD (HOT_CI * 32)   // doubles of slack behind every streamed array (tail chunks copy full size)
+#define HOT_PAD (HOT_CI_MAX * 32)   // doubles of slack behind every streamed array (tail chunks copy full size)
 #define FCOEF_N 12        // per-face equilibrium record: Ux Uy Uz a pre qx qy qz omrf RT 0 0
 
 // ---- upwind range codes -----------------------------------------------------------------------
@@ -123,9 +128,8 @@ struct HotMeta {
     uint4 mw;                     // upwind range codes of this (cell, lane)
 };
 
-#ifndef HOT_MINB
-#define HOT_MINB 2      // CTAs per SM the outgoing kernel is compiled for (register budget 65536 / (128 * HOT_MINB))
-#endif
+// CTAs per SM a kernel is compiled for (register budget 65536 / (128 * n)): 2 with CI = 4, 3 with CI = 2
+#define HOT_MINB(CI) ((CI) == 4 ? 2 : 3)
 #define HOT_PTRS 20   // stream pointer table entries per buffer (>= 2 * (2 + 8))
 
 // Reads the CSR entries of cell c; writes the stream sources of phase-1/2 into the pointer table `sp`
@@ -168,38 +172,42 @@ __device__ __forceinline__ void hot_load_meta(const StepArgs& a, int c, int lane
 }
 
 // chunk `ch` of the item whose pointers are in `sp` into `stage`; one commit group (all lanes call)
-template <int NTOT, int NSLOT, bool ALL>
+template <int CI, int NTOT, int NSLOT, bool ALL>
 __device__ __forceinline__ void hot_stage(const unsigned long long* sp, int ne, int ch, double* stage, int lane) {
-    const uint32_t loff = (uint32_t)lane * 16u + (uint32_t)ch * (HOT_CI * 256u);
+    const uint32_t loff = (uint32_t)lane * 16u + (uint32_t)ch * (CI * 256u);
     const uint32_t sdst = smem_u32(stage) + (uint32_t)lane * 16u;
 #pragma unroll
     for (int k = 0; k < NTOT; k++) {
         if (ALL || (k % NSLOT) <= ne) {
             const char* p = reinterpret_cast<const char*>(sp[k]) + loff;
 #pragma unroll
-            for (int part = 0; part < HOT_CI * 256 / 512; part++)
-                cp_async16(sdst + k * (HOT_CI * 256) + part * 512, p + part * 512);
+            for (int part = 0; part < CI * 256 / 512; part++)
+                cp_async16(sdst + k * (CI * 256) + part * 512, p + part * 512);
         }
     }
 }
 
-// interior cells: every stream lives in the same slab array, so 32-bit byte offsets (already including
-// the lane's 16 bytes) in registers replace the pointer table: one 64-bit add + two LDGSTS per stream
-template <int NFLD, int NSLOT>
+// one stream block of a chunk from `base` + off16 * 16 bytes (off16 already holds the lane's 16 bytes)
+template <int CI>
+__device__ __forceinline__ void hot_stage_one(uint32_t sdst, const double* base, uint32_t off16, uint32_t coff) {
+    const char* p = reinterpret_cast<const char*>(base) + (size_t)off16 * 16u + coff;
+#pragma unroll
+    for (int part = 0; part < CI * 256 / 512; part++) cp_async16(sdst + part * 512, p + part * 512);
+}
+
+// interior cells: every stream lives in the same slab array, so 32-bit offsets (16-byte units, already
+// including the lane's 16 bytes) in registers replace the pointer table: one 64-bit multiply-add + CI/2
+// LDGSTS per stream
+template <int CI, int NFLD, int NSLOT>
 __device__ __forceinline__ void hot_stage_off(const double* gbs, const double* hbs, const uint32_t (&soff)[NSLOT],
                                               int ch, double* stage, int lane) {
     const uint32_t sdst = smem_u32(stage) + (uint32_t)lane * 16u;
-    const uint32_t coff = (uint32_t)ch * (HOT_CI * 256u);
+    const uint32_t coff = (uint32_t)ch * (CI * 256u);
 #pragma unroll
     for (int fld = 0; fld < NFLD; fld++) {
-        const char* base = reinterpret_cast<const char*>(fld ? hbs : gbs) + coff;
 #pragma unroll
-        for (int k = 0; k < NSLOT; k++) {
-            const char* p = base + soff[k];
-#pragma unroll
-            for (int part = 0; part < HOT_CI * 256 / 512; part++)
-                cp_async16(sdst + (fld * NSLOT + k) * (HOT_CI * 256) + part * 512, p + part * 512);
-        }
+        for (int k = 0; k < NSLOT; k++)
+            hot_stage_one<CI>(sdst + (fld * NSLOT + k) * (CI * 256), fld ? hbs : gbs, soff[k], coff);
     }
 }
 
@@ -209,24 +217,24 @@ __device__ __forceinline__ void hot_stage_geo(const double* src, int ne, double*
 }
 
 // shared-memory plan of one warp
-template <int PHASE, bool HAS_H, int NE, int TW>
+template <int PHASE, bool HAS_H, int NE, int TW, int CI>
 struct HotPlan {
     static constexpr int NFLD = HAS_H ? 2 : 1;
     static constexpr int NSLOT = 1 + NE;
-    static constexpr int STAGE_D = NFLD * NSLOT * HOT_CI * 32;
+    static constexpr int STAGE_D = NFLD * NSLOT * CI * 32;
     static constexpr int GEO_D = NSLOT * 6;
     // PHASE 1 reduces its moments through the stage that was consumed last (STAGE_D >= 32 * 17)
-    static constexpr int EXTRA_D = (PHASE == 1) ? 0 : (NE * 4 * TW + NE * 2);
-    static_assert(STAGE_D >= 32 * 17, "stage too small for the moment reduction");
+    static constexpr bool RED_IN_STAGE = STAGE_D >= 32 * 17;
+    static constexpr int EXTRA_D = (PHASE == 1) ? (RED_IN_STAGE ? 0 : 32 * 17) : (NE * 4 * TW + NE * 2);
     static constexpr int PER_WARP_D = 2 * HOT_PTRS + 2 * GEO_D + HOT_STAGES * STAGE_D + EXTRA_D;
     static constexpr size_t PER_WARP = ((size_t)PER_WARP_D * 8 + 127) / 128 * 128;
-    static __host__ __device__ size_t txs_bytes(int ntab) { return ((size_t)(ntab + HOT_CI) * 48 + 127) / 128 * 128; }
+    static __host__ __device__ size_t txs_bytes(int ntab) { return ((size_t)(ntab + HOT_CI_MAX) * 48 + 127) / 128 * 128; }
     static __host__ size_t total(int ntab) { return txs_bytes(ntab) + HOT_WARPS * PER_WARP; }
 };
 
 // txs[t] = { -0.5 dt x, W0, W1, W2, W3, x }, zero weights past the table
 __device__ __forceinline__ void hot_fill_txs(const DevDV& dv, double hd, double* txs) {
-    for (int k = threadIdx.x; k < dv.ntab + HOT_CI; k += blockDim.x) {
+    for (int k = threadIdx.x; k < dv.ntab + HOT_CI_MAX; k += blockDim.x) {
         const int kk = min(k, dv.ntab - 1);
         const bool real = k < dv.ntab;
         txs[k * 6 + 0] = hd * dv.tx[kk];
@@ -239,8 +247,15 @@ __device__ __forceinline__ void hot_fill_txs(const DevDV& dv, double hd, double*
 }
 
 // bit 4*ch of the result: some / every point of chunk ch is set in m
-__device__ __forceinline__ unsigned hot_spread_any(unsigned m) { return (m | (m >> 1) | (m >> 2) | (m >> 3)) & 0x11111111u; }
-__device__ __forceinline__ unsigned hot_spread_all(unsigned m) { return (m & (m >> 1) & (m >> 2) & (m >> 3)) & 0x11111111u; }
+template <int CI>
+__device__ __forceinline__ unsigned hot_spread_any(unsigned m) {
+    static_assert(CI == 2 || CI == 4, "CI must be 2 or 4");
+    return CI == 4 ? ((m | (m >> 1) | (m >> 2) | (m >> 3)) & 0x11111111u) : ((m | (m >> 1)) & 0x55555555u);
+}
+template <int CI>
+__device__ __forceinline__ unsigned hot_spread_all(unsigned m) {
+    return CI == 4 ? ((m & (m >> 1) & (m >> 2) & (m >> 3)) & 0x11111111u) : ((m & (m >> 1)) & 0x55555555u);
+}
 
 // per-warp constants of the outgoing kernel
 struct HotCtx {
@@ -256,10 +271,10 @@ struct HotCtx {
 
 // One cell of the outgoing kernel.  INTERIOR: every one of the NE entries is an internal face, so all
 // face predicates are compile-time.  `prefetch(ch)` stages the chunk that follows chunk ch.
-template <int PHASE, bool HAS_H, int NE, int TW, bool INTERIOR, class Prefetch>
+template <int PHASE, bool HAS_H, int NE, int TW, int CI, bool INTERIOR, class Prefetch>
 __device__ __forceinline__ void hot_out_item(const StepArgs& a, const HotCtx& x, const HotMeta& cur,
                                              double* stages, int stage_d, uint32_t& q, Prefetch&& prefetch) {
-    constexpr int CI = HOT_CI, NSLOT = 1 + NE, NFLD = HAS_H ? 2 : 1;
+    constexpr int NSLOT = 1 + NE, NFLD = HAS_H ? 2 : 1;
     const int lane = x.lane, L = x.L, blk = x.blk;
     const int ne = INTERIOR ? NE : cur.ne, nint = INTERIOR ? NE : cur.nint;
     const double* gb_ = x.geo;
@@ -282,8 +297,8 @@ __device__ __forceinline__ void hot_out_item(const StepArgs& a, const HotCtx& x,
                     if ((ownmask >> j) & 1u) full[j] |= tie[j];
                     tie[j] = 0;
                 }
-                anyc[j] = __reduce_or_sync(0xffffffffu, hot_spread_any(full[j] | tie[j]));
-                allc[j] = __reduce_and_sync(0xffffffffu, hot_spread_all(full[j]));
+                anyc[j] = __reduce_or_sync(0xffffffffu, hot_spread_any<CI>(full[j] | tie[j]));
+                allc[j] = __reduce_and_sync(0xffffffffu, hot_spread_all<CI>(full[j]));
             }
         }
     }
@@ -325,7 +340,6 @@ __device__ __forceinline__ void hot_out_item(const StepArgs& a, const HotCtx& x,
         const double* sg = stages + (q & 1) * stage_d;
         const int i0 = ch * CI;
         const int tb = x.cb + i0;
-
 #pragma unroll
         for (int fld = 0; fld < NFLD; fld++) {
             const double* sf = sg + fld * NSLOT * CI * 32 + lane;
@@ -470,7 +484,7 @@ __device__ __forceinline__ void hot_out_item(const StepArgs& a, const HotCtx& x,
                 double uu[NM_H] = {0, 0, 0, 0};
                 if (HAS_H) expand_h(acch[j], x.wr, x.y, x.z, uu);
                 vv[13] = uu[0]; vv[14] = uu[1]; vv[15] = uu[2];
-                const double tot = warp_reduce16_smem(vv, stages + ((q & 1) ^ 1) * stage_d, lane);
+                const double tot = warp_reduce16_smem(vv, stage_d >= 32 * 17 ? stages + ((q & 1) ^ 1) * stage_d : x.red, lane);
                 const size_t slot = (size_t)2 * fbase[j] + (((ownmask >> j) & 1u) ? 0 : 1);
                 // one warp owns a slot per launch: the fire-and-forget add keeps the sum deterministic
                 if (lane < 16 && lane < x.nm) atomicAdd(a.fslot + slot * x.nm + lane, tot);
@@ -487,10 +501,10 @@ __device__ __forceinline__ void hot_out_item(const StepArgs& a, const HotCtx& x,
 // stages 2.1 + 3 (PHASE 1: face moments, boundary-face values, lagged boundary gradient) and
 // stage 4 (PHASE 2: relaxed internal-face values into the slab flux buffer).
 // discreteVelocity.C:412-691 / fvDVM.C:473-516 / discreteVelocity.C:867-881
-template <int PHASE, bool HAS_H, int NE, int TW>
-__global__ void __launch_bounds__(HOT_WARPS * 32, HOT_MINB)
+template <int PHASE, bool HAS_H, int NE, int TW, int CI>
+__global__ void __launch_bounds__(HOT_WARPS * 32, HOT_MINB(CI))
 k_hot_outgoing(StepArgs a) {
-    using P = HotPlan<PHASE, HAS_H, NE, TW>;
+    using P = HotPlan<PHASE, HAS_H, NE, TW, CI>;
     constexpr int NSLOT = P::NSLOT, NTOT = P::NFLD * P::NSLOT;
     extern __shared__ __align__(128) unsigned char dyn[];
     const DevDV& dv = a.dv;
@@ -522,7 +536,7 @@ k_hot_outgoing(StepArgs a) {
     x.tmin = 0; x.span = 0;
     if (PHASE == 2) table_range(dv, x.cb, x.tmin, x.span);
     x.lane = lane; x.L = L; x.blk = blk; x.nm = a.nm;
-    x.nchunk = (L + HOT_CI - 1) / HOT_CI;
+    x.nchunk = (L + CI - 1) / CI;
     x.slab_b = slab_b;
 
     const int nw = gridDim.x * HOT_WARPS;
@@ -534,7 +548,7 @@ k_hot_outgoing(StepArgs a) {
         hot_load_meta<HAS_H>(a, item, lane, gbs, hbs, gam_g, gam_h, NE, sptr, cur);
         __syncwarp();
         if (cur.ne <= NE) {
-            hot_stage<NTOT, NSLOT, false>(sptr, cur.ne, 0, stages, lane);
+            hot_stage<CI, NTOT, NSLOT, false>(sptr, cur.ne, 0, stages, lane);
             hot_stage_geo(a.geo6 + (size_t)(cur.e0 + cur.c) * 6, cur.ne, geo, lane);
         }
         cp_async_commit();
@@ -549,7 +563,7 @@ k_hot_outgoing(StepArgs a) {
         const bool next_ok = has_next && nxt.ne <= NE;
         auto stage_next_item = [&](double* stage) {
             if (next_ok) {
-                hot_stage<NTOT, NSLOT, false>(sp_nxt, nxt.ne, 0, stage, lane);
+                hot_stage<CI, NTOT, NSLOT, false>(sp_nxt, nxt.ne, 0, stage, lane);
                 hot_stage_geo(a.geo6 + (size_t)(nxt.e0 + nxt.c) * 6, nxt.ne, geo + (gsel ^ 1) * P::GEO_D, lane);
             }
         };
@@ -561,24 +575,24 @@ k_hot_outgoing(StepArgs a) {
             x.geo = geo + gsel * P::GEO_D;
             const bool interior = cur.ne == NE && cur.nint == NE;
             if (interior) {
-                uint32_t soff[NSLOT];
-                soff[0] = (uint32_t)cur.c * (uint32_t)(blk * 8) + (uint32_t)lane * 16u;
+                uint32_t soff[NSLOT];   // 16-byte units
+                soff[0] = (uint32_t)cur.c * (uint32_t)(blk / 2) + (uint32_t)lane;
 #pragma unroll
                 for (int j = 0; j < NE; j++)
-                    soff[1 + j] = (uint32_t)__shfl_sync(0xffffffffu, cur.other, j) * (uint32_t)(blk * 8) + (uint32_t)lane * 16u;
+                    soff[1 + j] = (uint32_t)__shfl_sync(0xffffffffu, cur.other, j) * (uint32_t)(blk / 2) + (uint32_t)lane;
                 auto prefetch = [&](int ch) {
                     double* st = stages + ((q & 1) ^ 1) * P::STAGE_D;
-                    if (ch + 1 < x.nchunk) hot_stage_off<P::NFLD, NSLOT>(gbs, hbs, soff, ch + 1, st, lane);
+                    if (ch + 1 < x.nchunk) hot_stage_off<CI, P::NFLD, NSLOT>(gbs, hbs, soff, ch + 1, st, lane);
                     else stage_next_item(st);
                 };
-                hot_out_item<PHASE, HAS_H, NE, TW, true>(a, x, cur, stages, P::STAGE_D, q, prefetch);
+                hot_out_item<PHASE, HAS_H, NE, TW, CI, true>(a, x, cur, stages, P::STAGE_D, q, prefetch);
             } else {
                 auto prefetch = [&](int ch) {
                     double* st = stages + ((q & 1) ^ 1) * P::STAGE_D;
-                    if (ch + 1 < x.nchunk) hot_stage<NTOT, NSLOT, false>(sp_cur, cur.ne, ch + 1, st, lane);
+                    if (ch + 1 < x.nchunk) hot_stage<CI, NTOT, NSLOT, false>(sp_cur, cur.ne, ch + 1, st, lane);
                     else stage_next_item(st);
                 };
-                hot_out_item<PHASE, HAS_H, NE, TW, false>(a, x, cur, stages, P::STAGE_D, q, prefetch);
+                hot_out_item<PHASE, HAS_H, NE, TW, CI, false>(a, x, cur, stages, P::STAGE_D, q, prefetch);
             }
         }
         cur = nxt; item = nitem; gsel ^= 1;
@@ -589,19 +603,19 @@ k_hot_outgoing(StepArgs a) {
 // -------------------------------------------------------------------------------------------------
 // stage 5 + the cell moments of stage 6: gTilde <- -1/3 gTilde + 4/3 gBarP - dt/V sum_f +-(xi.Sf) g_f
 // (discreteVelocity.C:934-978, fvDVM.C:612-622,712-721).  Streams: gTilde, gBarP, one per face.
-template <bool HAS_H, int NE>
+template <bool HAS_H, int NE, int CI>
 struct HotUpdPlan {
     static constexpr int NFLD = HAS_H ? 2 : 1;
     static constexpr int NSLOT = 2 + NE;
-    static constexpr int STAGE_D = NFLD * NSLOT * HOT_CI * 32;
+    static constexpr int STAGE_D = NFLD * NSLOT * CI * 32;
     static constexpr int PER_WARP_D = 2 * HOT_PTRS + HOT_STAGES * STAGE_D + 32 * 17;
     static constexpr size_t PER_WARP = ((size_t)PER_WARP_D * 8 + 127) / 128 * 128;
-    static __host__ __device__ size_t txs_bytes(int ntab) { return ((size_t)(ntab + HOT_CI) * 48 + 127) / 128 * 128; }
+    static __host__ __device__ size_t txs_bytes(int ntab) { return ((size_t)(ntab + HOT_CI_MAX) * 48 + 127) / 128 * 128; }
     static __host__ size_t total(int ntab) { return txs_bytes(ntab) + HOT_WARPS * PER_WARP; }
 };
 
 struct HotUpdMeta {
-    int c, e0, ne;
+    int c, e0, ne, nint, face;
 };
 
 template <bool HAS_H>
@@ -614,6 +628,8 @@ __device__ __forceinline__ void hot_upd_meta(const StepArgs& a, int c, int lane,
     M.c = c;
     M.e0 = m.cell_off[c];
     M.ne = m.cell_off[c + 1] - M.e0;
+    M.nint = m.cell_nint[c];
+    M.face = (M.ne <= NE && lane < M.ne) ? m.e_face[M.e0 + lane] : 0;
     if (M.ne <= NE && lane < 2 + M.ne) {
         int o = 0, f = 0;
         if (lane >= 2) { o = m.e_other[M.e0 + lane - 2]; f = m.e_face[M.e0 + lane - 2]; }
@@ -629,11 +645,11 @@ __device__ __forceinline__ void hot_upd_meta(const StepArgs& a, int c, int lane,
     }
 }
 
-template <bool HAS_H, int NE>
+template <bool HAS_H, int NE, int CI>
 __global__ void __launch_bounds__(HOT_WARPS * 32, 3)
 k_hot_update(StepArgs a) {
-    using P = HotUpdPlan<HAS_H, NE>;
-    constexpr int NSLOT = P::NSLOT, NTOT = P::NFLD * P::NSLOT, CI = HOT_CI;
+    using P = HotUpdPlan<HAS_H, NE, CI>;
+    constexpr int NSLOT = P::NSLOT, NTOT = P::NFLD * P::NSLOT;
     extern __shared__ __align__(128) unsigned char dyn[];
     const DevDV& dv = a.dv;
     const int L = dv.L, nc = a.m.nc, blk = L * 32;
@@ -667,7 +683,7 @@ k_hot_update(StepArgs a) {
     if (item < nc) {
         hot_upd_meta<HAS_H>(a, item, lane, gts, hts, gbs, hbs, gsbs, hsbs, NE, sptr, cur);
         __syncwarp();
-        if (cur.ne <= NE) hot_stage<NTOT, NSLOT, false>(sptr, cur.ne + 1, 0, stages, lane);
+        if (cur.ne <= NE) hot_stage<CI, NTOT, NSLOT, false>(sptr, cur.ne + 1, 0, stages, lane);
         cp_async_commit();
     }
     while (item < nc) {
@@ -680,12 +696,29 @@ k_hot_update(StepArgs a) {
         const bool next_ok = has_next && nxt.ne <= NE;
         if (cur.ne > NE) {
             __syncwarp();
-            if (next_ok) hot_stage<NTOT, NSLOT, false>(sp_nxt, nxt.ne + 1, 0, stages + (q & 1) * P::STAGE_D, lane);
+            if (next_ok) hot_stage<CI, NTOT, NSLOT, false>(sp_nxt, nxt.ne + 1, 0, stages + (q & 1) * P::STAGE_D, lane);
             cp_async_commit();
             cur = nxt; item = nitem; gsel ^= 1;
             continue;
         }
         const int ne = cur.ne, c = cur.c;
+        // interior cells stage from register offsets (16-byte units), see hot_stage_off
+        const bool interior = ne == NE && cur.nint == NE;
+        const uint32_t offc = (uint32_t)c * (uint32_t)(blk / 2) + (uint32_t)lane;
+        uint32_t offf[NE];
+#pragma unroll
+        for (int j = 0; j < NE; j++) offf[j] = (uint32_t)__shfl_sync(0xffffffffu, cur.face, j) * (uint32_t)(blk / 2) + (uint32_t)lane;
+        auto stage_interior = [&](int ch, double* st) {
+            const uint32_t sdst = smem_u32(st) + (uint32_t)lane * 16u, coff = (uint32_t)ch * (CI * 256u);
+#pragma unroll
+            for (int fld = 0; fld < P::NFLD; fld++) {
+                hot_stage_one<CI>(sdst + (fld * NSLOT + 0) * (CI * 256), fld ? hts : gts, offc, coff);
+                hot_stage_one<CI>(sdst + (fld * NSLOT + 1) * (CI * 256), fld ? hbs : gbs, offc, coff);
+#pragma unroll
+                for (int j = 0; j < NE; j++)
+                    hot_stage_one<CI>(sdst + (fld * NSLOT + 2 + j) * (CI * 256), fld ? a.fbuf_h : a.fbuf_g, offf[j], coff);
+            }
+        };
         // outward area vectors of the cell's faces (sign folded in), flux = x*Sx + (y*Sy + z*Sz)
         double Sx[NE], cyz[NE];
 #pragma unroll
@@ -704,8 +737,10 @@ k_hot_update(StepArgs a) {
         for (int ch = 0; ch < nchunk; ch++) {
             {
                 double* st = stages + ((q & 1) ^ 1) * P::STAGE_D;
-                if (ch + 1 < nchunk) hot_stage<NTOT, NSLOT, false>(sp_cur, ne + 1, ch + 1, st, lane);
-                else if (next_ok) hot_stage<NTOT, NSLOT, false>(sp_nxt, nxt.ne + 1, 0, st, lane);
+                if (ch + 1 < nchunk) {
+                    if (interior) stage_interior(ch + 1, st);
+                    else hot_stage<CI, NTOT, NSLOT, false>(sp_cur, ne + 1, ch + 1, st, lane);
+                } else if (next_ok) hot_stage<CI, NTOT, NSLOT, false>(sp_nxt, nxt.ne + 1, 0, st, lane);
             }
             cp_async_commit();
             cp_async_wait<1>();
@@ -769,15 +804,16 @@ k_hot_update(StepArgs a) {
 // by the two cells that share the face; each relaxes it to g_f with the face equilibrium
 // (discreteVelocity.C:867-881) and adds its flux (:934-978).  Boundary-face values come relaxed from
 // k_bnd_relax.  Replaces k_hot_outgoing<2> + k_hot_update and their flux buffer round trip.
-template <bool HAS_H, int NE, int TW>
+template <bool HAS_H, int NE, int TW, int CI>
 struct HotRelaxPlan {
     static constexpr int NFLD = HAS_H ? 2 : 1;
     static constexpr int NSLOT = 2 + NE;
-    static constexpr int STAGE_D = NFLD * NSLOT * HOT_CI * 32;
-    static constexpr int PER_WARP_D = 2 * HOT_PTRS + HOT_STAGES * STAGE_D + NE * 4 * TW + NE * 2;
+    static constexpr int STAGE_D = NFLD * NSLOT * CI * 32;
+    // the moment reduction (32 x 17 doubles) runs through the face tables, which are dead by then
+    static constexpr int TAB_D = (NE * 4 * TW + NE * 2) > 32 * 17 ? (NE * 4 * TW + NE * 2) : 32 * 17;
+    static constexpr int PER_WARP_D = 2 * HOT_PTRS + HOT_STAGES * STAGE_D + TAB_D;
     static constexpr size_t PER_WARP = ((size_t)PER_WARP_D * 8 + 127) / 128 * 128;
-    static_assert(STAGE_D >= 32 * 17, "stage too small for the moment reduction");
-    static __host__ __device__ size_t txs_bytes(int ntab) { return ((size_t)(ntab + HOT_CI) * 48 + 127) / 128 * 128; }
+    static __host__ __device__ size_t txs_bytes(int ntab) { return ((size_t)(ntab + HOT_CI_MAX) * 48 + 127) / 128 * 128; }
     static __host__ size_t total(int ntab) { return txs_bytes(ntab) + HOT_WARPS * PER_WARP; }
 };
 
@@ -816,11 +852,11 @@ __device__ __forceinline__ void hot_relax_meta(const StepArgs& a, int c, int lan
     }
 }
 
-template <bool HAS_H, int NE, int TW>
-__global__ void __launch_bounds__(HOT_WARPS * 32, 2)
+template <bool HAS_H, int NE, int TW, int CI>
+__global__ void __launch_bounds__(HOT_WARPS * 32, HOT_MINB(CI))
 k_hot_relax_update(StepArgs a) {
-    using P = HotRelaxPlan<HAS_H, NE, TW>;
-    constexpr int NSLOT = P::NSLOT, NTOT = P::NFLD * P::NSLOT, CI = HOT_CI;
+    using P = HotRelaxPlan<HAS_H, NE, TW, CI>;
+    constexpr int NSLOT = P::NSLOT, NTOT = P::NFLD * P::NSLOT;
     extern __shared__ __align__(128) unsigned char dyn[];
     const DevDV& dv = a.dv;
     const int L = dv.L, nc = a.m.nc, blk = L * 32;
@@ -861,7 +897,7 @@ k_hot_relax_update(StepArgs a) {
     if (item < nc) {
         hot_relax_meta<HAS_H>(a, item, lane, gts, hts, gbs, hbs, gsbs, hsbs, fk_g, fk_h, NE, sptr, cur);
         __syncwarp();
-        if (cur.ne <= NE) hot_stage<NTOT, NSLOT, false>(sptr, cur.ne + 1, 0, stages, lane);
+        if (cur.ne <= NE) hot_stage<CI, NTOT, NSLOT, false>(sptr, cur.ne + 1, 0, stages, lane);
         cp_async_commit();
     }
     while (item < nc) {
@@ -873,12 +909,29 @@ k_hot_relax_update(StepArgs a) {
         __syncwarp();
         const bool next_ok = has_next && nxt.ne <= NE;
         if (cur.ne > NE) {
-            if (next_ok) hot_stage<NTOT, NSLOT, false>(sp_nxt, nxt.ne + 1, 0, stages + (q & 1) * P::STAGE_D, lane);
+            if (next_ok) hot_stage<CI, NTOT, NSLOT, false>(sp_nxt, nxt.ne + 1, 0, stages + (q & 1) * P::STAGE_D, lane);
             cp_async_commit();
             cur = nxt; item = nitem; gsel ^= 1;
             continue;
         }
         const int ne = cur.ne, nint = cur.nint, c = cur.c;
+        // interior cells stage from register offsets (16-byte units), see hot_stage_off
+        const bool interior = ne == NE && nint == NE;
+        const uint32_t offc = (uint32_t)c * (uint32_t)(blk / 2) + (uint32_t)lane;
+        uint32_t offf[NE];
+#pragma unroll
+        for (int j = 0; j < NE; j++) offf[j] = (uint32_t)__shfl_sync(0xffffffffu, cur.face, j) * (uint32_t)(blk / 2) + (uint32_t)lane;
+        auto stage_interior = [&](int ch, double* st) {
+            const uint32_t sdst = smem_u32(st) + (uint32_t)lane * 16u, coff = (uint32_t)ch * (CI * 256u);
+#pragma unroll
+            for (int fld = 0; fld < P::NFLD; fld++) {
+                hot_stage_one<CI>(sdst + (fld * NSLOT + 0) * (CI * 256), fld ? hts : gts, offc, coff);
+                hot_stage_one<CI>(sdst + (fld * NSLOT + 1) * (CI * 256), fld ? hbs : gbs, offc, coff);
+#pragma unroll
+                for (int j = 0; j < NE; j++)
+                    hot_stage_one<CI>(sdst + (fld * NSLOT + 2 + j) * (CI * 256), fld ? fk_h : fk_g, offf[j], coff);
+            }
+        };
         // outward area vectors (sign folded in) and the face equilibria of the internal faces
         double Sx[NE], cyz[NE], EYZ[NE], YZ2[NE], QYZ[NE];
 #pragma unroll
@@ -916,8 +969,10 @@ k_hot_relax_update(StepArgs a) {
         for (int ch = 0; ch < nchunk; ch++) {
             {
                 double* st = stages + ((q & 1) ^ 1) * P::STAGE_D;
-                if (ch + 1 < nchunk) hot_stage<NTOT, NSLOT, false>(sp_cur, ne + 1, ch + 1, st, lane);
-                else if (next_ok) hot_stage<NTOT, NSLOT, false>(sp_nxt, nxt.ne + 1, 0, st, lane);
+                if (ch + 1 < nchunk) {
+                    if (interior) stage_interior(ch + 1, st);
+                    else hot_stage<CI, NTOT, NSLOT, false>(sp_cur, ne + 1, ch + 1, st, lane);
+                } else if (next_ok) hot_stage<CI, NTOT, NSLOT, false>(sp_nxt, nxt.ne + 1, 0, st, lane);
             }
             cp_async_commit();
             cp_async_wait<1>();
@@ -980,7 +1035,8 @@ k_hot_relax_update(StepArgs a) {
         double uu[NM_H] = {0, 0, 0, 0};
         if (HAS_H) expand_h(B, wr, y, z, uu);
         vv[13] = uu[0]; vv[14] = uu[1]; vv[15] = uu[2];
-        const double tot = warp_reduce16_smem(vv, stages + ((q & 1) ^ 1) * P::STAGE_D, lane);
+        __syncwarp();
+        const double tot = warp_reduce16_smem(vv, xtab, lane);
         if (lane < 16 && lane < nm) atomicAdd(a.cslot + (size_t)c * nm + lane, tot);
         if (HAS_H) {
             const double t3 = warp_sum(uu[3]);
