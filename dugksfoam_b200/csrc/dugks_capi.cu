@@ -837,6 +837,51 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
         b_invdc[b] = 1.0 / mesh->deltaCoeffs[f];
     }
 
+    // ---- axis-aligned cells: every LS vector and face offset of the cell has exactly ONE non-zero
+    // component (exact zeros, as orthogonal hexahedra give), two faces per axis, all internal.  Their
+    // entries are put in axis order (x, x, y, y[, z, z]) so that the kernels can skip the products with
+    // the exact zeros at compile time: the result is bit-identical to the general path.
+    std::vector<unsigned char> cell_cls(nc, 0);
+    {
+        const bool want = getenv("DUGKS_NO_AXIS") == nullptr;   // test hook: general path everywhere
+        std::vector<int> axis_of(MAX_CELL_FACES), order(MAX_CELL_FACES);
+        std::vector<double> tmp_geo(MAX_CELL_FACES * 9);
+        std::vector<int> tmp_i(MAX_CELL_FACES * 3);
+        for (int c = 0; c < nc && want; c++) {
+            const int n_e = cnt[c];
+            if (n_e != cnt_int[c] || (n_e != 4 && n_e != 6)) continue;
+            int per_axis[3] = {0, 0, 0};
+            bool ok = true;
+            for (int j = 0; j < n_e && ok; j++) {
+                const double* g = &e_geo[(size_t)(off[c] + j) * 9];
+                int ax = -1;
+                for (int d = 0; d < 3; d++)
+                    if (g[d] != 0.0 || g[3 + d] != 0.0) { if (ax >= 0 && ax != d) ok = false; ax = d; }
+                if (ax < 0) ok = false;
+                // the flux of the update kernels keeps the general form, so Sf is not constrained
+                if (ok) { axis_of[j] = ax; per_axis[ax]++; }
+            }
+            if (!ok) continue;
+            const int naxes = n_e / 2;
+            for (int d = 0; d < 3; d++) if (per_axis[d] != (d < naxes ? 2 : 0)) ok = false;
+            if (!ok) continue;
+            int k = 0;
+            for (int d = 0; d < 3; d++)
+                for (int j = 0; j < n_e; j++) if (axis_of[j] == d) order[k++] = j;
+            for (int j = 0; j < n_e; j++) {
+                const int e = off[c] + order[j];
+                for (int d = 0; d < 9; d++) tmp_geo[j * 9 + d] = e_geo[(size_t)e * 9 + d];
+                tmp_i[j * 3] = e_other[e]; tmp_i[j * 3 + 1] = e_face[e]; tmp_i[j * 3 + 2] = e_owner[e];
+            }
+            for (int j = 0; j < n_e; j++) {
+                const int e = off[c] + j;
+                for (int d = 0; d < 9; d++) e_geo[(size_t)e * 9 + d] = tmp_geo[j * 9 + d];
+                e_other[e] = tmp_i[j * 3]; e_face[e] = tmp_i[j * 3 + 1]; e_owner[e] = tmp_i[j * 3 + 2];
+            }
+            cell_cls[c] = 1;
+        }
+    }
+
     // ---- upload static data
     StepArgs& A = h->A;
     memset(&A, 0, sizeof A);
@@ -846,6 +891,26 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
     int *d_i; double* d_d;
     TRYB(dev_upload(h, &d_i, off)); M.cell_off = d_i;
     TRYB(dev_upload(h, &d_i, cnt_int)); M.cell_nint = d_i;
+    {
+        unsigned char* d_c = nullptr;
+        TRYB(dev_upload(h, &d_c, cell_cls)); A.cell_cls = d_c;
+        // per-cell record (CMETA_N ints): everything a warp needs to start a cell in one load level
+        std::vector<int> cmeta((size_t)nc * CMETA_N, 0);
+        for (int c = 0; c < nc; c++) {
+            int* rec = &cmeta[(size_t)c * CMETA_N];
+            rec[0] = off[c];
+            rec[1] = (cnt[c] & 0xff) | ((cnt_int[c] & 0xff) << 8) | ((int)cell_cls[c] << 16);
+            unsigned char* kinds = reinterpret_cast<unsigned char*>(rec + 18);
+            for (int j = 0; j < 8; j++) kinds[j] = 0xff;
+            for (int j = 0; j < cnt[c] && j < 8; j++) {
+                const int e = off[c] + j;
+                rec[2 + j] = e_other[e];
+                rec[10 + j] = e_face[e] | (e_owner[e] ? (int)0x80000000u : 0);
+                if (e_other[e] < 0) kinds[j] = (unsigned char)b_kind[-1 - e_other[e]];
+            }
+        }
+        TRYB(dev_upload(h, &d_i, cmeta)); A.cmeta = d_i;
+    }
     TRYB(dev_upload(h, &d_i, e_other)); M.e_other = d_i;
     TRYB(dev_upload(h, &d_i, e_face)); M.e_face = d_i;
     TRYB(dev_upload(h, &d_i, e_owner)); M.e_owner = d_i;

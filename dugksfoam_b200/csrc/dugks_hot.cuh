@@ -123,7 +123,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 // ---- per-warp item bookkeeping ------------------------------------------------------------------
 struct HotMeta {
-    int c, e0, ne, nint;
+    int c, e0, ne, nint, cls;
     int other, face, own, kind;   // lane j < ne: entry j (kind: -1 internal, else patch kind)
     uint4 mw;                     // upwind range codes of this (cell, lane)
 };
@@ -132,28 +132,41 @@ struct HotMeta {
 #define HOT_MINB(CI) ((CI) == 4 ? 2 : 3)
 #define HOT_PTRS 20   // stream pointer table entries per buffer (>= 2 * (2 + 8))
 
-// Reads the CSR entries of cell c; writes the stream sources of phase-1/2 into the pointer table `sp`
+// Per-cell record `cmeta` (20 ints, built by create()): [0] first entry e0, [1] ne | nint << 8 | cls << 16,
+// [2..9] other cell (or -1-b) of entry j, [10..17] face id | owner << 31, [18..19] patch kind bytes
+// (0xff = internal).  One dependency level instead of cell_off -> e_other -> b_kind.
+#define CMETA_N 20
+
+// Issues the loads of cell c's record and upwind codes; nothing is consumed here, so the latency hides
+// behind the cell the warp is working on.
+__device__ __forceinline__ void hot_meta_issue(const StepArgs& a, int c, int lane, HotMeta& M) {
+    const int* rec = a.cmeta + (size_t)c * CMETA_N;
+    const int l8 = lane & 7;
+    M.c = c;
+    M.e0 = rec[0];
+    M.ne = rec[1];                 // packed, unpacked by hot_meta_commit
+    M.other = rec[2 + l8];
+    M.face = rec[10 + l8];         // | owner << 31
+    M.kind = reinterpret_cast<const unsigned char*>(rec + 18)[l8];
+    M.mw = a.upw[((size_t)a.slab * a.m.nc + c) * 32 + lane];
+}
+
+// Unpacks the record and writes the stream sources of phase-1/2 into the pointer table `sp`
 // (slot 0 = own cell, 1+j = entry j; + NSLOT for the h field).
 template <bool HAS_H>
-__device__ __forceinline__ void hot_load_meta(const StepArgs& a, int c, int lane, const double* gbs,
-                                              const double* hbs, const double* gam_g, const double* gam_h,
-                                              int NE, unsigned long long* sp, HotMeta& M) {
-    const DevMesh& m = a.m;
+__device__ __forceinline__ void hot_meta_commit(const StepArgs& a, int lane, const double* gbs, const double* hbs,
+                                                const double* gam_g, const double* gam_h, int NE,
+                                                unsigned long long* sp, HotMeta& M) {
     const int blk = a.dv.L * 32;
     const int NSLOT = 1 + NE;
-    M.c = c;
-    M.e0 = m.cell_off[c];
-    M.ne = m.cell_off[c + 1] - M.e0;
-    M.nint = m.cell_nint[c];
-    M.other = 0; M.face = 0; M.own = 0; M.kind = -1;
-    M.mw = a.upw[((size_t)a.slab * m.nc + c) * 32 + lane];
+    const int pk = M.ne;
+    M.ne = pk & 0xff; M.nint = (pk >> 8) & 0xff; M.cls = (pk >> 16) & 0xff;
+    const bool valid = lane < M.ne && M.ne <= NE;
+    M.own = valid ? (int)((unsigned)M.face >> 31) : 0;
+    M.face = valid ? (M.face & 0x7fffffff) : 0;
+    M.kind = (valid && M.other < 0) ? M.kind : -1;
+    if (!valid) M.other = 0;
     if (M.ne <= NE) {
-        if (lane < M.ne) {
-            M.other = m.e_other[M.e0 + lane];
-            M.face = m.e_face[M.e0 + lane];
-            M.own = m.e_owner[M.e0 + lane];
-            if (M.other < 0) M.kind = m.b_kind[-1 - M.other];
-        }
         // lane j+1 <- entry j
         const int o = __shfl_up_sync(0xffffffffu, M.other, 1), k = __shfl_up_sync(0xffffffffu, M.kind, 1);
         if (lane <= M.ne) {
@@ -161,14 +174,15 @@ __device__ __forceinline__ void hot_load_meta(const StepArgs& a, int c, int lane
             for (int fld = 0; fld < (HAS_H ? 2 : 1); fld++) {
                 const double* cellsrc = fld ? hbs : gbs;
                 const double* src;
-                if (lane == 0) src = cellsrc + (size_t)c * blk;
+                if (lane == 0) src = cellsrc + (size_t)M.c * blk;
                 else if (o >= 0) src = cellsrc + (size_t)o * blk;
-                else if (k == K_SYMMETRY_PLANE) src = cellsrc + (size_t)c * blk;   // G' = 0: any finite data
+                else if (k == K_SYMMETRY_PLANE) src = cellsrc + (size_t)M.c * blk;   // G' = 0: any finite data
                 else src = (fld ? gam_h : gam_g) + (size_t)(-1 - o) * blk;
                 sp[fld * NSLOT + lane] = (unsigned long long)src;
             }
         }
     }
+    __syncwarp();
 }
 
 // chunk `ch` of the item whose pointers are in `sp` into `stage`; one commit group (all lanes call)
@@ -271,12 +285,15 @@ struct HotCtx {
 
 // One cell of the outgoing kernel.  INTERIOR: every one of the NE entries is an internal face, so all
 // face predicates are compile-time.  `prefetch(ch)` stages the chunk that follows chunk ch.
-template <int PHASE, bool HAS_H, int NE, int TW, int CI, bool INTERIOR, class Prefetch>
+// AXIS (implies INTERIOR): entries come in axis order with a single non-zero component each, so the
+// gradient is 2 products per axis and a face value 1 (exact zeros skipped: bit-identical results).
+template <int PHASE, bool HAS_H, int NE, int TW, int CI, bool INTERIOR, bool AXIS, class Prefetch>
 __device__ __forceinline__ void hot_out_item(const StepArgs& a, const HotCtx& x, const HotMeta& cur,
                                              double* stages, int stage_d, uint32_t& q, Prefetch&& prefetch) {
     constexpr int NSLOT = 1 + NE, NFLD = HAS_H ? 2 : 1;
     const int lane = x.lane, L = x.L, blk = x.blk;
-    const int ne = INTERIOR ? NE : cur.ne, nint = INTERIOR ? NE : cur.nint;
+    // INTERIOR: all NE entries exist (compile-time stream count); AXIS additionally: all of them internal
+    const int ne = INTERIOR ? NE : cur.ne, nint = AXIS ? NE : cur.nint;
     const double* gb_ = x.geo;
     const double* txs = x.txs;
     // ---- upwind masks of this (cell, lane) and their warp-uniform per-chunk summaries
@@ -297,8 +314,10 @@ __device__ __forceinline__ void hot_out_item(const StepArgs& a, const HotCtx& x,
                     if ((ownmask >> j) & 1u) full[j] |= tie[j];
                     tie[j] = 0;
                 }
-                anyc[j] = __reduce_or_sync(0xffffffffu, hot_spread_any<CI>(full[j] | tie[j]));
-                allc[j] = __reduce_and_sync(0xffffffffu, hot_spread_all<CI>(full[j]));
+                if (j < nint) {   // boundary entries keep their out-set in full[] but take no part in the face loop
+                    anyc[j] = __reduce_or_sync(0xffffffffu, hot_spread_any<CI>(full[j] | tie[j]));
+                    allc[j] = __reduce_and_sync(0xffffffffu, hot_spread_all<CI>(full[j]));
+                }
             }
         }
     }
@@ -354,9 +373,22 @@ __device__ __forceinline__ void hot_out_item(const StepArgs& a, const HotCtx& x,
                     gx[u] = G01.x * v[u]; gy[u] = G01.y * v[u]; gz[u] = G2 * v[u];
                 }
             }
+            double rax[NE];   // AXIS: the one non-zero component of Cf - C per face
 #pragma unroll
             for (int j = 0; j < NE; j++) {
-                if (j < ne) {
+                rax[j] = 0.0;
+                if (AXIS) {
+                    const int d = j >> 1;
+                    const double G = gb_[6 * (1 + j) + d];
+                    rax[j] = gb_[6 * (1 + j) + 3 + d];
+#pragma unroll
+                    for (int u = 0; u < CI; u++) {
+                        const double sv = sf[((1 + j) * CI + u) * 32];
+                        if (d == 0) gx[u] = fma(G, sv, gx[u]);
+                        else if (d == 1) gy[u] = fma(G, sv, gy[u]);
+                        else gz[u] = fma(G, sv, gz[u]);
+                    }
+                } else if (j < ne) {
                     const double2 G01 = lds2(gb_ + 6 * (1 + j));
                     const double G2 = gb_[6 * (1 + j) + 2];
 #pragma unroll
@@ -371,7 +403,8 @@ __device__ __forceinline__ void hot_out_item(const StepArgs& a, const HotCtx& x,
 #pragma unroll
             for (int u = 0; u < CI; u++) {
                 const double2 t0 = lds2(txs + (tb + u) * 6);
-                base[u] = fma(t0.x, gx[u], fma(x.yh, gy[u], fma(x.zh, gz[u], v[u])));
+                base[u] = (AXIS && NE == 4) ? fma(t0.x, gx[u], fma(x.yh, gy[u], v[u]))
+                                            : fma(t0.x, gx[u], fma(x.yh, gy[u], fma(x.zh, gz[u], v[u])));
                 if (PHASE == 1) {
                     const double2 t1 = lds2(txs + (tb + u) * 6 + 2);
                     W[u][0] = t0.y; W[u][1] = t1.x; W[u][2] = t1.y; W[u][3] = txs[(tb + u) * 6 + 4];
@@ -382,8 +415,16 @@ __device__ __forceinline__ void hot_out_item(const StepArgs& a, const HotCtx& x,
             for (int j = 0; j < NE; j++) {
                 if (j >= nint) continue;
                 if (!((anyc[j] >> i0) & 1u)) continue;                      // warp-uniform
-                const double2 Gr = lds2(gb_ + 6 * (1 + j) + 2), r12 = lds2(gb_ + 6 * (1 + j) + 4);
-                const double r0 = Gr.y, r1 = r12.x, r2 = r12.y;
+                double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+                if (!AXIS) {
+                    const double2 Gr = lds2(gb_ + 6 * (1 + j) + 2), r12 = lds2(gb_ + 6 * (1 + j) + 4);
+                    r0 = Gr.y; r1 = r12.x; r2 = r12.y;
+                }
+                // value at the face centre: base + (Cf - C).grad
+                auto face_val = [&](int u) {
+                    if (AXIS) return fma(rax[j], (j >> 1) == 0 ? gx[u] : ((j >> 1) == 1 ? gy[u] : gz[u]), base[u]);
+                    return fma(r0, gx[u], fma(r1, gy[u], fma(r2, gz[u], base[u])));
+                };
                 const bool allfull = (allc[j] >> i0) & 1u;                  // warp-uniform
                 if (PHASE == 1) {
                     // slabs in face-storage mode keep the reconstructed value for the fused relax+update
@@ -393,7 +434,7 @@ __device__ __forceinline__ void hot_out_item(const StepArgs& a, const HotCtx& x,
                     if (allfull) {
 #pragma unroll
                         for (int u = 0; u < CI; u++) {
-                            const double val = fma(r0, gx[u], fma(r1, gy[u], fma(r2, gz[u], base[u])));
+                            const double val = face_val(u);
                             if (keep) keep[u * 32] = val;
                             if (fld == 0) {
                                 accg[j][0] = fma(W[u][0], val, accg[j][0]); accg[j][1] = fma(W[u][1], val, accg[j][1]);
@@ -407,7 +448,7 @@ __device__ __forceinline__ void hot_out_item(const StepArgs& a, const HotCtx& x,
                         const unsigned wbk = ((ownmask >> j) & 1u) ? (fb | tbits) : fb;
 #pragma unroll
                         for (int u = 0; u < CI; u++) {
-                            double val = fma(r0, gx[u], fma(r1, gy[u], fma(r2, gz[u], base[u])));
+                            double val = face_val(u);
                             if (keep && ((wbk >> u) & 1u)) keep[u * 32] = val;
                             // this side's share: all of it, half of it on a tie (:513-529), or none
                             const int hi = ((fb >> u) & 1u) ? 0x3ff00000 : (((tbits >> u) & 1u) ? 0x3fe00000 : 0);
@@ -426,7 +467,7 @@ __device__ __forceinline__ void hot_out_item(const StepArgs& a, const HotCtx& x,
                     const unsigned wb = full[j] >> i0;
 #pragma unroll
                     for (int u = 0; u < CI; u++) {
-                        const double val = fma(r0, gx[u], fma(r1, gy[u], fma(r2, gz[u], base[u])));
+                        const double val = face_val(u);
                         const double* xt = x.xtab + ((size_t)j * TW + (tb + u - x.tmin)) * 4;
                         const double2 x01 = lds2(xt);
                         const double cc = x01.y + YZ2[j];
@@ -441,7 +482,7 @@ __device__ __forceinline__ void hot_out_item(const StepArgs& a, const HotCtx& x,
             }
             // ---- boundary faces of this cell (PHASE 1): lagged normal gradient (:436-470) and the
             // outgoing half of the patch rules (:533-690)
-            if (!INTERIOR && PHASE == 1 && nint < ne) {
+            if (!AXIS && PHASE == 1 && nint < ne) {
                 for (int j = nint; j < ne; j++) {
                     const int kind = __shfl_sync(0xffffffffu, cur.kind, j);
                     const int b = -1 - __shfl_sync(0xffffffffu, cur.other, j);
@@ -545,8 +586,8 @@ k_hot_outgoing(StepArgs a) {
     int gsel = 0;          // pointer / geometry buffer of the current item
     HotMeta cur{}, nxt{};
     if (item < nc) {
-        hot_load_meta<HAS_H>(a, item, lane, gbs, hbs, gam_g, gam_h, NE, sptr, cur);
-        __syncwarp();
+        hot_meta_issue(a, item, lane, cur);
+        hot_meta_commit<HAS_H>(a, lane, gbs, hbs, gam_g, gam_h, NE, sptr, cur);
         if (cur.ne <= NE) {
             hot_stage<CI, NTOT, NSLOT, false>(sptr, cur.ne, 0, stages, lane);
             hot_stage_geo(a.geo6 + (size_t)(cur.e0 + cur.c) * 6, cur.ne, geo, lane);
@@ -558,10 +599,14 @@ k_hot_outgoing(StepArgs a) {
         const bool has_next = nitem < nc;
         unsigned long long* sp_cur = sptr + gsel * HOT_PTRS;
         unsigned long long* sp_nxt = sptr + (gsel ^ 1) * HOT_PTRS;
-        if (has_next) hot_load_meta<HAS_H>(a, nitem, lane, gbs, hbs, gam_g, gam_h, NE, sp_nxt, nxt);
-        __syncwarp();
-        const bool next_ok = has_next && nxt.ne <= NE;
+        if (has_next) hot_meta_issue(a, nitem, lane, nxt);
+        bool next_ok = false;
+        // called once, right before the last chunk of the current cell is computed
         auto stage_next_item = [&](double* stage) {
+            if (has_next) {
+                hot_meta_commit<HAS_H>(a, lane, gbs, hbs, gam_g, gam_h, NE, sp_nxt, nxt);
+                next_ok = nxt.ne <= NE;
+            }
             if (next_ok) {
                 hot_stage<CI, NTOT, NSLOT, false>(sp_nxt, nxt.ne, 0, stage, lane);
                 hot_stage_geo(a.geo6 + (size_t)(nxt.e0 + nxt.c) * 6, nxt.ne, geo + (gsel ^ 1) * P::GEO_D, lane);
@@ -574,7 +619,7 @@ k_hot_outgoing(StepArgs a) {
         } else {
             x.geo = geo + gsel * P::GEO_D;
             const bool interior = cur.ne == NE && cur.nint == NE;
-            if (interior) {
+            if (interior && cur.cls && (NE == 4 || NE == 6)) {
                 uint32_t soff[NSLOT];   // 16-byte units
                 soff[0] = (uint32_t)cur.c * (uint32_t)(blk / 2) + (uint32_t)lane;
 #pragma unroll
@@ -585,14 +630,30 @@ k_hot_outgoing(StepArgs a) {
                     if (ch + 1 < x.nchunk) hot_stage_off<CI, P::NFLD, NSLOT>(gbs, hbs, soff, ch + 1, st, lane);
                     else stage_next_item(st);
                 };
-                hot_out_item<PHASE, HAS_H, NE, TW, CI, true>(a, x, cur, stages, P::STAGE_D, q, prefetch);
+                hot_out_item<PHASE, HAS_H, NE, TW, CI, true, (NE == 4 || NE == 6)>(a, x, cur, stages, P::STAGE_D, q, prefetch);
+            } else if (cur.ne == NE) {
+                // all NE entries exist; boundary entries (if any) stream the lagged gradient from another
+                // array, so only all-internal cells can use the register offsets
+                uint32_t soff[NSLOT];   // 16-byte units
+                soff[0] = (uint32_t)cur.c * (uint32_t)(blk / 2) + (uint32_t)lane;
+#pragma unroll
+                for (int j = 0; j < NE; j++)
+                    soff[1 + j] = (uint32_t)__shfl_sync(0xffffffffu, cur.other, j) * (uint32_t)(blk / 2) + (uint32_t)lane;
+                auto prefetch = [&](int ch) {
+                    double* st = stages + ((q & 1) ^ 1) * P::STAGE_D;
+                    if (ch + 1 < x.nchunk) {
+                        if (interior) hot_stage_off<CI, P::NFLD, NSLOT>(gbs, hbs, soff, ch + 1, st, lane);
+                        else hot_stage<CI, NTOT, NSLOT, true>(sp_cur, NE, ch + 1, st, lane);
+                    } else stage_next_item(st);
+                };
+                hot_out_item<PHASE, HAS_H, NE, TW, CI, true, false>(a, x, cur, stages, P::STAGE_D, q, prefetch);
             } else {
                 auto prefetch = [&](int ch) {
                     double* st = stages + ((q & 1) ^ 1) * P::STAGE_D;
                     if (ch + 1 < x.nchunk) hot_stage<CI, NTOT, NSLOT, false>(sp_cur, cur.ne, ch + 1, st, lane);
                     else stage_next_item(st);
                 };
-                hot_out_item<PHASE, HAS_H, NE, TW, CI, false>(a, x, cur, stages, P::STAGE_D, q, prefetch);
+                hot_out_item<PHASE, HAS_H, NE, TW, CI, false, false>(a, x, cur, stages, P::STAGE_D, q, prefetch);
             }
         }
         cur = nxt; item = nitem; gsel ^= 1;
@@ -615,34 +676,45 @@ struct HotUpdPlan {
 };
 
 struct HotUpdMeta {
-    int c, e0, ne, nint, face;
+    int c, e0, ne, nint, face;   // face: lane j < ne: face id of entry j
+    int so, sf;                  // this lane's stream slot (lane - 2): other cell / face id of that entry
 };
 
+// loads only (see hot_meta_issue)
+__device__ __forceinline__ void hot_upd_issue(const StepArgs& a, int c, int lane, HotUpdMeta& M) {
+    const int* rec = a.cmeta + (size_t)c * CMETA_N;
+    M.c = c;
+    M.e0 = rec[0];
+    M.ne = rec[1];
+    M.face = rec[10 + (lane & 7)];
+    M.so = rec[2 + ((lane - 2) & 7)];
+    M.sf = rec[10 + ((lane - 2) & 7)];
+}
+
+// fsrc_g/h: where internal-face values come from (flux buffer or kept face values of the slab)
 template <bool HAS_H>
-__device__ __forceinline__ void hot_upd_meta(const StepArgs& a, int c, int lane, const double* gts, const double* hts,
-                                             const double* gbs, const double* hbs, const double* gsbs,
-                                             const double* hsbs, int NE, unsigned long long* sp, HotUpdMeta& M) {
-    const DevMesh& m = a.m;
+__device__ __forceinline__ void hot_upd_commit(const StepArgs& a, int lane, const double* gts, const double* hts,
+                                               const double* gbs, const double* hbs, const double* gsbs,
+                                               const double* hsbs, const double* fsrc_g, const double* fsrc_h, int NE,
+                                               unsigned long long* sp, HotUpdMeta& M) {
     const int blk = a.dv.L * 32;
     const int NSLOT = 2 + NE;
-    M.c = c;
-    M.e0 = m.cell_off[c];
-    M.ne = m.cell_off[c + 1] - M.e0;
-    M.nint = m.cell_nint[c];
-    M.face = (M.ne <= NE && lane < M.ne) ? m.e_face[M.e0 + lane] : 0;
+    const int pk = M.ne;
+    M.ne = pk & 0xff; M.nint = (pk >> 8) & 0xff;
+    M.face = (lane < M.ne && M.ne <= NE) ? (M.face & 0x7fffffff) : 0;
     if (M.ne <= NE && lane < 2 + M.ne) {
-        int o = 0, f = 0;
-        if (lane >= 2) { o = m.e_other[M.e0 + lane - 2]; f = m.e_face[M.e0 + lane - 2]; }
+        const int o = M.so, f = M.sf & 0x7fffffff;
 #pragma unroll
         for (int fld = 0; fld < (HAS_H ? 2 : 1); fld++) {
             const double* src;
-            if (lane == 0) src = (fld ? hts : gts) + (size_t)c * blk;
-            else if (lane == 1) src = (fld ? hbs : gbs) + (size_t)c * blk;
-            else if (o >= 0) src = (fld ? a.fbuf_h : a.fbuf_g) + (size_t)f * blk;
+            if (lane == 0) src = (fld ? hts : gts) + (size_t)M.c * blk;
+            else if (lane == 1) src = (fld ? hbs : gbs) + (size_t)M.c * blk;
+            else if (o >= 0) src = (fld ? fsrc_h : fsrc_g) + (size_t)f * blk;
             else src = (fld ? hsbs : gsbs) + (size_t)(-1 - o) * blk;
             sp[fld * NSLOT + lane] = (unsigned long long)src;
         }
     }
+    __syncwarp();
 }
 
 template <bool HAS_H, int NE, int CI>
@@ -681,8 +753,8 @@ k_hot_update(StepArgs a) {
     int gsel = 0;
     HotUpdMeta cur{}, nxt{};
     if (item < nc) {
-        hot_upd_meta<HAS_H>(a, item, lane, gts, hts, gbs, hbs, gsbs, hsbs, NE, sptr, cur);
-        __syncwarp();
+        hot_upd_issue(a, item, lane, cur);
+        hot_upd_commit<HAS_H>(a, lane, gts, hts, gbs, hbs, gsbs, hsbs, a.fbuf_g, a.fbuf_h, NE, sptr, cur);
         if (cur.ne <= NE) hot_stage<CI, NTOT, NSLOT, false>(sptr, cur.ne + 1, 0, stages, lane);
         cp_async_commit();
     }
@@ -691,12 +763,15 @@ k_hot_update(StepArgs a) {
         const bool has_next = nitem < nc;
         unsigned long long* sp_cur = sptr + gsel * HOT_PTRS;
         unsigned long long* sp_nxt = sptr + (gsel ^ 1) * HOT_PTRS;
-        if (has_next) hot_upd_meta<HAS_H>(a, nitem, lane, gts, hts, gbs, hbs, gsbs, hsbs, NE, sp_nxt, nxt);
-        __syncwarp();
-        const bool next_ok = has_next && nxt.ne <= NE;
+        if (has_next) hot_upd_issue(a, nitem, lane, nxt);
+        // called once, right before the last chunk of the current cell is computed
+        auto stage_next_item = [&](double* st) {
+            if (!has_next) return;
+            hot_upd_commit<HAS_H>(a, lane, gts, hts, gbs, hbs, gsbs, hsbs, a.fbuf_g, a.fbuf_h, NE, sp_nxt, nxt);
+            if (nxt.ne <= NE) hot_stage<CI, NTOT, NSLOT, false>(sp_nxt, nxt.ne + 1, 0, st, lane);
+        };
         if (cur.ne > NE) {
-            __syncwarp();
-            if (next_ok) hot_stage<CI, NTOT, NSLOT, false>(sp_nxt, nxt.ne + 1, 0, stages + (q & 1) * P::STAGE_D, lane);
+            stage_next_item(stages + (q & 1) * P::STAGE_D);
             cp_async_commit();
             cur = nxt; item = nitem; gsel ^= 1;
             continue;
@@ -740,7 +815,7 @@ k_hot_update(StepArgs a) {
                 if (ch + 1 < nchunk) {
                     if (interior) stage_interior(ch + 1, st);
                     else hot_stage<CI, NTOT, NSLOT, false>(sp_cur, ne + 1, ch + 1, st, lane);
-                } else if (next_ok) hot_stage<CI, NTOT, NSLOT, false>(sp_nxt, nxt.ne + 1, 0, st, lane);
+                } else stage_next_item(st);
             }
             cp_async_commit();
             cp_async_wait<1>();
@@ -817,41 +892,6 @@ struct HotRelaxPlan {
     static __host__ size_t total(int ntab) { return txs_bytes(ntab) + HOT_WARPS * PER_WARP; }
 };
 
-struct HotRelaxMeta {
-    int c, e0, ne, nint, face;
-};
-
-template <bool HAS_H>
-__device__ __forceinline__ void hot_relax_meta(const StepArgs& a, int c, int lane, const double* gts, const double* hts,
-                                               const double* gbs, const double* hbs, const double* gsbs,
-                                               const double* hsbs, const double* fk_g, const double* fk_h, int NE,
-                                               unsigned long long* sp, HotRelaxMeta& M) {
-    const DevMesh& m = a.m;
-    const int blk = a.dv.L * 32;
-    const int NSLOT = 2 + NE;
-    M.c = c;
-    M.e0 = m.cell_off[c];
-    M.ne = m.cell_off[c + 1] - M.e0;
-    M.nint = m.cell_nint[c];
-    M.face = 0;
-    if (M.ne <= NE) {
-        if (lane < M.ne) M.face = m.e_face[M.e0 + lane];
-        if (lane < 2 + M.ne) {
-            int o = 0, f = 0;
-            if (lane >= 2) { o = m.e_other[M.e0 + lane - 2]; f = m.e_face[M.e0 + lane - 2]; }
-#pragma unroll
-            for (int fld = 0; fld < (HAS_H ? 2 : 1); fld++) {
-                const double* src;
-                if (lane == 0) src = (fld ? hts : gts) + (size_t)c * blk;
-                else if (lane == 1) src = (fld ? hbs : gbs) + (size_t)c * blk;
-                else if (o >= 0) src = (fld ? fk_h : fk_g) + (size_t)f * blk;
-                else src = (fld ? hsbs : gsbs) + (size_t)(-1 - o) * blk;
-                sp[fld * NSLOT + lane] = (unsigned long long)src;
-            }
-        }
-    }
-}
-
 template <bool HAS_H, int NE, int TW, int CI>
 __global__ void __launch_bounds__(HOT_WARPS * 32, HOT_MINB(CI))
 k_hot_relax_update(StepArgs a) {
@@ -893,10 +933,10 @@ k_hot_relax_update(StepArgs a) {
     int item = blockIdx.x * HOT_WARPS + wib;
     uint32_t q = 0;
     int gsel = 0;
-    HotRelaxMeta cur{}, nxt{};
+    HotUpdMeta cur{}, nxt{};
     if (item < nc) {
-        hot_relax_meta<HAS_H>(a, item, lane, gts, hts, gbs, hbs, gsbs, hsbs, fk_g, fk_h, NE, sptr, cur);
-        __syncwarp();
+        hot_upd_issue(a, item, lane, cur);
+        hot_upd_commit<HAS_H>(a, lane, gts, hts, gbs, hbs, gsbs, hsbs, fk_g, fk_h, NE, sptr, cur);
         if (cur.ne <= NE) hot_stage<CI, NTOT, NSLOT, false>(sptr, cur.ne + 1, 0, stages, lane);
         cp_async_commit();
     }
@@ -905,11 +945,15 @@ k_hot_relax_update(StepArgs a) {
         const bool has_next = nitem < nc;
         unsigned long long* sp_cur = sptr + gsel * HOT_PTRS;
         unsigned long long* sp_nxt = sptr + (gsel ^ 1) * HOT_PTRS;
-        if (has_next) hot_relax_meta<HAS_H>(a, nitem, lane, gts, hts, gbs, hbs, gsbs, hsbs, fk_g, fk_h, NE, sp_nxt, nxt);
-        __syncwarp();
-        const bool next_ok = has_next && nxt.ne <= NE;
+        if (has_next) hot_upd_issue(a, nitem, lane, nxt);
+        // called once, right before the last chunk of the current cell is computed
+        auto stage_next_item = [&](double* st) {
+            if (!has_next) return;
+            hot_upd_commit<HAS_H>(a, lane, gts, hts, gbs, hbs, gsbs, hsbs, fk_g, fk_h, NE, sp_nxt, nxt);
+            if (nxt.ne <= NE) hot_stage<CI, NTOT, NSLOT, false>(sp_nxt, nxt.ne + 1, 0, st, lane);
+        };
         if (cur.ne > NE) {
-            if (next_ok) hot_stage<CI, NTOT, NSLOT, false>(sp_nxt, nxt.ne + 1, 0, stages + (q & 1) * P::STAGE_D, lane);
+            stage_next_item(stages + (q & 1) * P::STAGE_D);
             cp_async_commit();
             cur = nxt; item = nitem; gsel ^= 1;
             continue;
@@ -972,7 +1016,7 @@ k_hot_relax_update(StepArgs a) {
                 if (ch + 1 < nchunk) {
                     if (interior) stage_interior(ch + 1, st);
                     else hot_stage<CI, NTOT, NSLOT, false>(sp_cur, ne + 1, ch + 1, st, lane);
-                } else if (next_ok) hot_stage<CI, NTOT, NSLOT, false>(sp_nxt, nxt.ne + 1, 0, st, lane);
+                } else stage_next_item(st);
             }
             cp_async_commit();
             cp_async_wait<1>();

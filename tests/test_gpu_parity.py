@@ -102,6 +102,8 @@ _PATHS = [
     ("keep_all", {}),                                   # face-storage slabs: fused relax+update
     ("keep_none", {"DUGKS_KEEP_SLABS": "0"}),           # flux-buffer path (what one GPU uses when memory is short)
     ("keep_one", {"DUGKS_KEEP_SLABS": "1"}),            # both kinds of slab in one step
+    ("no_axis", {"DUGKS_NO_AXIS": "1"}),                # general path also for axis-aligned cells
+    ("no_axis_keep_none", {"DUGKS_NO_AXIS": "1", "DUGKS_KEEP_SLABS": "0"}),
     ("gen1_tma", {"DUGKS_NO_HOT": "1"}),                # first-generation bulk-copy kernels
     ("gen1_ldg", {"DUGKS_NO_HOT": "1", "DUGKS_NO_TMA": "1"}),
     ("generic", {"DUGKS_NO_HOT": "1", "DUGKS_FORCE_GENERIC": "1"}),   # cells with many faces
@@ -111,7 +113,7 @@ _PATHS = [
 @pytest.mark.parametrize("path,env", _PATHS, ids=[p[0] for p in _PATHS])
 def test_every_kernel_path(oracle_lib, monkeypatch, path, env):
     """Every device code path that can carry the step gives the oracle's answer."""
-    for k in ("DUGKS_KEEP_SLABS", "DUGKS_NO_HOT", "DUGKS_NO_TMA", "DUGKS_FORCE_GENERIC"):
+    for k in ("DUGKS_KEEP_SLABS", "DUGKS_NO_HOT", "DUGKS_NO_TMA", "DUGKS_FORCE_GENERIC", "DUGKS_NO_AXIS"):
         monkeypatch.delenv(k, raising=False)
     for k, v in env.items():
         monkeypatch.setenv(k, v)
@@ -125,7 +127,7 @@ def test_every_kernel_path(oracle_lib, monkeypatch, path, env):
         st = dv.stats()
         if path == "keep_all":
             assert st["keep_slabs"] == st["n_slabs"]
-        if path in ("keep_none", "gen1_tma", "gen1_ldg", "generic"):
+        if path in ("keep_none", "gen1_tma", "gen1_ldg", "generic", "no_axis_keep_none"):
             assert st["keep_slabs"] == 0
         orc = oracle_lib.Oracle(case)
         dt = case.courant_dt(0.5)
