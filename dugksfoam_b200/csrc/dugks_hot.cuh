@@ -16,6 +16,8 @@
 //     cell while they finish the current one, so the copy engine never idles at cell boundaries;
 //   * face equilibria of phase 2 come from per-face coefficient records written by k_face_macros.
 #pragma once
+#include <type_traits>
+
 #include "dugks_tma.cuh"
 
 #ifndef HOT_WARPS
@@ -121,6 +123,30 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// Loads that must be ISSUED where they are written (the next cell's record, long before its use): as
+// plain C++ the compiler sinks them to their first use to save registers, which puts the full memory
+// latency back on the critical path (profiles/r01_ncu_summary_r3c.txt).  Read-only data only (.nc).
+__device__ __forceinline__ int ldg_early(const int* p) {
+    int v;
+    asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int2 ldg_early2(const int* p) {
+    int2 v;
+    asm volatile("ld.global.nc.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int ldg_early_u8(const unsigned char* p) {
+    int v;
+    asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint4 ldg_early4(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
 // ---- per-warp item bookkeeping ------------------------------------------------------------------
 struct HotMeta {
     int c, e0, ne, nint, cls;
@@ -143,12 +169,13 @@ __device__ __forceinline__ void hot_meta_issue(const StepArgs& a, int c, int lan
     const int* rec = a.cmeta + (size_t)c * CMETA_N;
     const int l8 = lane & 7;
     M.c = c;
-    M.e0 = rec[0];
-    M.ne = rec[1];                 // packed, unpacked by hot_meta_commit
-    M.other = rec[2 + l8];
-    M.face = rec[10 + l8];         // | owner << 31
-    M.kind = reinterpret_cast<const unsigned char*>(rec + 18)[l8];
-    M.mw = a.upw[((size_t)a.slab * a.m.nc + c) * 32 + lane];
+    const int2 h2 = ldg_early2(rec);
+    M.e0 = h2.x;
+    M.ne = h2.y;                   // packed, unpacked by hot_meta_commit
+    M.other = ldg_early(rec + 2 + l8);
+    M.face = ldg_early(rec + 10 + l8);         // | owner << 31
+    M.kind = ldg_early_u8(reinterpret_cast<const unsigned char*>(rec + 18) + l8);
+    M.mw = ldg_early4(a.upw + ((size_t)a.slab * a.m.nc + c) * 32 + lane);
 }
 
 // Unpacks the record and writes the stream sources of phase-1/2 into the pointer table `sp`
@@ -684,11 +711,12 @@ struct HotUpdMeta {
 __device__ __forceinline__ void hot_upd_issue(const StepArgs& a, int c, int lane, HotUpdMeta& M) {
     const int* rec = a.cmeta + (size_t)c * CMETA_N;
     M.c = c;
-    M.e0 = rec[0];
-    M.ne = rec[1];
-    M.face = rec[10 + (lane & 7)];
-    M.so = rec[2 + ((lane - 2) & 7)];
-    M.sf = rec[10 + ((lane - 2) & 7)];
+    const int2 h2 = ldg_early2(rec);
+    M.e0 = h2.x;
+    M.ne = h2.y;
+    M.face = ldg_early(rec + 10 + (lane & 7));
+    M.so = ldg_early(rec + 2 + ((lane - 2) & 7));
+    M.sf = ldg_early(rec + 10 + ((lane - 2) & 7));
 }
 
 // fsrc_g/h: where internal-face values come from (flux buffer or kept face values of the slab)
@@ -886,7 +914,8 @@ struct HotRelaxPlan {
     static constexpr int STAGE_D = NFLD * NSLOT * CI * 32;
     // the moment reduction (32 x 17 doubles) runs through the face tables, which are dead by then
     static constexpr int TAB_D = (NE * 4 * TW + NE * 2) > 32 * 17 ? (NE * 4 * TW + NE * 2) : 32 * 17;
-    static constexpr int PER_WARP_D = 2 * HOT_PTRS + HOT_STAGES * STAGE_D + TAB_D;
+    static constexpr int REC_D = NE * (FCOEF_N + 4);     // face equilibrium records + outward area vectors of a cell
+    static constexpr int PER_WARP_D = 2 * HOT_PTRS + 2 * REC_D + HOT_STAGES * STAGE_D + TAB_D;
     static constexpr size_t PER_WARP = ((size_t)PER_WARP_D * 8 + 127) / 128 * 128;
     static __host__ __device__ size_t txs_bytes(int ntab) { return ((size_t)(ntab + HOT_CI_MAX) * 48 + 127) / 128 * 128; }
     static __host__ size_t total(int ntab) { return txs_bytes(ntab) + HOT_WARPS * PER_WARP; }
@@ -905,7 +934,8 @@ k_hot_relax_update(StepArgs a) {
     hot_fill_txs(dv, 1.0, txs);
     unsigned char* wbase = dyn + P::txs_bytes(dv.ntab) + wib * P::PER_WARP;
     unsigned long long* sptr = reinterpret_cast<unsigned long long*>(wbase);
-    double* stages = reinterpret_cast<double*>(wbase) + 2 * HOT_PTRS;
+    double* recs = reinterpret_cast<double*>(wbase) + 2 * HOT_PTRS;   // [2][NE][FCOEF_N] | [NE][4] per buffer
+    double* stages = recs + 2 * P::REC_D;
     double* xtab = stages + HOT_STAGES * P::STAGE_D;       // [NE][TW][4]
     double* unic = xtab + NE * 4 * TW;                     // [NE][2] omrf, RT
     __syncthreads();
@@ -929,6 +959,24 @@ k_hot_relax_update(StepArgs a) {
     const int nm = a.nm;
     const double kd = (double)(a.gas.K + 3 - a.gas.D);
 
+    // face equilibrium records (16-byte pieces: 6 per face) and outward area vectors (2 per entry) of a
+    // cell into `dst`, same commit group as its first chunk
+    auto stage_records = [&](const HotUpdMeta& M, double* dst) {
+        const uint32_t sd = smem_u32(dst);
+#pragma unroll
+        for (int r = 0; r < (NE * 8 + 31) / 32; r++) {
+            const int p = lane + 32 * r;
+            const int jf = min(p / 6, NE - 1);
+            const int f = __shfl_sync(0xffffffffu, M.face, jf);
+            if (p < NE * 6) {
+                if (jf < M.ne) cp_async16(sd + p * 16, reinterpret_cast<const char*>(a.fcoef + (size_t)f * FCOEF_N) + (p % 6) * 16);
+            } else if (p < NE * 8) {
+                const int pe = p - NE * 6;
+                if (pe / 2 < M.ne)
+                    cp_async16(sd + NE * FCOEF_N * 8 + pe * 16, reinterpret_cast<const char*>(a.geoS + (size_t)M.e0 * 4) + pe * 16);
+            }
+        }
+    };
     const int nw = gridDim.x * HOT_WARPS;
     int item = blockIdx.x * HOT_WARPS + wib;
     uint32_t q = 0;
@@ -937,7 +985,10 @@ k_hot_relax_update(StepArgs a) {
     if (item < nc) {
         hot_upd_issue(a, item, lane, cur);
         hot_upd_commit<HAS_H>(a, lane, gts, hts, gbs, hbs, gsbs, hsbs, fk_g, fk_h, NE, sptr, cur);
-        if (cur.ne <= NE) hot_stage<CI, NTOT, NSLOT, false>(sptr, cur.ne + 1, 0, stages, lane);
+        if (cur.ne <= NE) {
+            hot_stage<CI, NTOT, NSLOT, false>(sptr, cur.ne + 1, 0, stages, lane);
+            stage_records(cur, recs);
+        }
         cp_async_commit();
     }
     while (item < nc) {
@@ -950,7 +1001,10 @@ k_hot_relax_update(StepArgs a) {
         auto stage_next_item = [&](double* st) {
             if (!has_next) return;
             hot_upd_commit<HAS_H>(a, lane, gts, hts, gbs, hbs, gsbs, hsbs, fk_g, fk_h, NE, sp_nxt, nxt);
-            if (nxt.ne <= NE) hot_stage<CI, NTOT, NSLOT, false>(sp_nxt, nxt.ne + 1, 0, st, lane);
+            if (nxt.ne <= NE) {
+                hot_stage<CI, NTOT, NSLOT, false>(sp_nxt, nxt.ne + 1, 0, st, lane);
+                stage_records(nxt, recs + (gsel ^ 1) * P::REC_D);
+            }
         };
         if (cur.ne > NE) {
             stage_next_item(stages + (q & 1) * P::STAGE_D);
@@ -958,9 +1012,12 @@ k_hot_relax_update(StepArgs a) {
             cur = nxt; item = nitem; gsel ^= 1;
             continue;
         }
-        const int ne = cur.ne, nint = cur.nint, c = cur.c;
+        // FULL: all NE entries are internal faces (compile-time face predicates)
+        auto run_item = [&](auto full_c) {
+        constexpr bool FULL = decltype(full_c)::value;
+        const int ne = FULL ? NE : cur.ne, nint = FULL ? NE : cur.nint, c = cur.c;
         // interior cells stage from register offsets (16-byte units), see hot_stage_off
-        const bool interior = ne == NE && nint == NE;
+        const bool interior = FULL;
         const uint32_t offc = (uint32_t)c * (uint32_t)(blk / 2) + (uint32_t)lane;
         uint32_t offf[NE];
 #pragma unroll
@@ -977,18 +1034,22 @@ k_hot_relax_update(StepArgs a) {
             }
         };
         // outward area vectors (sign folded in) and the face equilibria of the internal faces
+        // the records of this cell were staged together with its first chunk (the only group in flight)
+        cp_async_wait<0>();
+        __syncwarp();
+        const double* rec_f = recs + gsel * P::REC_D;
+        const double* rec_s = rec_f + NE * FCOEF_N;
         double Sx[NE], cyz[NE], EYZ[NE], YZ2[NE], QYZ[NE];
 #pragma unroll
         for (int j = 0; j < NE; j++) {
             Sx[j] = 0.0; cyz[j] = 0.0; EYZ[j] = YZ2[j] = QYZ[j] = 0.0;
             if (j < ne) {
-                const double* S = a.geoS + (size_t)(cur.e0 + j) * 4;
+                const double* S = rec_s + j * 4;
                 Sx[j] = S[0];
                 cyz[j] = fma(y, S[1], z * S[2]);
             }
             if (j < nint) {
-                const int f = __shfl_sync(0xffffffffu, cur.face, j);
-                const double* fc = a.fcoef + (size_t)f * FCOEF_N;
+                const double* fc = rec_f + j * FCOEF_N;
                 const double Ux = fc[0], Uy = fc[1], Uz = fc[2], ia = fc[3], pre = fc[4];
                 const double qx = fc[5], qy = fc[6], qz = fc[7];
                 for (int tt = lane; tt < span; tt += 32) {
@@ -1086,6 +1147,9 @@ k_hot_relax_update(StepArgs a) {
             const double t3 = warp_sum(uu[3]);
             if (lane == 0) atomicAdd(a.cslot + (size_t)c * nm + 16, t3);
         }
+        };
+        if (cur.ne == NE && cur.nint == NE) run_item(std::true_type{});
+        else run_item(std::false_type{});
         cur = nxt; item = nitem; gsel ^= 1;
     }
     cp_async_wait<0>();
