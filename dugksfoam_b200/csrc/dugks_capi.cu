@@ -113,7 +113,8 @@ struct dugks_handle {
     // second-generation kernels (dugks_hot.cuh)
     bool use_hot = true, has_far = false;
     int hot_ne = 6, hot_grid_out1 = 148, hot_grid_out2 = 148, hot_grid_upd = 148, hot_grid_rlx = 148;
-    size_t hsmem_rlx = 0;
+    size_t hsmem_rlx = 0, hsmem_half = 0;
+    int hot_grid_half = 148;
     // face-storage slabs: phase 1 keeps the reconstructed face values of slabs [0, n_keep) so that
     // phase 2 is ONE fused relax+update pass for them (no second gradient, no flux-buffer round trip)
     int n_keep = 0;
@@ -278,6 +279,13 @@ static int hot_configure(dugks_handle* h) {
     else DUGKS_HOT_CFG(8);
 #undef DUGKS_HOT_CFG
     if (e != cudaSuccess) return fail(h, DUGKS_ERR_CUDA, "cudaFuncSetAttribute (hot kernels): %s", cudaGetErrorString(e));
+    int occ_half = 1;
+    h->hsmem_half = HotHalfPlan<H>::total(h->L, tw, ntab);
+    if (h->hsmem_half <= 200 * 1024) {
+        e = cudaFuncSetAttribute(k_hot_halfstep<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->hsmem_half);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_half, k_hot_halfstep<H>, HOT_WARPS * 32, h->hsmem_half);
+        if (e != cudaSuccess) return fail(h, DUGKS_ERR_CUDA, "k_hot_halfstep configuration: %s", cudaGetErrorString(e));
+    } else h->hsmem_half = 0;
     int dev_sms = 148;
     cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->device);
     const int max_ctas = (h->nc + HOT_WARPS - 1) / HOT_WARPS;
@@ -285,6 +293,7 @@ static int hot_configure(dugks_handle* h) {
     h->hot_grid_out2 = std::max(1, std::min(dev_sms * std::max(occ[1], 1), max_ctas));
     h->hot_grid_upd = std::max(1, std::min(dev_sms * std::max(occ[2], 1), max_ctas));
     h->hot_grid_rlx = std::max(1, std::min(dev_sms * std::max(occ[3], 1), max_ctas));
+    h->hot_grid_half = std::max(1, std::min(dev_sms * std::max(occ_half, 1), max_ctas));
     if (getenv("DUGKS_VERBOSE"))
         fprintf(stderr, "dugks: hot kernels NE=%d smem %zu/%zu/%zu/%zu B, CTAs per SM %d/%d/%d/%d\n", h->hot_ne, h->hsmem_out1,
                 h->hsmem_out2, h->hsmem_upd, h->hsmem_rlx, occ[0], occ[1], occ[2], occ[3]);
@@ -297,7 +306,10 @@ static int launch_slab_kernels_phase1(dugks_handle* h, StepArgs a) {
     long long items = (long long)h->nc * (h->Rs / 32);
     {
         Timed t(h, 2);
-        k_cell_halfstep<H><<<grid_for(items), WARPS_PER_CTA * 32, 0, h->stream>>>(a, 0);
+        if (h->use_hot && h->hsmem_half > 0)
+            k_hot_halfstep<H><<<h->hot_grid_half, HOT_WARPS * 32, h->hsmem_half, h->stream>>>(a, h->tma_tw);
+        else
+            k_cell_halfstep<H><<<grid_for(items), WARPS_PER_CTA * 32, 0, h->stream>>>(a, 0);
     }
     if ((rc = check_launch(h, "k_cell_halfstep"))) return rc;
     if (h->use_hot) {
@@ -352,7 +364,11 @@ static int launch_slab_kernels_phase2(dugks_handle* h, StepArgs a) {
     long long items = (long long)h->nc * (h->Rs / 32);
     if (h->nbf > 0) {
         long long bitems = (long long)h->nbf * (h->Rs / 32);
-        k_bnd_relax<H><<<grid_for(bitems), WARPS_PER_CTA * 32, 0, h->stream>>>(a);
+        if (h->use_hot) {
+            const size_t sm = ((size_t)((h->ntab + 1) & ~1) + (size_t)WARPS_PER_CTA * h->tma_tw * 4) * sizeof(double);
+            k_hot_bnd_relax<H><<<grid_for(bitems), WARPS_PER_CTA * 32, sm, h->stream>>>(a, h->tma_tw);
+        } else
+            k_bnd_relax<H><<<grid_for(bitems), WARPS_PER_CTA * 32, 0, h->stream>>>(a);
         if ((rc = check_launch(h, "k_bnd_relax"))) return rc;
     }
     if (h->use_hot && a.slab < h->n_keep) {

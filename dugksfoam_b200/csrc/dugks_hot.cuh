@@ -266,7 +266,8 @@ struct HotPlan {
     static constexpr int GEO_D = NSLOT * 6;
     // PHASE 1 reduces its moments through the stage that was consumed last (STAGE_D >= 32 * 17)
     static constexpr bool RED_IN_STAGE = STAGE_D >= 32 * 17;
-    static constexpr int EXTRA_D = (PHASE == 1) ? (RED_IN_STAGE ? 0 : 32 * 17) : (NE * 4 * TW + NE * 2);
+    static constexpr int FREC_D = NE * FCOEF_N;   // PHASE 2: face equilibrium records of a cell (double-buffered)
+    static constexpr int EXTRA_D = (PHASE == 1) ? (RED_IN_STAGE ? 0 : 32 * 17) : (NE * 4 * TW + NE * 2 + 2 * FREC_D);
     static constexpr int PER_WARP_D = 2 * HOT_PTRS + 2 * GEO_D + HOT_STAGES * STAGE_D + EXTRA_D;
     static constexpr size_t PER_WARP = ((size_t)PER_WARP_D * 8 + 127) / 128 * 128;
     static __host__ __device__ size_t txs_bytes(int ntab) { return ((size_t)(ntab + HOT_CI_MAX) * 48 + 127) / 128 * 128; }
@@ -305,6 +306,7 @@ struct HotCtx {
     double* red;           // PHASE 1 reduction scratch
     double* xtab;          // PHASE 2 [NE][TW][4]
     double* unic;          // PHASE 2 [NE][2]
+    const double* frec;    // PHASE 2 face equilibrium records of the current cell [NE][FCOEF_N]
     double y, z, wr, yh, zh, kd;
     int cb, tmin, span, lane, L, blk, nm, nchunk;
     size_t slab_b;
@@ -350,6 +352,10 @@ __device__ __forceinline__ void hot_out_item(const StepArgs& a, const HotCtx& x,
     }
     double* const fkeep_g = (PHASE == 1 && a.fkeep_g) ? a.fkeep_g + (size_t)a.slab * a.m.nif * blk : nullptr;
     double* const fkeep_h = (PHASE == 1 && HAS_H && a.fkeep_h) ? a.fkeep_h + (size_t)a.slab * a.m.nif * blk : nullptr;
+    if (PHASE == 2) {   // the face records were staged with this cell's first chunk (the only group in flight)
+        cp_async_wait<0>();
+        __syncwarp();
+    }
     // ---- accumulators (PHASE 1) / face equilibrium tables (PHASE 2)
     double accg[NE][4], acch[NE][2];
     double EYZ[NE], YZ2[NE], QYZ[NE];
@@ -359,7 +365,7 @@ __device__ __forceinline__ void hot_out_item(const StepArgs& a, const HotCtx& x,
         acch[j][0] = acch[j][1] = 0.0;
         EYZ[j] = YZ2[j] = QYZ[j] = 0.0;
         if (PHASE == 2 && j < nint && anyc[j] != 0) {
-            const double* fc = a.fcoef + (size_t)fbase[j] * FCOEF_N;
+            const double* fc = x.frec + j * FCOEF_N;
             const double Ux = fc[0], Uy = fc[1], Uz = fc[2], ia = fc[3], pre = fc[4];
             const double qx = fc[5], qy = fc[6], qz = fc[7];
             for (int tt = lane; tt < x.span; tt += 32) {
@@ -597,6 +603,19 @@ k_hot_outgoing(StepArgs a) {
     HotCtx x;
     x.txs = txs;
     x.red = extra; x.xtab = extra; x.unic = extra + NE * 4 * TW;
+    double* frecs = extra + NE * 4 * TW + NE * 2;   // PHASE 2: [2][NE][FCOEF_N]
+    auto stage_frec = [&](const HotMeta& M, double* dst) {
+        if (PHASE != 2) return;
+        const uint32_t sd = smem_u32(dst);
+#pragma unroll
+        for (int r = 0; r < (NE * 6 + 31) / 32; r++) {
+            const int p = lane + 32 * r;
+            const int jf = min(p / 6, NE - 1);
+            const int f = __shfl_sync(0xffffffffu, M.face, jf);
+            if (p < NE * 6 && jf < M.nint)
+                cp_async16(sd + p * 16, reinterpret_cast<const char*>(a.fcoef + (size_t)f * FCOEF_N) + (p % 6) * 16);
+        }
+    };
     x.y = dv.row_y[grow]; x.z = dv.row_z[grow]; x.wr = dv.row_w[grow];
     x.yh = hd * x.y; x.zh = hd * x.z;
     x.kd = (double)(a.gas.K + 3 - a.gas.D);
@@ -618,6 +637,7 @@ k_hot_outgoing(StepArgs a) {
         if (cur.ne <= NE) {
             hot_stage<CI, NTOT, NSLOT, false>(sptr, cur.ne, 0, stages, lane);
             hot_stage_geo(a.geo6 + (size_t)(cur.e0 + cur.c) * 6, cur.ne, geo, lane);
+            stage_frec(cur, frecs);
         }
         cp_async_commit();
     }
@@ -637,6 +657,7 @@ k_hot_outgoing(StepArgs a) {
             if (next_ok) {
                 hot_stage<CI, NTOT, NSLOT, false>(sp_nxt, nxt.ne, 0, stage, lane);
                 hot_stage_geo(a.geo6 + (size_t)(nxt.e0 + nxt.c) * 6, nxt.ne, geo + (gsel ^ 1) * P::GEO_D, lane);
+                stage_frec(nxt, frecs + (gsel ^ 1) * P::FREC_D);
             }
         };
         if (cur.ne > NE) {      // cell with too many faces: the generic kernels take it
@@ -645,6 +666,7 @@ k_hot_outgoing(StepArgs a) {
             cp_async_commit();
         } else {
             x.geo = geo + gsel * P::GEO_D;
+            x.frec = frecs + gsel * P::FREC_D;
             const bool interior = cur.ne == NE && cur.nint == NE;
             if (interior && cur.cls && (NE == 4 || NE == 6)) {
                 uint32_t soff[NSLOT];   // 16-byte units
@@ -1153,4 +1175,183 @@ k_hot_relax_update(StepArgs a) {
         cur = nxt; item = nitem; gsel ^= 1;
     }
     cp_async_wait<0>();
+}
+
+// -------------------------------------------------------------------------------------------------
+// stage 1, gTilde -> gBarP (discreteVelocity.C:346-410), as a pure stream: persistent warps, the whole
+// row block of the NEXT cell (and its macro record) is in flight while the current cell's equilibrium
+// tables are built and applied; output goes straight to global memory.
+template <bool HAS_H>
+struct HotHalfPlan {
+    static constexpr int NFLD = HAS_H ? 2 : 1;
+    static __host__ __device__ size_t stage_d(int L) { return (size_t)NFLD * L * 32; }                 // doubles
+    static __host__ __device__ size_t per_warp(int L, int tw) {
+        return ((2 * stage_d(L) + 2 * 16 /*macro records*/ + 4 * (size_t)tw) * 8 + 127) / 128 * 128;
+    }
+    static __host__ size_t total(int L, int tw, int ntab) { return ((size_t)ntab * 8 + 127) / 128 * 128 + HOT_WARPS * per_warp(L, tw); }
+};
+
+template <bool HAS_H>
+__global__ void __launch_bounds__(HOT_WARPS * 32, 4)
+k_hot_halfstep(StepArgs a, int tw) {
+    using P = HotHalfPlan<HAS_H>;
+    extern __shared__ __align__(128) unsigned char dyn[];
+    const DevDV& dv = a.dv;
+    const int L = dv.L, nc = a.m.nc, blk = L * 32;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double* txs = reinterpret_cast<double*>(dyn);                    // abscissae
+    for (int k = threadIdx.x; k < dv.ntab; k += blockDim.x) txs[k] = dv.tx[k];
+    unsigned char* wbase = dyn + ((size_t)dv.ntab * 8 + 127) / 128 * 128 + wib * P::per_warp(L, tw);
+    const size_t stage_d = P::stage_d(L);
+    double* stages = reinterpret_cast<double*>(wbase);               // [2][NFLD][L][32]
+    double* mrec = stages + 2 * stage_d;                             // [2][16] cell macro records (9 used)
+    double* xtab = mrec + 2 * 16;                                    // [tw][4]
+    __syncthreads();
+    const size_t slab_c = (size_t)a.slab * nc * blk;
+    const double* gts = a.gt + slab_c;
+    const double* hts = HAS_H ? a.ht + slab_c : nullptr;
+    double* gbs = a.gb + slab_c;
+    double* hbs = HAS_H ? a.hb + slab_c : nullptr;
+    const int grow = a.slab * 32 + lane;
+    const double y = dv.row_y[grow], z = dv.row_z[grow];
+    const int cb = dv.row_cbase[grow];
+    int tmin, span;
+    table_range(dv, cb, tmin, span);
+    const double kd = (double)(a.gas.K + 3 - a.gas.D);
+    const int npiece = blk / 2;                                      // 16-byte pieces per field block
+
+    auto stage_cell = [&](int c, int buf) {
+        const uint32_t sd = smem_u32(stages + buf * stage_d);
+#pragma unroll
+        for (int fld = 0; fld < P::NFLD; fld++) {
+            const char* src = reinterpret_cast<const char*>((fld ? hts : gts) + (size_t)c * blk);
+            for (int p = lane; p < npiece; p += 32) cp_async16(sd + (fld * npiece + p) * 16, src + p * 16);
+        }
+        if (lane < MAC_N)   // 72-byte records are only 8-byte aligned
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(mrec + buf * 16 + lane)),
+                         "l"(a.cmac + (size_t)c * MAC_N + lane));
+    };
+    const int nw = gridDim.x * HOT_WARPS;
+    int c = blockIdx.x * HOT_WARPS + wib, buf = 0;
+    if (c < nc) stage_cell(c, 0);
+    cp_async_commit();
+    for (; c < nc; c += nw, buf ^= 1) {
+        if (c + nw < nc) stage_cell(c + nw, buf ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncwarp();
+        const double* mc = mrec + buf * 16;
+        const double rf = 1.5 * a.dt / (2.0 * mc[5] + a.dt);         // discreteVelocity.C:393
+        const EqCoef e = make_eq(a.gas, mc, rf);
+        for (int tt = lane; tt < span; tt += 32) {
+            const double cx = txs[tmin + tt] - e.Ux;
+            const double x2 = cx * cx * e.a;
+            double* xt = xtab + tt * 4;
+            xt[0] = exp(-0.5 * x2); xt[1] = x2; xt[2] = cx * e.qx; xt[3] = 0.0;
+        }
+        const double cy = y - e.Uy, cz = z - e.Uz;
+        const double yz2 = (cy * cy + cz * cz) * e.a;
+        const double EYZ = e.pre * exp(-0.5 * yz2);
+        const double YZ2 = yz2 - a.gas.D - 2.0;
+        const double QYZ = cy * e.qy + cz * e.qz;
+        const double omrf = 1.0 - rf;
+        __syncwarp();
+        const double* sg = stages + buf * stage_d + lane;
+        double* dg = gbs + (size_t)c * blk + lane;
+        double* dh = HAS_H ? hbs + (size_t)c * blk + lane : nullptr;
+        const double* xt0 = xtab + (cb - tmin) * 4;
+#pragma unroll 4
+        for (int i = 0; i < L; i++) {
+            const double2 x01 = lds2(xt0 + i * 4);
+            const double cc = x01.y + YZ2;                           // cSqrByRT - D - 2
+            const double cq = xt0[i * 4 + 2] + QYZ;                  // (1-Pr) cqBy5pRT
+            const double gM = x01.x * EYZ;                           // rf * gEqBGK
+            dg[i * 32] = fma(omrf, sg[i * 32], fma(cq, cc, 1.0) * gM);                                  // :405,1042
+            if (HAS_H)
+                dh[i * 32] = fma(omrf, sg[(L + i) * 32], (kd + cq * ((cc + 2.0) * kd - 2.0 * a.gas.K)) * gM * e.RT);   // :406,1043
+        }
+        __syncwarp();   // stage and tables are free again
+    }
+    cp_async_wait<0>();
+}
+
+// -------------------------------------------------------------------------------------------------
+// stage 2.3 (wall incoming Maxwellian, discreteVelocity.C:693-731) and stage 4 on boundary faces
+// (:886-931) with the separable equilibrium tables: one exp per table entry and lane instead of two per
+// (face, DV).  Same rules as k_bnd_relax (dugks_kernels.cuh).  item = boundary face.
+template <bool HAS_H>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+k_hot_bnd_relax(StepArgs a, int tw) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    const DevDV& dv = a.dv;
+    double* txs = reinterpret_cast<double*>(dyn);                          // abscissae
+    for (int k = threadIdx.x; k < dv.ntab; k += blockDim.x) txs[k] = dv.tx[k];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double* xtab = txs + ((dv.ntab + 1) & ~1) + (size_t)wib * tw * 4;     // [tw][4]: EX, X2, QX, EXwall
+    const int L = dv.L, blk = L * 32;
+    const double hstep = 0.5 * a.dt;
+    const int grow = a.slab * 32 + lane;
+    const double y = dv.row_y[grow], z = dv.row_z[grow];
+    const int cb = dv.row_cbase[grow];
+    int tmin, span;
+    table_range(dv, cb, tmin, span);
+    const double kd = (double)(a.gas.K + 3 - a.gas.D);
+    for (int b = blockIdx.x * WARPS_PER_CTA + wib; b < a.m.nbf; b += gridDim.x * WARPS_PER_CTA) {
+        const int kind = a.m.b_kind[b];
+        const double sx = a.m.b_Sf[(size_t)b * 3], sy = a.m.b_Sf[(size_t)b * 3 + 1], sz = a.m.b_Sf[(size_t)b * 3 + 2];
+        const double* bm = a.bmac + (size_t)b * 5;
+        const double* mf = a.fmac + (size_t)(a.m.nif + b) * MAC_N;
+        const double rf = hstep / (2.0 * mf[5] + hstep);                   // discreteVelocity.C:867
+        const EqCoef e = make_eq(a.gas, mf, rf);
+        const double omrf = 1.0 - rf;
+        const bool wall = kind == K_MAXWELL_WALL;
+        // wall Maxwellian rho_w / (2 pi R T_w)^(D/2) exp(-|xi - U_w|^2 / 2 R T_w), :1063-1075
+        const double RTw = a.gas.R * bm[4], aw = 1.0 / RTw;
+        double prew = 0.0;
+        if (wall) {
+            const double sq = sqrt(2.0 * DUGKS_PI * RTw);
+            prew = bm[0] / ((a.gas.D == 3) ? sq * sq * sq : ((a.gas.D == 2) ? sq * sq : sq));
+        }
+        for (int tt = lane; tt < span; tt += 32) {
+            const double xv = txs[tmin + tt];
+            const double cx = xv - e.Ux, x2 = cx * cx * e.a;
+            double* xt = xtab + tt * 4;
+            xt[0] = exp(-0.5 * x2); xt[1] = x2; xt[2] = cx * e.qx;
+            const double cw = xv - bm[1];
+            xt[3] = wall ? exp(-0.5 * cw * cw * aw) : 0.0;
+        }
+        const double cy = y - e.Uy, cz = z - e.Uz;
+        const double yz2 = (cy * cy + cz * cz) * e.a;
+        const double EYZ = e.pre * exp(-0.5 * yz2), YZ2 = yz2 - a.gas.D - 2.0, QYZ = cy * e.qy + cz * e.qz;
+        double EYZw = 0.0;
+        if (wall) {
+            const double wy = y - bm[2], wz = z - bm[3];
+            EYZw = prew * exp(-0.5 * (wy * wy + wz * wz) * aw);
+        }
+        const double hfw = RTw * kd;
+        const double ySy = __dmul_rn(y, sy), zSz = __dmul_rn(z, sz);
+        __syncwarp();
+        const size_t bbase = ((size_t)a.slab * a.m.nbf + b) * blk + lane;
+        const double* xt0 = xtab + (cb - tmin) * 4;
+        for (int i = 0; i < L; i++) {
+            const double phi = __dadd_rn(__dadd_rn(__dmul_rn(txs[cb + i], sx), ySy), zSz);
+            const double2 x01 = lds2(xt0 + i * 4), x23 = lds2(xt0 + i * 4 + 2);
+            double g = a.gsb[bbase + (size_t)i * 32];
+            double hh = HAS_H ? a.hsb[bbase + (size_t)i * 32] : 0.0;
+            if (wall && phi <= 0) {                                       // :713-727
+                g = x23.y * EYZw;
+                hh = g * hfw;
+            }
+            const double cc = x01.y + YZ2, cq = x23.x + QYZ, gM = x01.x * EYZ;
+            const double gS = fma(cq, cc, 1.0) * gM;
+            const double hS = HAS_H ? (kd + cq * ((cc + 2.0) * kd - 2.0 * a.gas.K)) * gM * e.RT : 0.0;
+            if (kind == K_SYMMETRY_PLANE) { g = fma(omrf, g, gS); hh = fma(omrf, hh, hS); }   // :880-881 [OF-lib]
+            if (phi > 0) { g = fma(omrf, g, gS); hh = fma(omrf, hh, hS); }                    // :907-919
+            if (kind == K_DVM_SYMMETRY) { g = fma(omrf, g, gS); hh = fma(omrf, hh, hS); }     // :922-930
+            a.gsb[bbase + (size_t)i * 32] = g;
+            if (HAS_H) a.hsb[bbase + (size_t)i * 32] = hh;
+        }
+        __syncwarp();
+    }
 }
