@@ -70,7 +70,8 @@ __global__ void k_build_upwind(StepArgs a, uint4* out, int* bad) {
          t += (long long)gridDim.x * blockDim.x) {
         const int lane = (int)(t & 31);
         const long long sc = t >> 5;
-        const int c = (int)(sc % a.m.nc), slab = (int)(sc / a.m.nc);
+        const int item = (int)(sc % a.m.nc), slab = (int)(sc / a.m.nc);
+        const int c = a.cmeta[(size_t)item * 24 + 20];   // codes are stored in traversal order
         const int grow = slab * 32 + lane;
         const double y = dv.row_y[grow], z = dv.row_z[grow];
         const int cb = dv.row_cbase[grow];
@@ -119,6 +120,16 @@ __device__ __forceinline__ void cp_async16(uint32_t sdst, const void* gsrc) {
     // the __syncwarp that ends the chunk which read it
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(gsrc));
 }
+// single-use data (state rows read once per pass, upwind codes): L2 evict-first, so that the row blocks
+// every neighbour re-reads stay resident
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void cp_async16_ef(uint32_t sdst, const void* gsrc, unsigned long long pol) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(sdst), "l"(gsrc), "l"(pol));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -143,7 +154,9 @@ __device__ __forceinline__ int ldg_early_u8(const unsigned char* p) {
 }
 __device__ __forceinline__ uint4 ldg_early4(const uint4* p) {
     uint4 v;
-    asm volatile("ld.global.nc.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
     return v;
 }
 
@@ -158,24 +171,27 @@ struct HotMeta {
 #define HOT_MINB(CI) ((CI) == 4 ? 2 : 3)
 #define HOT_PTRS 20   // stream pointer table entries per buffer (>= 2 * (2 + 8))
 
-// Per-cell record `cmeta` (20 ints, built by create()): [0] first entry e0, [1] ne | nint << 8 | cls << 16,
+// Per-cell record `cmeta` (24 ints, built by create()): [0] first entry e0, [1] ne | nint << 8 | cls << 16,
 // [2..9] other cell (or -1-b) of entry j, [10..17] face id | owner << 31, [18..19] patch kind bytes
-// (0xff = internal).  One dependency level instead of cell_off -> e_other -> b_kind.
-#define CMETA_N 20
+// (0xff = internal), [20] the cell.  One dependency level instead of cell_off -> e_other -> b_kind.
+// Records (and the upwind codes) are stored in TRAVERSAL order: warps walk the mesh along a space-
+// filling curve of the cell centres so that all neighbours of a cell are visited close in time and
+// their row blocks are still in L2 (natural order: +-z neighbours of a 64^3 mesh are 29 MB apart).
+#define CMETA_N 24
 
 // Issues the loads of cell c's record and upwind codes; nothing is consumed here, so the latency hides
 // behind the cell the warp is working on.
-__device__ __forceinline__ void hot_meta_issue(const StepArgs& a, int c, int lane, HotMeta& M) {
-    const int* rec = a.cmeta + (size_t)c * CMETA_N;
+__device__ __forceinline__ void hot_meta_issue(const StepArgs& a, int item, int lane, HotMeta& M) {
+    const int* rec = a.cmeta + (size_t)item * CMETA_N;
     const int l8 = lane & 7;
-    M.c = c;
+    M.c = ldg_early(rec + 20);
     const int2 h2 = ldg_early2(rec);
     M.e0 = h2.x;
     M.ne = h2.y;                   // packed, unpacked by hot_meta_commit
     M.other = ldg_early(rec + 2 + l8);
     M.face = ldg_early(rec + 10 + l8);         // | owner << 31
     M.kind = ldg_early_u8(reinterpret_cast<const unsigned char*>(rec + 18) + l8);
-    M.mw = ldg_early4(a.upw + ((size_t)a.slab * a.m.nc + c) * 32 + lane);
+    M.mw = ldg_early4(a.upw + ((size_t)a.slab * a.m.nc + item) * 32 + lane);
 }
 
 // Unpacks the record and writes the stream sources of phase-1/2 into the pointer table `sp`
@@ -234,6 +250,13 @@ __device__ __forceinline__ void hot_stage_one(uint32_t sdst, const double* base,
     const char* p = reinterpret_cast<const char*>(base) + (size_t)off16 * 16u + coff;
 #pragma unroll
     for (int part = 0; part < CI * 256 / 512; part++) cp_async16(sdst + part * 512, p + part * 512);
+}
+template <int CI>
+__device__ __forceinline__ void hot_stage_one_ef(uint32_t sdst, const double* base, uint32_t off16, uint32_t coff,
+                                                 unsigned long long pol) {
+    const char* p = reinterpret_cast<const char*>(base) + (size_t)off16 * 16u + coff;
+#pragma unroll
+    for (int part = 0; part < CI * 256 / 512; part++) cp_async16_ef(sdst + part * 512, p + part * 512, pol);
 }
 
 // interior cells: every stream lives in the same slab array, so 32-bit offsets (16-byte units, already
@@ -468,7 +491,7 @@ __device__ __forceinline__ void hot_out_item(const StepArgs& a, const HotCtx& x,
 #pragma unroll
                         for (int u = 0; u < CI; u++) {
                             const double val = face_val(u);
-                            if (keep) keep[u * 32] = val;
+                            if (keep) __stcs(keep + u * 32, val);
                             if (fld == 0) {
                                 accg[j][0] = fma(W[u][0], val, accg[j][0]); accg[j][1] = fma(W[u][1], val, accg[j][1]);
                                 accg[j][2] = fma(W[u][2], val, accg[j][2]); accg[j][3] = fma(W[u][3], val, accg[j][3]);
@@ -482,7 +505,7 @@ __device__ __forceinline__ void hot_out_item(const StepArgs& a, const HotCtx& x,
 #pragma unroll
                         for (int u = 0; u < CI; u++) {
                             double val = face_val(u);
-                            if (keep && ((wbk >> u) & 1u)) keep[u * 32] = val;
+                            if (keep && ((wbk >> u) & 1u)) __stcs(keep + u * 32, val);
                             // this side's share: all of it, half of it on a tie (:513-529), or none
                             const int hi = ((fb >> u) & 1u) ? 0x3ff00000 : (((tbits >> u) & 1u) ? 0x3fe00000 : 0);
                             val *= __hiloint2double(hi, 0);
@@ -509,7 +532,7 @@ __device__ __forceinline__ void hot_out_item(const StepArgs& a, const HotCtx& x,
                         double eq;
                         if (fld == 0) eq = fma(cq, cc, 1.0) * gM;                                      // :1042
                         else eq = (x.kd + cq * ((cc + 2.0) * x.kd - 2.0 * a.gas.K)) * gM * frt;        // :1043
-                        if (allfull || ((wb >> u) & 1u)) dst[u * 32] = fma(omrf, val, eq);             // :880-881
+                        if (allfull || ((wb >> u) & 1u)) __stcs(dst + u * 32, fma(omrf, val, eq));             // :880-881
                     }
                 }
             }
@@ -730,9 +753,9 @@ struct HotUpdMeta {
 };
 
 // loads only (see hot_meta_issue)
-__device__ __forceinline__ void hot_upd_issue(const StepArgs& a, int c, int lane, HotUpdMeta& M) {
-    const int* rec = a.cmeta + (size_t)c * CMETA_N;
-    M.c = c;
+__device__ __forceinline__ void hot_upd_issue(const StepArgs& a, int item, int lane, HotUpdMeta& M) {
+    const int* rec = a.cmeta + (size_t)item * CMETA_N;
+    M.c = ldg_early(rec + 20);
     const int2 h2 = ldg_early2(rec);
     M.e0 = h2.x;
     M.ne = h2.y;
@@ -797,6 +820,7 @@ k_hot_update(StepArgs a) {
     const int nchunk = (L + CI - 1) / CI;
     const int nm = a.nm;
 
+    const unsigned long long pol_ef = l2_evict_first_policy();
     const int nw = gridDim.x * HOT_WARPS;
     int item = blockIdx.x * HOT_WARPS + wib;
     uint32_t q = 0;
@@ -837,8 +861,8 @@ k_hot_update(StepArgs a) {
             const uint32_t sdst = smem_u32(st) + (uint32_t)lane * 16u, coff = (uint32_t)ch * (CI * 256u);
 #pragma unroll
             for (int fld = 0; fld < P::NFLD; fld++) {
-                hot_stage_one<CI>(sdst + (fld * NSLOT + 0) * (CI * 256), fld ? hts : gts, offc, coff);
-                hot_stage_one<CI>(sdst + (fld * NSLOT + 1) * (CI * 256), fld ? hbs : gbs, offc, coff);
+                hot_stage_one_ef<CI>(sdst + (fld * NSLOT + 0) * (CI * 256), fld ? hts : gts, offc, coff, pol_ef);
+                hot_stage_one_ef<CI>(sdst + (fld * NSLOT + 1) * (CI * 256), fld ? hbs : gbs, offc, coff, pol_ef);
 #pragma unroll
                 for (int j = 0; j < NE; j++)
                     hot_stage_one<CI>(sdst + (fld * NSLOT + 2 + j) * (CI * 256), fld ? a.fbuf_h : a.fbuf_g, offf[j], coff);
@@ -896,7 +920,7 @@ k_hot_update(StepArgs a) {
                 for (int u = 0; u < CI; u++) {
                     const double vnew = (-1.0 / 3) * sf[u * 32] + (4.0 / 3) * sf[(CI + u) * 32] - sum[u] * dtv;   // :937,952
                     if (i0 + u >= L) continue;   // tail chunk (warp-uniform)
-                    (fld == 0 ? gdst : hdst)[(i0 + u) * 32] = vnew;
+                    __stcs((fld == 0 ? gdst : hdst) + (i0 + u) * 32, vnew);
                     if (fld == 0) {
                         A[0] = fma(W[u][0], vnew, A[0]); A[1] = fma(W[u][1], vnew, A[1]);
                         A[2] = fma(W[u][2], vnew, A[2]); A[3] = fma(W[u][3], vnew, A[3]);
@@ -999,6 +1023,7 @@ k_hot_relax_update(StepArgs a) {
             }
         }
     };
+    const unsigned long long pol_ef = l2_evict_first_policy();
     const int nw = gridDim.x * HOT_WARPS;
     int item = blockIdx.x * HOT_WARPS + wib;
     uint32_t q = 0;
@@ -1048,8 +1073,8 @@ k_hot_relax_update(StepArgs a) {
             const uint32_t sdst = smem_u32(st) + (uint32_t)lane * 16u, coff = (uint32_t)ch * (CI * 256u);
 #pragma unroll
             for (int fld = 0; fld < P::NFLD; fld++) {
-                hot_stage_one<CI>(sdst + (fld * NSLOT + 0) * (CI * 256), fld ? hts : gts, offc, coff);
-                hot_stage_one<CI>(sdst + (fld * NSLOT + 1) * (CI * 256), fld ? hbs : gbs, offc, coff);
+                hot_stage_one_ef<CI>(sdst + (fld * NSLOT + 0) * (CI * 256), fld ? hts : gts, offc, coff, pol_ef);
+                hot_stage_one_ef<CI>(sdst + (fld * NSLOT + 1) * (CI * 256), fld ? hbs : gbs, offc, coff, pol_ef);
 #pragma unroll
                 for (int j = 0; j < NE; j++)
                     hot_stage_one<CI>(sdst + (fld * NSLOT + 2 + j) * (CI * 256), fld ? fk_h : fk_g, offf[j], coff);
@@ -1145,7 +1170,7 @@ k_hot_relax_update(StepArgs a) {
                 for (int u = 0; u < CI; u++) {
                     const double vnew = (-1.0 / 3) * sf[u * 32] + (4.0 / 3) * sf[(CI + u) * 32] - sum[u] * dtv;   // :937,952
                     if (i0 + u >= L) continue;   // tail chunk (warp-uniform)
-                    (fld == 0 ? gdst : hdst)[(i0 + u) * 32] = vnew;
+                    __stcs((fld == 0 ? gdst : hdst) + (i0 + u) * 32, vnew);
                     if (fld == 0) {
                         A[0] = fma(W[u][0], vnew, A[0]); A[1] = fma(W[u][1], vnew, A[1]);
                         A[2] = fma(W[u][2], vnew, A[2]); A[3] = fma(W[u][3], vnew, A[3]);
@@ -1219,13 +1244,14 @@ k_hot_halfstep(StepArgs a, int tw) {
     table_range(dv, cb, tmin, span);
     const double kd = (double)(a.gas.K + 3 - a.gas.D);
     const int npiece = blk / 2;                                      // 16-byte pieces per field block
+    const unsigned long long pol_ef = l2_evict_first_policy();
 
     auto stage_cell = [&](int c, int buf) {
         const uint32_t sd = smem_u32(stages + buf * stage_d);
 #pragma unroll
         for (int fld = 0; fld < P::NFLD; fld++) {
             const char* src = reinterpret_cast<const char*>((fld ? hts : gts) + (size_t)c * blk);
-            for (int p = lane; p < npiece; p += 32) cp_async16(sd + (fld * npiece + p) * 16, src + p * 16);
+            for (int p = lane; p < npiece; p += 32) cp_async16_ef(sd + (fld * npiece + p) * 16, src + p * 16, pol_ef);
         }
         if (lane < MAC_N)   // 72-byte records are only 8-byte aligned
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(mrec + buf * 16 + lane)),
@@ -1266,9 +1292,9 @@ k_hot_halfstep(StepArgs a, int tw) {
             const double cc = x01.y + YZ2;                           // cSqrByRT - D - 2
             const double cq = xt0[i * 4 + 2] + QYZ;                  // (1-Pr) cqBy5pRT
             const double gM = x01.x * EYZ;                           // rf * gEqBGK
-            dg[i * 32] = fma(omrf, sg[i * 32], fma(cq, cc, 1.0) * gM);                                  // :405,1042
+            __stcs(dg + i * 32, fma(omrf, sg[i * 32], fma(cq, cc, 1.0) * gM));                                  // :405,1042
             if (HAS_H)
-                dh[i * 32] = fma(omrf, sg[(L + i) * 32], (kd + cq * ((cc + 2.0) * kd - 2.0 * a.gas.K)) * gM * e.RT);   // :406,1043
+                __stcs(dh + i * 32, fma(omrf, sg[(L + i) * 32], (kd + cq * ((cc + 2.0) * kd - 2.0 * a.gas.K)) * gM * e.RT));   // :406,1043
         }
         __syncwarp();   // stage and tables are free again
     }
