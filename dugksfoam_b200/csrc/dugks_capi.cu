@@ -114,7 +114,9 @@ struct dugks_handle {
     bool use_hot = true, has_far = false;
     int hot_ne = 6, hot_grid_out1 = 148, hot_grid_out2 = 148, hot_grid_upd = 148, hot_grid_rlx = 148;
     size_t hsmem_rlx = 0, hsmem_half = 0;
-    int hot_grid_half = 148;
+    int hot_grid_half = 148, hot_grid_axis = 148;
+    bool split_axis = false;
+    int n_axis = 0;
     // face-storage slabs: phase 1 keeps the reconstructed face values of slabs [0, n_keep) so that
     // phase 2 is ONE fused relax+update pass for them (no second gradient, no flux-buffer round trip)
     int n_keep = 0;
@@ -221,7 +223,19 @@ static void launch_hot_outgoing(dugks_handle* h, const StepArgs& a) {
     const size_t sm = PHASE == 1 ? h->hsmem_out1 : h->hsmem_out2;
     const int tw = PHASE == 1 ? 32 : h->tma_tw;
     const int grid = PHASE == 1 ? h->hot_grid_out1 : h->hot_grid_out2;
-#define DUGKS_HOT_OUT(NE_, TW_) k_hot_outgoing<PHASE, H, NE_, TW_, (PHASE == 1 ? CI_OUT1 : CI_OUT2)><<<grid, HOT_WARPS * 32, sm, h->stream>>>(a)
+    if (PHASE == 1 && h->split_axis) {
+        // mostly axis-aligned mesh: the light variant alone runs 3 CTAs/SM, a second launch takes the rest
+        if (h->hot_ne == 4) {
+            k_hot_outgoing<1, H, 4, 32, CI_OUT1, 1><<<h->hot_grid_axis, HOT_WARPS * 32, sm, h->stream>>>(a);
+            k_hot_outgoing<1, H, 4, 32, CI_OUT1, 2><<<grid, HOT_WARPS * 32, sm, h->stream>>>(a);
+        } else {
+            k_hot_outgoing<1, H, 6, 32, CI_OUT1, 1><<<h->hot_grid_axis, HOT_WARPS * 32, sm, h->stream>>>(a);
+            k_hot_outgoing<1, H, 6, 32, CI_OUT1, 2><<<grid, HOT_WARPS * 32, sm, h->stream>>>(a);
+        }
+        h->launches++;
+        return;
+    }
+#define DUGKS_HOT_OUT(NE_, TW_) k_hot_outgoing<PHASE, H, NE_, TW_, (PHASE == 1 ? CI_OUT1 : CI_OUT2), 0><<<grid, HOT_WARPS * 32, sm, h->stream>>>(a)
     if (h->hot_ne == 4) { if (tw == 32) DUGKS_HOT_OUT(4, 32); else DUGKS_HOT_OUT(4, 64); }
     else if (h->hot_ne == 6) { if (tw == 32) DUGKS_HOT_OUT(6, 32); else DUGKS_HOT_OUT(6, 64); }
     else { if (tw == 32) DUGKS_HOT_OUT(8, 32); else DUGKS_HOT_OUT(8, 64); }
@@ -251,7 +265,7 @@ static cudaError_t hot_cfg_rlx(dugks_handle* h, int* occ) {
 }
 template <int PHASE, bool H, int NE, int TW>
 static cudaError_t hot_attr_out(size_t bytes) {
-    return cudaFuncSetAttribute(k_hot_outgoing<PHASE, H, NE, TW, (PHASE == 1 ? CI_OUT1 : CI_OUT2)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    return cudaFuncSetAttribute(k_hot_outgoing<PHASE, H, NE, TW, (PHASE == 1 ? CI_OUT1 : CI_OUT2), 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 template <bool H>
 static int hot_configure(dugks_handle* h) {
@@ -268,9 +282,9 @@ static int hot_configure(dugks_handle* h) {
         if (e == cudaSuccess) e = tw == 32 ? hot_attr_out<2, H, NE_, 32>(h->hsmem_out2) : hot_attr_out<2, H, NE_, 64>(h->hsmem_out2); \
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_hot_update<H, NE_, CI_UPD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->hsmem_upd); \
         /* persistent grids: CTAs the SM can hold (registers and shared memory) times the SM count */    \
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], k_hot_outgoing<1, H, NE_, 32, CI_OUT1>, HOT_WARPS * 32, h->hsmem_out1); \
-        if (e == cudaSuccess) e = tw == 32 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], k_hot_outgoing<2, H, NE_, 32, CI_OUT2>, HOT_WARPS * 32, h->hsmem_out2) \
-                                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], k_hot_outgoing<2, H, NE_, 64, CI_OUT2>, HOT_WARPS * 32, h->hsmem_out2); \
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], k_hot_outgoing<1, H, NE_, 32, CI_OUT1, 0>, HOT_WARPS * 32, h->hsmem_out1); \
+        if (e == cudaSuccess) e = tw == 32 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], k_hot_outgoing<2, H, NE_, 32, CI_OUT2, 0>, HOT_WARPS * 32, h->hsmem_out2) \
+                                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], k_hot_outgoing<2, H, NE_, 64, CI_OUT2, 0>, HOT_WARPS * 32, h->hsmem_out2); \
         if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], k_hot_update<H, NE_, CI_UPD>, HOT_WARPS * 32, h->hsmem_upd); \
         if (e == cudaSuccess) e = tw == 32 ? hot_cfg_rlx<H, NE_, 32>(h, &occ[3]) : hot_cfg_rlx<H, NE_, 64>(h, &occ[3]); \
     } while (0)
@@ -279,6 +293,22 @@ static int hot_configure(dugks_handle* h) {
     else DUGKS_HOT_CFG(8);
 #undef DUGKS_HOT_CFG
     if (e != cudaSuccess) return fail(h, DUGKS_ERR_CUDA, "cudaFuncSetAttribute (hot kernels): %s", cudaGetErrorString(e));
+    int occ_axis = 1;
+    h->split_axis = false;
+    if (e == cudaSuccess && (h->hot_ne == 4 || h->hot_ne == 6) && 2 * (long long)h->n_axis > h->nc &&
+        getenv("DUGKS_SPLIT_AXIS") != nullptr) {   // opt-in experiment: measured slower (27.7 vs 21.9 ms per step at 32^3)
+        if (h->hot_ne == 4) {
+            e = cudaFuncSetAttribute(k_hot_outgoing<1, H, 4, 32, CI_OUT1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->hsmem_out1);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_hot_outgoing<1, H, 4, 32, CI_OUT1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->hsmem_out1);
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_axis, k_hot_outgoing<1, H, 4, 32, CI_OUT1, 1>, HOT_WARPS * 32, h->hsmem_out1);
+        } else {
+            e = cudaFuncSetAttribute(k_hot_outgoing<1, H, 6, 32, CI_OUT1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->hsmem_out1);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_hot_outgoing<1, H, 6, 32, CI_OUT1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->hsmem_out1);
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_axis, k_hot_outgoing<1, H, 6, 32, CI_OUT1, 1>, HOT_WARPS * 32, h->hsmem_out1);
+        }
+        if (e != cudaSuccess) return fail(h, DUGKS_ERR_CUDA, "axis-split kernel configuration: %s", cudaGetErrorString(e));
+        h->split_axis = occ_axis >= 3;
+    }
     int occ_half = 1;
     h->hsmem_half = HotHalfPlan<H>::total(h->L, tw, ntab);
     if (h->hsmem_half <= 200 * 1024) {
@@ -294,9 +324,10 @@ static int hot_configure(dugks_handle* h) {
     h->hot_grid_upd = std::max(1, std::min(dev_sms * std::max(occ[2], 1), max_ctas));
     h->hot_grid_rlx = std::max(1, std::min(dev_sms * std::max(occ[3], 1), max_ctas));
     h->hot_grid_half = std::max(1, std::min(dev_sms * std::max(occ_half, 1), max_ctas));
+    h->hot_grid_axis = std::max(1, std::min(dev_sms * std::max(occ_axis, 1), max_ctas));
     if (getenv("DUGKS_VERBOSE"))
-        fprintf(stderr, "dugks: hot kernels NE=%d smem %zu/%zu/%zu/%zu B, CTAs per SM %d/%d/%d/%d\n", h->hot_ne, h->hsmem_out1,
-                h->hsmem_out2, h->hsmem_upd, h->hsmem_rlx, occ[0], occ[1], occ[2], occ[3]);
+        fprintf(stderr, "dugks: hot kernels NE=%d smem %zu/%zu/%zu/%zu B, CTAs per SM %d/%d/%d/%d, axis cells %d of %d, split %d (%d CTAs/SM)\n", h->hot_ne, h->hsmem_out1,
+                h->hsmem_out2, h->hsmem_upd, h->hsmem_rlx, occ[0], occ[1], occ[2], occ[3], h->n_axis, h->nc, (int)h->split_axis, occ_axis);
     return 0;
 }
 
@@ -899,6 +930,7 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
                 e_other[e] = tmp_i[j * 3]; e_face[e] = tmp_i[j * 3 + 1]; e_owner[e] = tmp_i[j * 3 + 2];
             }
             cell_cls[c] = 1;
+            h->n_axis++;
         }
     }
 

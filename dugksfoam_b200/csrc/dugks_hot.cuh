@@ -598,10 +598,17 @@ __device__ __forceinline__ void hot_out_item(const StepArgs& a, const HotCtx& x,
 // stages 2.1 + 3 (PHASE 1: face moments, boundary-face values, lagged boundary gradient) and
 // stage 4 (PHASE 2: relaxed internal-face values into the slab flux buffer).
 // discreteVelocity.C:412-691 / fvDVM.C:473-516 / discreteVelocity.C:867-881
-template <int PHASE, bool HAS_H, int NE, int TW, int CI>
-__global__ void __launch_bounds__(HOT_WARPS * 32, HOT_MINB(CI))
+// SEL: 0 = every cell; 1 = only axis-aligned cells (the light variant alone fits 3 CTAs/SM);
+//      2 = only the other cells (run as a second launch when SEL = 1 is used)
+template <int PHASE, bool HAS_H, int NE, int TW, int CI, int SEL>
+__global__ void __launch_bounds__(HOT_WARPS * 32, (SEL == 1 ? 3 : HOT_MINB(CI)))
 k_hot_outgoing(StepArgs a) {
     using P = HotPlan<PHASE, HAS_H, NE, TW, CI>;
+    auto mine = [](const HotMeta& M) {
+        if (M.ne > NE) return false;
+        const bool axis = M.cls != 0 && M.ne == NE && M.nint == NE && (NE == 4 || NE == 6);
+        return SEL == 0 || (SEL == 1 ? axis : !axis);
+    };
     constexpr int NSLOT = P::NSLOT, NTOT = P::NFLD * P::NSLOT;
     extern __shared__ __align__(128) unsigned char dyn[];
     const DevDV& dv = a.dv;
@@ -657,7 +664,7 @@ k_hot_outgoing(StepArgs a) {
     if (item < nc) {
         hot_meta_issue(a, item, lane, cur);
         hot_meta_commit<HAS_H>(a, lane, gbs, hbs, gam_g, gam_h, NE, sptr, cur);
-        if (cur.ne <= NE) {
+        if (mine(cur)) {
             hot_stage<CI, NTOT, NSLOT, false>(sptr, cur.ne, 0, stages, lane);
             hot_stage_geo(a.geo6 + (size_t)(cur.e0 + cur.c) * 6, cur.ne, geo, lane);
             stage_frec(cur, frecs);
@@ -675,7 +682,7 @@ k_hot_outgoing(StepArgs a) {
         auto stage_next_item = [&](double* stage) {
             if (has_next) {
                 hot_meta_commit<HAS_H>(a, lane, gbs, hbs, gam_g, gam_h, NE, sp_nxt, nxt);
-                next_ok = nxt.ne <= NE;
+                next_ok = mine(nxt);
             }
             if (next_ok) {
                 hot_stage<CI, NTOT, NSLOT, false>(sp_nxt, nxt.ne, 0, stage, lane);
@@ -683,7 +690,7 @@ k_hot_outgoing(StepArgs a) {
                 stage_frec(nxt, frecs + (gsel ^ 1) * P::FREC_D);
             }
         };
-        if (cur.ne > NE) {      // cell with too many faces: the generic kernels take it
+        if (!mine(cur)) {       // too many faces (the generic kernels take it) or the other launch's cell
             __syncwarp();
             stage_next_item(stages + (q & 1) * P::STAGE_D);
             cp_async_commit();
@@ -691,7 +698,7 @@ k_hot_outgoing(StepArgs a) {
             x.geo = geo + gsel * P::GEO_D;
             x.frec = frecs + gsel * P::FREC_D;
             const bool interior = cur.ne == NE && cur.nint == NE;
-            if (interior && cur.cls && (NE == 4 || NE == 6)) {
+            if (SEL != 2 && interior && cur.cls && (NE == 4 || NE == 6)) {
                 uint32_t soff[NSLOT];   // 16-byte units
                 soff[0] = (uint32_t)cur.c * (uint32_t)(blk / 2) + (uint32_t)lane;
 #pragma unroll
@@ -703,7 +710,7 @@ k_hot_outgoing(StepArgs a) {
                     else stage_next_item(st);
                 };
                 hot_out_item<PHASE, HAS_H, NE, TW, CI, true, (NE == 4 || NE == 6)>(a, x, cur, stages, P::STAGE_D, q, prefetch);
-            } else if (cur.ne == NE) {
+            } else if (SEL != 1 && cur.ne == NE) {
                 // all NE entries exist; boundary entries (if any) stream the lagged gradient from another
                 // array, so only all-internal cells can use the register offsets
                 uint32_t soff[NSLOT];   // 16-byte units
@@ -719,7 +726,7 @@ k_hot_outgoing(StepArgs a) {
                     } else stage_next_item(st);
                 };
                 hot_out_item<PHASE, HAS_H, NE, TW, CI, true, false>(a, x, cur, stages, P::STAGE_D, q, prefetch);
-            } else {
+            } else if (SEL != 1) {
                 auto prefetch = [&](int ch) {
                     double* st = stages + ((q & 1) ^ 1) * P::STAGE_D;
                     if (ch + 1 < x.nchunk) hot_stage<CI, NTOT, NSLOT, false>(sp_cur, cur.ne, ch + 1, st, lane);
