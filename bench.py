@@ -269,13 +269,24 @@ def main():
     peak, peak_src = peaks()
     balg = b_alg(case, nf)
     achieved = gups / world * balg   # GB/s per GPU (each GPU advances 1/world of the updates) vs one GPU's HBM peak
-    traffic = None
+    traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "traffic_per_update.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and world == 1:
         try:
-            traffic = json.load(open(tp)).get(args.workload)
+            t = json.load(open(tp)).get(args.workload)
+            traffic, traffic_src = t["dram_gb_per_step"], t["source"]
         except Exception:
             traffic = None
+    # algorithmic bytes per update of each kernel family: half-step 8+8; outgoing reads 8 and
+    # writes F*8 (kept face values or out-flux); update/relax reads 8+8+F*8 and writes 8
+    F8 = 8.0 * nf * case.faces_per_cell()
+    alg = {"k_cell_halfstep": 16.0 * nf, "k_cell_outgoing": 8.0 * nf + F8, "k_cell_update": 24.0 * nf + F8}
+    for name, v in fam.items():
+        if v["launches_per_step"] > 0 and v["ms_per_step"] > 0:
+            upd = updates_per_step / world * (v["launches_per_step"] / st0["n_slabs"])   # updates this family touches per step
+            v["alg_bytes_per_update"] = alg[name]
+            v["achieved_gbs"] = upd * alg[name] / (v["ms_per_step"] * 1e-3) / 1e9
+            v["frac_of_peak"] = v["achieved_gbs"] / peaks()[0]
     dom = max(fam, key=lambda k: fam[k]["ms_per_step"])
     line = {
         "metric": METRIC, "value": gups, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -285,14 +296,15 @@ def main():
                    "h_elided": bool(st0["h_elided"]), "nf": nf, "faces_per_cell": case.faces_per_cell(),
                    "parallelism": f"dv{world}", "dt": dt,
                    "l2_policy": "inputs larger than L2 (state is tens of GB per GPU)",
-                   "slabs_per_step": st0["n_slabs"], "slab_dvs": st0["slab_dvs"],
+                   "slabs_per_step": st0["n_slabs"], "slab_dvs": st0["slab_dvs"], "face_storage_slabs": st0["keep_slabs"],
                    "device_bytes": st0["device_bytes"]},
         "e2e": {"value": e2e_gups, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s / K * 1e3},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src,
+                     "traffic": traffic, "traffic_unit": "GB of DRAM reads+writes per step (ncu)", "traffic_source": traffic_src,
+                     "peak_source": peak_src,
                      "scope": "whole step (all kernels of one evolution()), per GPU",
                      "algorithmic_bytes_per_update": balg,
                      "dominant_kernel": dom, "kernels": fam},
