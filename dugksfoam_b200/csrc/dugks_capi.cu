@@ -225,12 +225,16 @@ static void launch_hot_outgoing(dugks_handle* h, const StepArgs& a) {
     const int grid = PHASE == 1 ? h->hot_grid_out1 : h->hot_grid_out2;
     if (PHASE == 1 && h->split_axis) {
         // mostly axis-aligned mesh: the light variant alone runs 3 CTAs/SM, a second launch takes the rest
+        StepArgs a1 = a, a2 = a;
+        a1.item0 = 0; a1.item1 = h->n_axis;
+        a2.item0 = h->n_axis; a2.item1 = h->nc;
+        const int grid2 = std::max(1, std::min(grid, (h->nc - h->n_axis + HOT_WARPS - 1) / HOT_WARPS));
         if (h->hot_ne == 4) {
-            k_hot_outgoing<1, H, 4, 32, CI_OUT1, 1><<<h->hot_grid_axis, HOT_WARPS * 32, sm, h->stream>>>(a);
-            k_hot_outgoing<1, H, 4, 32, CI_OUT1, 2><<<grid, HOT_WARPS * 32, sm, h->stream>>>(a);
+            k_hot_outgoing<1, H, 4, 32, CI_OUT1, 1><<<h->hot_grid_axis, HOT_WARPS * 32, sm, h->stream>>>(a1);
+            if (h->n_axis < h->nc) k_hot_outgoing<1, H, 4, 32, CI_OUT1, 2><<<grid2, HOT_WARPS * 32, sm, h->stream>>>(a2);
         } else {
-            k_hot_outgoing<1, H, 6, 32, CI_OUT1, 1><<<h->hot_grid_axis, HOT_WARPS * 32, sm, h->stream>>>(a);
-            k_hot_outgoing<1, H, 6, 32, CI_OUT1, 2><<<grid, HOT_WARPS * 32, sm, h->stream>>>(a);
+            k_hot_outgoing<1, H, 6, 32, CI_OUT1, 1><<<h->hot_grid_axis, HOT_WARPS * 32, sm, h->stream>>>(a1);
+            if (h->n_axis < h->nc) k_hot_outgoing<1, H, 6, 32, CI_OUT1, 2><<<grid2, HOT_WARPS * 32, sm, h->stream>>>(a2);
         }
         h->launches++;
         return;
@@ -1001,6 +1005,9 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
             }
             std::stable_sort(order.begin(), order.end(), [&](int x, int y2) { return key[x] < key[y2]; });
         }
+        // split launches (DUGKS_SPLIT_AXIS): axis-aligned cells first, the others after them
+        if (getenv("DUGKS_SPLIT_AXIS") != nullptr)
+            std::stable_partition(order.begin(), order.end(), [&](int c) { return cell_cls[c] != 0; });
         // per-cell record (CMETA_N ints) in traversal order: everything a warp needs to start a cell in one load level
         std::vector<int> cmeta((size_t)nc * CMETA_N, 0);
         for (int item = 0; item < nc; item++) {

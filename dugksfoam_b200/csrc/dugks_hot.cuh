@@ -600,8 +600,11 @@ __device__ __forceinline__ void hot_out_item(const StepArgs& a, const HotCtx& x,
 // discreteVelocity.C:412-691 / fvDVM.C:473-516 / discreteVelocity.C:867-881
 // SEL: 0 = every cell; 1 = only axis-aligned cells (the light variant alone fits 3 CTAs/SM);
 //      2 = only the other cells (run as a second launch when SEL = 1 is used)
+#ifndef HOT_K1_MINB
+#define HOT_K1_MINB 2
+#endif
 template <int PHASE, bool HAS_H, int NE, int TW, int CI, int SEL>
-__global__ void __launch_bounds__(HOT_WARPS * 32, (SEL == 1 ? 3 : HOT_MINB(CI)))
+__global__ void __launch_bounds__(HOT_WARPS * 32, (SEL == 1 ? 3 : (PHASE == 1 ? HOT_K1_MINB : HOT_MINB(CI))))
 k_hot_outgoing(StepArgs a) {
     using P = HotPlan<PHASE, HAS_H, NE, TW, CI>;
     auto mine = [](const HotMeta& M) {
@@ -657,11 +660,13 @@ k_hot_outgoing(StepArgs a) {
     x.slab_b = slab_b;
 
     const int nw = gridDim.x * HOT_WARPS;
-    int item = blockIdx.x * HOT_WARPS + wib;
+    // items [a.item0, a.item1) of the traversal order (the whole mesh unless the launch is split by cell class)
+    const int item_end = a.item1 > 0 ? a.item1 : nc;
+    int item = a.item0 + blockIdx.x * HOT_WARPS + wib;
     uint32_t q = 0;        // flat chunk counter of this warp: stage = q & 1
     int gsel = 0;          // pointer / geometry buffer of the current item
     HotMeta cur{}, nxt{};
-    if (item < nc) {
+    if (item < item_end) {
         hot_meta_issue(a, item, lane, cur);
         hot_meta_commit<HAS_H>(a, lane, gbs, hbs, gam_g, gam_h, NE, sptr, cur);
         if (mine(cur)) {
@@ -671,9 +676,9 @@ k_hot_outgoing(StepArgs a) {
         }
         cp_async_commit();
     }
-    while (item < nc) {
+    while (item < item_end) {
         const int nitem = item + nw;
-        const bool has_next = nitem < nc;
+        const bool has_next = nitem < item_end;
         unsigned long long* sp_cur = sptr + gsel * HOT_PTRS;
         unsigned long long* sp_nxt = sptr + (gsel ^ 1) * HOT_PTRS;
         if (has_next) hot_meta_issue(a, nitem, lane, nxt);
