@@ -579,9 +579,12 @@ struct RowDesc {
 };
 
 static int choose_chunks(int n, int D, long long base_rows_local) {
-    // pick the number of ix-chunks minimising padding waste, L <= MAX_L, prefer long rows
+    // Number of ix-chunks per row: rows of L = ceil(n / nch) <= MAX_L points, 32 rows per slab.
+    // Cost of a slab pass ~ (per-cell overhead + L): setting up a cell (upwind codes, equilibrium tables,
+    // moment reduction) costs about as much as 8 velocity points, so short rows only pay when they
+    // remove a lot of padding (measured at 8 GPUs: L = 4 gave 41.8 ms per step, L = 28 about 26 ms).
     int best = -1;
-    double best_waste = 1e9;
+    double best_cost = 1e300;
     for (int nch = 1; nch <= n; nch++) {
         int L = (n + nch - 1) / nch;
         if (L > MAX_L) continue;
@@ -589,9 +592,9 @@ static int choose_chunks(int n, int D, long long base_rows_local) {
         if ((long long)nch * L > NT_MAX) continue;
         if (nch > 1 && base_rows_local < 32) continue;   // a warp must not span more than two chunks
         long long rows = base_rows_local * nch;
-        long long padded = (rows + 31) / 32 * 32;
-        double waste = 1.0 - (double)(base_rows_local * n) / (double)(padded * L);
-        if (waste < best_waste - 0.08) { best_waste = waste; best = nch; }   // prefer long rows unless padding drops by > 8%
+        long long slabs = (rows + 31) / 32;
+        double cost = (double)slabs * (8.0 + L);
+        if (cost < best_cost * 0.98) { best_cost = cost; best = nch; }   // ties: the longer rows
     }
     return best;
 }
