@@ -217,7 +217,12 @@ static int do_allreduce(dugks_handle* h, double* buf, size_t n) {
 // are compile-time; create() picks the smallest that fits the mesh / velocity layout.
 // Points per chunk: 4 where the moment accumulators set the register count anyway (2 CTAs/SM),
 // 2 for the table-heavy phase-2 kernels so that they run 3 CTAs/SM (profiles/r01_occupancy_ab.txt)
-constexpr int CI_OUT1 = 4, CI_OUT2 = 2, CI_UPD = 4, CI_RLX = 2;
+#ifndef DUGKS_CI_OUT1
+#define DUGKS_CI_OUT1 4
+#endif
+constexpr int CI_OUT1 = DUGKS_CI_OUT1, CI_OUT2 = 2, CI_RLX = 2;
+// update kernel of the flux-buffer path: 4 points per chunk, 2 when h doubles the streams (shared memory per CTA)
+#define CI_UPD (H ? 2 : 4)
 template <int PHASE, bool H>
 static void launch_hot_outgoing(dugks_handle* h, const StepArgs& a) {
     const size_t sm = PHASE == 1 ? h->hsmem_out1 : h->hsmem_out2;
