@@ -96,6 +96,10 @@ struct dugks_handle {
     dugks_allreduce_fn reduce = nullptr;
     void* reduce_user = nullptr;
     void* nccl_comm = nullptr;
+    // host side of the accessors: pinned staging buffer, last boundary macros the caller set
+    double* pin = nullptr;
+    size_t pin_count = 0;
+    std::vector<double> last_rho_b, last_U_b, last_T_b;
     // stats
     uint64_t launches = 0, steps = 0;
     // kernel timing
@@ -647,6 +651,7 @@ extern "C" void dugks_destroy(dugks_handle_t* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->nccl_comm && g_nccl.destroy) g_nccl.destroy(h->nccl_comm);
     for (auto& b : h->bufs) cudaFree(b.p);
+    if (h->pin) cudaFreeHost(h->pin);
     for (auto& e : h->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto& e : h->pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -1132,6 +1137,11 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
     }
     for (int b = 0; b < nbf; b++)
         for (int d = 0; d < 3; d++) fmac[(size_t)(nif + b) * MAC_N + 1 + d] = U_b[(size_t)b * 3 + d];
+    if (nbf > 0) {
+        h->last_rho_b.assign(rho_b, rho_b + nbf);
+        h->last_U_b.assign(U_b, U_b + (size_t)3 * nbf);
+        h->last_T_b.assign(T_b, T_b + nbf);
+    }
     TRYB(dev_upload(h, &A.cmac, cmac));
     TRYB(dev_upload(h, &A.bmac, bmac));
     TRYB(dev_upload(h, &A.fmac, fmac));
@@ -1298,17 +1308,32 @@ extern "C" int dugks_sync(dugks_handle_t* h) {
 
 extern "C" void* dugks_stream(dugks_handle_t* h) { return h ? (void*)h->stream : nullptr; }
 
-static int fetch(dugks_handle* h, const double* dev, size_t n, std::vector<double>& host) {
-    host.resize(n);
+// D2H through a pinned staging buffer owned by the handle (pageable copies run at a fraction of the
+// PCIe rate and the macro fields are read every step by the host's time loop)
+static int fetch_pinned(dugks_handle* h, const double* dev, size_t n, const double** out) {
     CUDA_TRY(h, cudaSetDevice(h->device));
-    CUDA_TRY(h, cudaMemcpyAsync(host.data(), dev, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (n > h->pin_count) {
+        if (h->pin) cudaFreeHost(h->pin);
+        h->pin = nullptr; h->pin_count = 0;
+        CUDA_TRY(h, cudaHostAlloc((void**)&h->pin, n * sizeof(double), cudaHostAllocDefault));
+        h->pin_count = n;
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(h->pin, dev, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    *out = h->pin;
+    return 0;
+}
+static int fetch(dugks_handle* h, const double* dev, size_t n, std::vector<double>& host) {
+    const double* p = nullptr;
+    int rc = fetch_pinned(h, dev, n, &p);
+    if (rc) return rc;
+    host.assign(p, p + n);
     return 0;
 }
 
-static void unpack_macros(const std::vector<double>& m, size_t n, double* rho, double* U, double* T, double* q, double* tau) {
+static void unpack_macros(const double* m, size_t n, double* rho, double* U, double* T, double* q, double* tau) {
     for (size_t k = 0; k < n; k++) {
-        const double* p = m.data() + k * MAC_N;
+        const double* p = m + k * MAC_N;
         if (rho) rho[k] = p[0];
         if (U) { U[3 * k] = p[1]; U[3 * k + 1] = p[2]; U[3 * k + 2] = p[3]; }
         if (T) T[k] = p[4];
@@ -1319,8 +1344,8 @@ static void unpack_macros(const std::vector<double>& m, size_t n, double* rho, d
 
 extern "C" int dugks_get_cell_macros(dugks_handle_t* h, double* rho, double* U, double* T, double* q, double* tau) {
     if (!h) return DUGKS_ERR_INVALID;
-    std::vector<double> m;
-    int rc = fetch(h, h->A.cmac, (size_t)h->nc * MAC_N, m);
+    const double* m = nullptr;
+    int rc = fetch_pinned(h, h->A.cmac, (size_t)h->nc * MAC_N, &m);
     if (rc) return rc;
     unpack_macros(m, h->nc, rho, U, T, q, tau);
     return 0;
@@ -1328,8 +1353,8 @@ extern "C" int dugks_get_cell_macros(dugks_handle_t* h, double* rho, double* U, 
 
 extern "C" int dugks_get_face_macros(dugks_handle_t* h, double* rho, double* U, double* T, double* q, double* tau) {
     if (!h) return DUGKS_ERR_INVALID;
-    std::vector<double> m;
-    int rc = fetch(h, h->A.fmac, (size_t)h->nf * MAC_N, m);
+    const double* m = nullptr;
+    int rc = fetch_pinned(h, h->A.fmac, (size_t)h->nf * MAC_N, &m);
     if (rc) return rc;
     unpack_macros(m, h->nf, rho, U, T, q, tau);
     return 0;
@@ -1350,6 +1375,18 @@ extern "C" int dugks_get_boundary_macros(dugks_handle_t* h, double* rho_b, doubl
 
 extern "C" int dugks_set_boundary_macros(dugks_handle_t* h, const double* rho_b, const double* U_b, const double* T_b) {
     if (!h) return DUGKS_ERR_INVALID;
+    {
+        // arrays identical to the ones set last (the usual case: fixedValue patches that do not vary in
+        // time) are a no-op: nothing is copied and the wall in-flux constants stay valid
+        const size_t nb = (size_t)h->nbf;
+        auto same = [](const double* p, const std::vector<double>& last, size_t n) {
+            return p == nullptr || (last.size() == n && memcmp(p, last.data(), n * sizeof(double)) == 0);
+        };
+        if (same(rho_b, h->last_rho_b, nb) && same(U_b, h->last_U_b, 3 * nb) && same(T_b, h->last_T_b, nb)) return 0;
+        if (rho_b) h->last_rho_b.assign(rho_b, rho_b + nb);
+        if (U_b) h->last_U_b.assign(U_b, U_b + 3 * nb);
+        if (T_b) h->last_T_b.assign(T_b, T_b + nb);
+    }
     std::vector<double> m;
     int rc = fetch(h, h->A.bmac, (size_t)h->nbf * 5, m);
     if (rc) return rc;

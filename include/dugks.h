@@ -217,7 +217,8 @@ int dugks_sync(dugks_handle_t* h);
 
 /* Caller-side update of fixedValue boundary macros (time-varying BCs).
  * Any pointer may be NULL (unchanged).  Wall in-flux constants
- * (fvDVM.C:263-309) are recomputed. */
+ * (fvDVM.C:263-309) are recomputed.  Arrays identical to the ones passed last
+ * (or at create) are a no-op. */
 int dugks_set_boundary_macros(dugks_handle_t* h, const double* rho_b,
                               const double* U_b, const double* T_b);
 
