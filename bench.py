@@ -33,6 +33,7 @@ WORKLOADS = {
     "cavity3d_32_gh28": ("cavity3d", dict(n=32, nDV=28)),
     "cavity3d_16_gh16": ("cavity3d", dict(n=16, nDV=16)),
     "cavity2d_60_gh28": ("cavity2d", dict(n=60, nDV=28)),            # demo/cavity shape
+    "tri2d_316_gh28": ("tri2d", dict(n=316, nDV=28)),                # BASELINE configs[3] shape: ~200k triangles
 }
 # bounded CPU sample of the same workload shape (3-D cavity, 28^3 GH velocities, same gas/BCs)
 CPU_SAMPLE = ("cavity3d", dict(n=8, nDV=28))
@@ -42,6 +43,8 @@ def build_case(kind, kw):
     from dugksfoam_b200 import case as cs
     if kind == "cavity3d":
         return cs.cavity3d_case(kw["n"], kw["nDV"])
+    if kind == "tri2d":
+        return cs.tri_cavity_case(kw["n"], kw["nDV"])
     return cs.cavity2d_case(kw["n"], kw["nDV"], quad=kw.get("quad", "GH"))
 
 
@@ -142,7 +145,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     kind, kw = WORKLOADS[args.workload]
-    wl_name = f"{'3-D' if kind == 'cavity3d' else '2-D'} cavity {kw['n']}^{3 if kind == 'cavity3d' else 2} hex cells x " \
+    wl_name = f"{'3-D' if kind == 'cavity3d' else '2-D'} cavity {kw['n']}^{3 if kind == 'cavity3d' else 2} " \
+              f"{'triangular-prism (unstructured)' if kind == 'tri2d' else 'hex'} cells x " \
               f"{kw['nDV']}^{3 if kind == 'cavity3d' else 2} {kw.get('quad', 'GH')} velocities, Kn=0.075 argon, Maxwell walls"
 
     if args.impl == "reference":
