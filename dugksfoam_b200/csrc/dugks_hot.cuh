@@ -127,6 +127,11 @@ __device__ __forceinline__ unsigned long long l2_evict_first_policy() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
+__device__ __forceinline__ unsigned long long l2_evict_last_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 __device__ __forceinline__ void cp_async16_ef(uint32_t sdst, const void* gsrc, unsigned long long pol) {
     asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(sdst), "l"(gsrc), "l"(pol));
 }
@@ -1036,6 +1041,7 @@ k_hot_relax_update(StepArgs a) {
         }
     };
     const unsigned long long pol_ef = l2_evict_first_policy();
+    const unsigned long long pol_el = l2_evict_last_policy();
     const int nw = gridDim.x * HOT_WARPS;
     int item = blockIdx.x * HOT_WARPS + wib;
     uint32_t q = 0;
@@ -1088,8 +1094,8 @@ k_hot_relax_update(StepArgs a) {
                 hot_stage_one_ef<CI>(sdst + (fld * NSLOT + 0) * (CI * 256), fld ? hts : gts, offc, coff, pol_ef);
                 hot_stage_one_ef<CI>(sdst + (fld * NSLOT + 1) * (CI * 256), fld ? hbs : gbs, offc, coff, pol_ef);
 #pragma unroll
-                for (int j = 0; j < NE; j++)
-                    hot_stage_one<CI>(sdst + (fld * NSLOT + 2 + j) * (CI * 256), fld ? fk_h : fk_g, offf[j], coff);
+                for (int j = 0; j < NE; j++)   // every face block is read by two cells: keep it in L2 for the second one
+                    hot_stage_one_ef<CI>(sdst + (fld * NSLOT + 2 + j) * (CI * 256), fld ? fk_h : fk_g, offf[j], coff, pol_el);
             }
         };
         // outward area vectors (sign folded in) and the face equilibria of the internal faces
