@@ -64,7 +64,7 @@ struct dugks_handle {
     // sizes
     int nc = 0, nif = 0, nbf = 0, nf = 0, D = 3;
     int n1d = 0, nxi = 0;          // global DV grid
-    int nch = 1, L = 0, Rs = 32, nslab = 0, ntab = 0, tabw = 0;
+    int nch = 1, L = 0, Lt = 0, Rs = 32, nslab = 0, ntab = 0, tabw = 0;
     int nrows = 0;                 // padded local rows = nslab*Rs
     int nvl = 0;                   // local (real) DVs
     bool hasH = true;
@@ -339,6 +339,8 @@ static int hot_configure(dugks_handle* h) {
     h->hot_grid_half = std::max(1, std::min(dev_sms * std::max(occ_half, 1), max_ctas));
     h->hot_grid_axis = std::max(1, std::min(dev_sms * std::max(occ_axis, 1), max_ctas));
     if (getenv("DUGKS_VERBOSE"))
+        fprintf(stderr, "dugks: rows of %d points, %d slabs, short-row tail slab: %d points per row\n", h->L, h->nslab, h->Lt);
+    if (getenv("DUGKS_VERBOSE"))
         fprintf(stderr, "dugks: hot kernels NE=%d smem %zu/%zu/%zu/%zu B, CTAs per SM %d/%d/%d/%d, axis cells %d of %d, split %d (%d CTAs/SM)\n", h->hot_ne, h->hsmem_out1,
                 h->hsmem_out2, h->hsmem_upd, h->hsmem_rlx, occ[0], occ[1], occ[2], occ[3], h->n_axis, h->nc, (int)h->split_axis, occ_axis);
     return 0;
@@ -585,6 +587,7 @@ static int step_impl(dugks_handle* h, double dt) {
 struct RowDesc {
     int iy, iz, chunk;
     double y, z, w;
+    int cbase = 0, len = 0;   // first ix of the row and its number of points
 };
 
 static int choose_chunks(int n, int D, long long base_rows_local) {
@@ -797,6 +800,27 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
         int sa = (a.z < 0 ? 0 : 2) + (a.y < 0 ? 0 : 1), sb = (b.z < 0 ? 0 : 2) + (b.y < 0 ? 0 : 1);
         return sa < sb;
     });
+    for (auto& rd : rows) { rd.cbase = rd.chunk * L; rd.len = L; }
+    // short-row tail slab (dv_len, dugks_device.cuh): the rows that would leave the last slab mostly
+    // empty are cut into ix-chunks of Lt points and fill the lanes of one short slab
+    h->Lt = 0;
+    {
+        const int r_last = (int)rows.size() % h->Rs;
+        const bool allow = nch == 1 && getenv("DUGKS_NO_TAIL") == nullptr && getenv("DUGKS_NO_HOT") == nullptr;
+        if (allow && r_last > 0 && h->Rs / r_last >= 2 && n >= 2) {
+            int ncht = std::min(h->Rs / r_last, n);
+            const int Lt = (n + ncht - 1) / ncht;
+            ncht = (n + Lt - 1) / Lt;
+            if (r_last * ncht <= h->Rs && Lt < L && ncht * Lt <= NT_MAX) {
+                std::vector<RowDesc> tail(rows.end() - r_last, rows.end());
+                rows.resize(rows.size() - r_last);
+                for (int ct = 0; ct < ncht; ct++)
+                    for (RowDesc rd : tail) { rd.chunk = ct; rd.cbase = ct * Lt; rd.len = Lt; rows.push_back(rd); }
+                h->Lt = Lt;
+                h->ntab = std::max(h->ntab, ncht * Lt);
+            }
+        }
+    }
     const int nreal = (int)rows.size();
     h->nrows = (nreal + h->Rs - 1) / h->Rs * h->Rs;
     h->nslab = h->nrows / h->Rs;
@@ -805,7 +829,7 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
     std::vector<int> row_cb(h->nrows);
     for (int k = 0; k < h->nrows; k++) {
         const RowDesc& rd = rows[std::min(k, nreal - 1)];   // padding rows duplicate the last row with weight 0
-        row_y[k] = rd.y; row_z[k] = rd.z; row_cb[k] = rd.chunk * L;
+        row_y[k] = rd.y; row_z[k] = rd.z; row_cb[k] = rd.cbase;
         if (k < nreal) row_w[k] = rd.w;
     }
     // tables along x: entries beyond n duplicate the last abscissa with weight 0
@@ -820,7 +844,8 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
     for (int k0 = 0; k0 < h->nrows; k0 += 32) {
         int mn = 1 << 30, mx = -1;
         for (int k = k0; k < k0 + 32; k++) { mn = std::min(mn, row_cb[k]); mx = std::max(mx, row_cb[k]); }
-        h->tabw = std::max(h->tabw, mx + L - mn);
+        const int len = rows[std::min(k0, nreal - 1)].len;
+        h->tabw = std::max(h->tabw, mx + len - mn);
     }
     // flat index <-> global id, mirror partners
     h->flat_gid.assign(h->nflat, -1);
@@ -828,8 +853,8 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
     for (int k = 0; k < nreal; k++) {
         int s = k / h->Rs, r = k % h->Rs;
         const RowDesc& rd = rows[k];
-        for (int i = 0; i < L; i++) {
-            int ix = rd.chunk * L + i;
+        for (int i = 0; i < rd.len; i++) {
+            int ix = rd.cbase + i;
             if (ix >= n) continue;
             int gid = (rd.iz * ny + rd.iy) * n + ix;
             size_t flat = ((size_t)s * L + i) * h->Rs + r;
@@ -1091,6 +1116,7 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
     h->use_tma = getenv("DUGKS_NO_TMA") == nullptr;            // test hook: per-element LDG kernels instead
     h->ci = TMA_CI;
     h->use_fast = getenv("DUGKS_FORCE_GENERIC") == nullptr;   // test hook: run every cell through the generic kernels
+    if (h->Lt > 0) h->use_fast = false;                        // only the generic and second-generation kernels know short rows
     TRYB(dev_upload(h, &d_d, std::vector<double>(mesh->V, mesh->V + nc))); M.V = d_d;
     TRYB(dev_upload(h, &d_i, b_owner)); M.b_owner = d_i;
     TRYB(dev_upload(h, &d_i, b_kind)); M.b_kind = d_i;
@@ -1100,7 +1126,7 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
     TRYB(dev_upload(h, &d_d, b_r)); M.b_r = d_d;
     TRYB(dev_upload(h, &d_d, std::vector<double>(mesh->deltaCoeffs, mesh->deltaCoeffs + nif))); M.dcoef_int = d_d;
     DevDV& V = A.dv;
-    V.L = L; V.Rs = h->Rs; V.nslab = h->nslab; V.ntab = h->ntab; V.hasH = h->hasH; V.tabw = h->tabw;
+    V.L = L; V.Lt = h->Lt; V.Rs = h->Rs; V.nslab = h->nslab; V.ntab = h->ntab; V.hasH = h->hasH; V.tabw = h->tabw;
     TRYB(dev_upload(h, &d_d, tx)); V.tx = d_d;
     TRYB(dev_upload(h, &d_d, row_y)); V.row_y = d_d;
     TRYB(dev_upload(h, &d_d, row_z)); V.row_z = d_d;

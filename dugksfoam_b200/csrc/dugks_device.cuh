@@ -57,6 +57,7 @@ struct DevMesh {
 
 struct DevDV {
     int L, Rs, nslab, ntab, hasH;
+    int Lt;                  // > 0: the LAST slab holds short rows of Lt points (stride stays L), see dv_len
     int tabw;                // table width: largest span (in table entries) any warp needs
     const double* tx;        // [5][ntab]: xi_x, w_x, w_x xi_x, w_x xi_x^2, w_x xi_x^3
     const double* row_y;     // [nslab*Rs] xi_y of the row
@@ -64,6 +65,14 @@ struct DevDV {
     const double* row_w;     // [nslab*Rs] w_z*w_y (0 for padding rows)
     const int* row_cbase;    // [nslab*Rs] first table index of the row's chunk
 };
+
+// Points per row of a slab.  All slabs use rows of L points except, optionally, the last one: when a
+// rank's row count leaves a nearly empty last slab (98 rows = 3 slabs + 2 rows at 8 GPUs), those few
+// rows are cut into ix-chunks of Lt points so that they fill the 32 lanes of ONE short slab instead of
+// idling 30 of them for L points.  Array strides are L everywhere; only loop counts use dv_len.
+__host__ __device__ __forceinline__ int dv_len(const DevDV& dv, int slab) {
+    return (dv.Lt > 0 && slab == dv.nslab - 1) ? dv.Lt : dv.L;
+}
 
 // ---- macro arrays: 9 doubles per cell / face: rho, Ux,Uy,Uz, T, tau, qx,qy,qz
 #define MAC_N 9

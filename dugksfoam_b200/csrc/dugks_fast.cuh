@@ -111,7 +111,7 @@ k_cell_outgoing_fast(StepArgs a) {
         const double y = dv.row_y[grow], z = dv.row_z[grow], wr = dv.row_w[grow];
         const int cb = dv.row_cbase[grow];
         int tmin, span;
-        table_range(dv, cb, tmin, span);
+        table_range(dv, cb, tmin, span, dv.L);
         __syncwarp();
         const int cidx = c * L * Rs + r;
         int oidx[FAST_NE];

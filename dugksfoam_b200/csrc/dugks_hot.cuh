@@ -82,7 +82,7 @@ __global__ void k_build_upwind(StepArgs a, uint4* out, int* bad) {
             const int o = a.m.e_other[e0 + j];
             const bool isown = a.m.e_owner[e0 + j] != 0;
             unsigned full = 0, tie = 0;
-            for (int i = 0; i < dv.L; i++) {
+            for (int i = 0; i < dv_len(dv, slab); i++) {
                 const double phi = dot_exact(dv.tx[cb + i], y, z, g[6], g[7], g[8]);
                 if (o >= 0) {
                     const bool neg = phi < -DUGKS_VSMALL, pos = phi >= DUGKS_VSMALL;
@@ -99,7 +99,7 @@ __global__ void k_build_upwind(StepArgs a, uint4* out, int* bad) {
                 }
             }
             unsigned code = 0;
-            if (!hot_encode(full, tie, dv.L, code)) atomicOr(bad, 1);
+            if (!hot_encode(full, tie, dv_len(dv, slab), code)) atomicOr(bad, 1);
             codes[j] = (unsigned short)code;
         }
         uint4 w;
@@ -659,9 +659,10 @@ k_hot_outgoing(StepArgs a) {
     x.kd = (double)(a.gas.K + 3 - a.gas.D);
     x.cb = dv.row_cbase[grow];
     x.tmin = 0; x.span = 0;
-    if (PHASE == 2) table_range(dv, x.cb, x.tmin, x.span);
-    x.lane = lane; x.L = L; x.blk = blk; x.nm = a.nm;
-    x.nchunk = (L + CI - 1) / CI;
+    const int Ln = dv_len(dv, a.slab);     // points per row of THIS slab (strides use L)
+    if (PHASE == 2) table_range(dv, x.cb, x.tmin, x.span, Ln);
+    x.lane = lane; x.L = Ln; x.blk = blk; x.nm = a.nm;
+    x.nchunk = (Ln + CI - 1) / CI;
     x.slab_b = slab_b;
 
     const int nw = gridDim.x * HOT_WARPS;
@@ -834,7 +835,8 @@ k_hot_update(StepArgs a) {
     const int grow = a.slab * 32 + lane;
     const double y = dv.row_y[grow], z = dv.row_z[grow], wr = dv.row_w[grow];
     const int cb = dv.row_cbase[grow];
-    const int nchunk = (L + CI - 1) / CI;
+    const int Ln = dv_len(dv, a.slab);     // points per row of THIS slab (strides use L)
+    const int nchunk = (Ln + CI - 1) / CI;
     const int nm = a.nm;
 
     const unsigned long long pol_ef = l2_evict_first_policy();
@@ -936,7 +938,7 @@ k_hot_update(StepArgs a) {
 #pragma unroll
                 for (int u = 0; u < CI; u++) {
                     const double vnew = (-1.0 / 3) * sf[u * 32] + (4.0 / 3) * sf[(CI + u) * 32] - sum[u] * dtv;   // :937,952
-                    if (i0 + u >= L) continue;   // tail chunk (warp-uniform)
+                    if (i0 + u >= Ln) continue;   // tail chunk (warp-uniform)
                     __stcs((fld == 0 ? gdst : hdst) + (i0 + u) * 32, vnew);
                     if (fld == 0) {
                         A[0] = fma(W[u][0], vnew, A[0]); A[1] = fma(W[u][1], vnew, A[1]);
@@ -1016,9 +1018,10 @@ k_hot_relax_update(StepArgs a) {
     const int grow = a.slab * 32 + lane;
     const double y = dv.row_y[grow], z = dv.row_z[grow], wr = dv.row_w[grow];
     const int cb = dv.row_cbase[grow];
+    const int Ln = dv_len(dv, a.slab);     // points per row of THIS slab (strides use L)
     int tmin, span;
-    table_range(dv, cb, tmin, span);
-    const int nchunk = (L + CI - 1) / CI;
+    table_range(dv, cb, tmin, span, Ln);
+    const int nchunk = (Ln + CI - 1) / CI;
     const int nm = a.nm;
     const double kd = (double)(a.gas.K + 3 - a.gas.D);
 
@@ -1187,7 +1190,7 @@ k_hot_relax_update(StepArgs a) {
 #pragma unroll
                 for (int u = 0; u < CI; u++) {
                     const double vnew = (-1.0 / 3) * sf[u * 32] + (4.0 / 3) * sf[(CI + u) * 32] - sum[u] * dtv;   // :937,952
-                    if (i0 + u >= L) continue;   // tail chunk (warp-uniform)
+                    if (i0 + u >= Ln) continue;   // tail chunk (warp-uniform)
                     __stcs((fld == 0 ? gdst : hdst) + (i0 + u) * 32, vnew);
                     if (fld == 0) {
                         A[0] = fma(W[u][0], vnew, A[0]); A[1] = fma(W[u][1], vnew, A[1]);
@@ -1258,10 +1261,11 @@ k_hot_halfstep(StepArgs a, int tw) {
     const int grow = a.slab * 32 + lane;
     const double y = dv.row_y[grow], z = dv.row_z[grow];
     const int cb = dv.row_cbase[grow];
+    const int Ln = dv_len(dv, a.slab);                               // points per row of THIS slab (strides use L)
     int tmin, span;
-    table_range(dv, cb, tmin, span);
+    table_range(dv, cb, tmin, span, Ln);
     const double kd = (double)(a.gas.K + 3 - a.gas.D);
-    const int npiece = blk / 2;                                      // 16-byte pieces per field block
+    const int npiece = Ln * 16;                                      // 16-byte pieces per field block
     const unsigned long long pol_ef = l2_evict_first_policy();
 
     auto stage_cell = [&](int c, int buf) {
@@ -1305,14 +1309,14 @@ k_hot_halfstep(StepArgs a, int tw) {
         double* dh = HAS_H ? hbs + (size_t)c * blk + lane : nullptr;
         const double* xt0 = xtab + (cb - tmin) * 4;
 #pragma unroll 4
-        for (int i = 0; i < L; i++) {
+        for (int i = 0; i < Ln; i++) {
             const double2 x01 = lds2(xt0 + i * 4);
             const double cc = x01.y + YZ2;                           // cSqrByRT - D - 2
             const double cq = xt0[i * 4 + 2] + QYZ;                  // (1-Pr) cqBy5pRT
             const double gM = x01.x * EYZ;                           // rf * gEqBGK
             __stcs(dg + i * 32, fma(omrf, sg[i * 32], fma(cq, cc, 1.0) * gM));                                  // :405,1042
             if (HAS_H)
-                __stcs(dh + i * 32, fma(omrf, sg[(L + i) * 32], (kd + cq * ((cc + 2.0) * kd - 2.0 * a.gas.K)) * gM * e.RT));   // :406,1043
+                __stcs(dh + i * 32, fma(omrf, sg[(Ln + i) * 32], (kd + cq * ((cc + 2.0) * kd - 2.0 * a.gas.K)) * gM * e.RT));   // :406,1043
         }
         __syncwarp();   // stage and tables are free again
     }
@@ -1338,8 +1342,9 @@ k_hot_bnd_relax(StepArgs a, int tw) {
     const int grow = a.slab * 32 + lane;
     const double y = dv.row_y[grow], z = dv.row_z[grow];
     const int cb = dv.row_cbase[grow];
+    const int Ln = dv_len(dv, a.slab);
     int tmin, span;
-    table_range(dv, cb, tmin, span);
+    table_range(dv, cb, tmin, span, Ln);
     const double kd = (double)(a.gas.K + 3 - a.gas.D);
     for (int b = blockIdx.x * WARPS_PER_CTA + wib; b < a.m.nbf; b += gridDim.x * WARPS_PER_CTA) {
         const int kind = a.m.b_kind[b];
@@ -1378,7 +1383,7 @@ k_hot_bnd_relax(StepArgs a, int tw) {
         __syncwarp();
         const size_t bbase = ((size_t)a.slab * a.m.nbf + b) * blk + lane;
         const double* xt0 = xtab + (cb - tmin) * 4;
-        for (int i = 0; i < L; i++) {
+        for (int i = 0; i < Ln; i++) {
             const double phi = __dadd_rn(__dadd_rn(__dmul_rn(txs[cb + i], sx), ySy), zSz);
             const double2 x01 = lds2(xt0 + i * 4), x23 = lds2(xt0 + i * 4 + 2);
             double g = a.gsb[bbase + (size_t)i * 32];

@@ -195,7 +195,7 @@ __device__ __forceinline__ void nbr_gradient(const CellStage& s, int ne, const N
 }
 
 // warp-uniform table range of the rows held by this warp
-__device__ __forceinline__ void table_range(const DevDV& dv, int cb, int& tmin, int& span) {
+__device__ __forceinline__ void table_range(const DevDV& dv, int cb, int& tmin, int& span, int len) {
     int mn = cb, mx = cb;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -203,7 +203,7 @@ __device__ __forceinline__ void table_range(const DevDV& dv, int cb, int& tmin, 
         mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     }
     tmin = mn;
-    span = mx + dv.L - mn;
+    span = mx + len - mn;
     if (span > dv.tabw) span = dv.tabw;  // create() sizes tabw as the largest span of any warp
 }
 
@@ -243,7 +243,7 @@ k_cell_halfstep(StepArgs a, int init) {
         double y = dv.row_y[grow], z = dv.row_z[grow];
         int cb = dv.row_cbase[grow];
         int tmin, span;
-        table_range(dv, cb, tmin, span);
+        table_range(dv, cb, tmin, span, dv_len(dv, a.slab));
         const double* mc = a.cmac + (size_t)c * MAC_N;
         double rf = init ? 1.0 : 1.5 * a.dt / (2.0 * mc[5] + a.dt);   // discreteVelocity.C:393
         EqCoef e = make_eq(a.gas, mc, rf);
@@ -262,7 +262,7 @@ k_cell_halfstep(StepArgs a, int init) {
         const double* src_h = a.ht;
         double* dst_g = init ? a.gt : a.gb;
         double* dst_h = init ? a.ht : a.hb;
-        for (int i = 0; i < dv.L; i++) {
+        for (int i = 0; i < dv_len(dv, a.slab); i++) {
             size_t idx = base + (size_t)i * dv.Rs;
             double cc = tab[tw + t0 + i] + YZ2;          // cSqrByRT - D - 2
             double cq = tab[2 * tw + t0 + i] + QYZ;      // (1-Pr) cqBy5pRT
@@ -311,7 +311,7 @@ k_cell_outgoing(StepArgs a) {
         double y = dv.row_y[grow], z = dv.row_z[grow], wr = dv.row_w[grow];
         int cb = dv.row_cbase[grow];
         int tmin, span;
-        table_range(dv, cb, tmin, span);
+        table_range(dv, cb, tmin, span, dv_len(dv, a.slab));
         int ne = stage_cell(a, c, lane, st);
         if (a.skip_small && ne <= FAST_NE) continue;   // warp-uniform
         int nint = a.m.cell_nint[c];
@@ -413,20 +413,20 @@ k_cell_outgoing(StepArgs a) {
             if (fast) {
                 NbrVals<HAS_H> A, B;
                 nbr_load<HAS_H>(a, st, ne, cellbase, (size_t)r, A);
-                for (int i = 0; i < dv.L; i += 2) {
+                for (int i = 0; i < dv_len(dv, a.slab); i += 2) {
                     double gg[3], gh[3];
-                    bool hasB = i + 1 < dv.L;
+                    bool hasB = i + 1 < dv_len(dv, a.slab);
                     if (hasB) nbr_load<HAS_H>(a, st, ne, cellbase, (size_t)(i + 1) * dv.Rs + r, B);
                     nbr_gradient<HAS_H>(st, ne, A, gg, gh);
                     body(i, A.v0, A.w0, gg, gh);
-                    if (i + 2 < dv.L) nbr_load<HAS_H>(a, st, ne, cellbase, (size_t)(i + 2) * dv.Rs + r, A);
+                    if (i + 2 < dv_len(dv, a.slab)) nbr_load<HAS_H>(a, st, ne, cellbase, (size_t)(i + 2) * dv.Rs + r, A);
                     if (hasB) {
                         nbr_gradient<HAS_H>(st, ne, B, gg, gh);
                         body(i + 1, B.v0, B.w0, gg, gh);
                     }
                 }
             } else {
-                for (int i = 0; i < dv.L; i++) {
+                for (int i = 0; i < dv_len(dv, a.slab); i++) {
                     size_t ir = (size_t)i * dv.Rs + r;
                     double v0 = a.gb[base + (size_t)i * dv.Rs];
                     double w0 = HAS_H ? a.hb[base + (size_t)i * dv.Rs] : 0.0;
@@ -499,7 +499,7 @@ k_bnd_outgoing(StepArgs a, int far_only) {
         size_t bbase = dv_index(dv, a.slab, a.m.nbf, b, 0, r);
         const double* bm = a.bmac + (size_t)b * 5;
         const double* mc = a.cmac + (size_t)c * MAC_N;
-        for (int i = 0; i < dv.L; i++) {
+        for (int i = 0; i < dv_len(dv, a.slab); i++) {
             size_t ir = (size_t)i * dv.Rs + r;
             double x = txs[cb + i];
             double v0 = a.gb[cbase + (size_t)i * dv.Rs];
@@ -560,6 +560,7 @@ __global__ void k_bnd_symmetry(StepArgs a, const double* snap_g, const double* s
          t += (long long)gridDim.x * blockDim.x) {
         int j = (int)(t / ndvpad), k = (int)(t % ndvpad);
         int s = k / slabsz, rem = k % slabsz, i = rem / dv.Rs, r = rem % dv.Rs;
+        if (i >= dv_len(dv, s)) continue;
         int grow = s * dv.Rs + r;
         double x = dv.tx[dv.row_cbase[grow] + i], y = dv.row_y[grow], z = dv.row_z[grow];
         if (dot_exact(x, y, z, s0x, s0y, s0z) <= 0) {     // :775 (first face of the patch)
@@ -600,7 +601,7 @@ k_bnd_moments(StepArgs a) {
         double sx = Sf[0], sy = Sf[1], sz = Sf[2];
         size_t bbase = dv_index(dv, a.slab, a.m.nbf, b, 0, r);
         double A[4] = {0, 0, 0, 0}, B[2] = {0, 0};
-        for (int i = 0; i < dv.L; i++) {
+        for (int i = 0; i < dv_len(dv, a.slab); i++) {
             int t = cb + i;
             double x = txs[t];
             bool use = true;
@@ -666,7 +667,7 @@ k_wall_constants(StepArgs a, double* cin, double* win) {
         const double* bm = a.bmac + (size_t)b * 5;
         double A[4] = {0, 0, 0, 0}, B[2] = {0, 0}, inb = 0.0;
         double hfac = (a.gas.R * bm[4]) * (a.gas.K + 3 - a.gas.D);
-        for (int i = 0; i < dv.L; i++) {
+        for (int i = 0; i < dv_len(dv, a.slab); i++) {
             int t = cb + i;
             double x = txs[t];
             double phi = dot_exact(x, y, z, sx, sy, sz);
@@ -795,7 +796,7 @@ k_bnd_relax(StepArgs a) {
         EqCoef e = make_eq(a.gas, mf, rf);
         double omrf = 1.0 - rf;
         size_t bbase = dv_index(dv, a.slab, a.m.nbf, b, 0, r);
-        for (int i = 0; i < dv.L; i++) {
+        for (int i = 0; i < dv_len(dv, a.slab); i++) {
             double x = txs[cb + i];
             size_t bo = bbase + (size_t)i * dv.Rs;
             double phi = dot_exact(x, y, z, sx, sy, sz);
@@ -906,15 +907,15 @@ k_cell_update(StepArgs a) {
             };
             Vals P, Q;
             load(0, P);
-            for (int i = 0; i < dv.L; i += 2) {
-                bool hasQ = i + 1 < dv.L;
+            for (int i = 0; i < dv_len(dv, a.slab); i += 2) {
+                bool hasQ = i + 1 < dv_len(dv, a.slab);
                 if (hasQ) load(i + 1, Q);
                 compute(i, P);
-                if (i + 2 < dv.L) load(i + 2, P);
+                if (i + 2 < dv_len(dv, a.slab)) load(i + 2, P);
                 if (hasQ) compute(i + 1, Q);
             }
         } else {
-            for (int i = 0; i < dv.L; i++) {
+            for (int i = 0; i < dv_len(dv, a.slab); i++) {
                 double x = txs[cb + i];
                 size_t ir = (size_t)i * dv.Rs + r;
                 size_t idx = base + (size_t)i * dv.Rs;
@@ -1007,7 +1008,7 @@ __global__ void k_bnd_init_mixed(StepArgs a) {
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
          t += (long long)gridDim.x * blockDim.x) {
         int b = (int)(t / slabsz), rem = (int)(t % slabsz), i = rem / dv.Rs, r = rem % dv.Rs;
-        if (a.m.b_kind[b] != K_MIXED) continue;
+        if (a.m.b_kind[b] != K_MIXED || i >= dv_len(dv, a.slab)) continue;
         int grow = a.slab * dv.Rs + r;
         double x = dv.tx[dv.row_cbase[grow] + i], y = dv.row_y[grow], z = dv.row_z[grow];
         const double* bm = a.bmac + (size_t)b * 5;

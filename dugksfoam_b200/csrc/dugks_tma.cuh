@@ -92,7 +92,7 @@ struct OutgoingCell {
         const double y = dv.row_y[grow], z = dv.row_z[grow], wr = dv.row_w[grow];
         const int cb = dv.row_cbase[grow];
         int tmin = 0, span = 0;
-        if (PHASE == 2) table_range(dv, cb, tmin, span);
+        if (PHASE == 2) table_range(dv, cb, tmin, span, dv.L);
         const int nchunk = (L + CI - 1) / CI;
         // exact upwind thresholds on the OUTWARD flux phi' = +-(xi.Sf) of this cell
         // (discreteVelocity.C:495,506: owner side full if phi >= VSMALL, neighbour side full if phi < -VSMALL)
