@@ -50,6 +50,7 @@ struct Nccl {
 static Nccl g_nccl;
 
 static thread_local std::string g_create_error = "no error";
+#define COURANT_BLOCKS 592   // partial results of the two-stage Courant-number reduction
 
 // ------------------------------------------------------------------------------
 struct DevBuf {
@@ -90,6 +91,7 @@ struct dugks_handle {
     int* d_mirror = nullptr;           // [3][nflat]
     double *snap_g = nullptr, *snap_h = nullptr;
     double* d_co = nullptr;
+    double* d_bstage = nullptr;        // [5 nbf] staging of dugks_set_boundary_macros
     bool has_sym = false, has_wall = false;
     size_t nflat = 0;                  // nslab*L*Rs
     // collective
@@ -1209,7 +1211,8 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
     TRYB(dev_alloc(h, &h->wall_cin, (size_t)nbf * h->nm));
     TRYB(dev_alloc(h, &h->wall_in, (size_t)nbf));
     TRYB(dev_alloc(h, &A.wall_diag, (size_t)nbf * 12));
-    TRYB(dev_alloc(h, &h->d_co, 2));
+    TRYB(dev_alloc(h, &h->d_co, 2 + 2 * COURANT_BLOCKS));
+    TRYB(dev_alloc(h, &h->d_bstage, (size_t)5 * nbf));
     A.wall_cin = h->wall_cin; A.wall_in = h->wall_in;
     A.gam_old_g = h->gam_a_g; A.gam_old_h = h->gam_a_h; A.gam_new_g = h->gam_b_g; A.gam_new_h = h->gam_b_h;
 
@@ -1413,17 +1416,23 @@ extern "C" int dugks_set_boundary_macros(dugks_handle_t* h, const double* rho_b,
         if (U_b) h->last_U_b.assign(U_b, U_b + 3 * nb);
         if (T_b) h->last_T_b.assign(T_b, T_b + nb);
     }
-    std::vector<double> m;
-    int rc = fetch(h, h->A.bmac, (size_t)h->nbf * 5, m);
+    if (h->nbf == 0) return 0;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    // H2D of the fields that were given into a staging buffer, scattered into bmac on the device
+    // (stream ordered: no device->host round trip, no synchronisation)
+    const size_t nb = (size_t)h->nbf;
+    double *d_rho = nullptr, *d_U = nullptr, *d_T = nullptr;
+    if (rho_b) { d_rho = h->d_bstage; CUDA_TRY(h, cudaMemcpyAsync(d_rho, rho_b, nb * sizeof(double), cudaMemcpyHostToDevice, h->stream)); }
+    if (U_b) { d_U = h->d_bstage + nb; CUDA_TRY(h, cudaMemcpyAsync(d_U, U_b, 3 * nb * sizeof(double), cudaMemcpyHostToDevice, h->stream)); }
+    if (T_b) { d_T = h->d_bstage + 4 * nb; CUDA_TRY(h, cudaMemcpyAsync(d_T, T_b, nb * sizeof(double), cudaMemcpyHostToDevice, h->stream)); }
+    k_set_bmac<<<(h->nbf + 127) / 128, 128, 0, h->stream>>>(h->A, d_rho, d_U, d_T);
+    int rc = check_launch(h, "k_set_bmac");
     if (rc) return rc;
-    for (int b = 0; b < h->nbf; b++) {
-        if (rho_b) m[(size_t)b * 5] = rho_b[b];
-        if (U_b) for (int d = 0; d < 3; d++) m[(size_t)b * 5 + 1 + d] = U_b[3 * b + d];
-        if (T_b) m[(size_t)b * 5 + 4] = T_b[b];
-    }
-    CUDA_TRY(h, cudaMemcpyAsync(h->A.bmac, m.data(), m.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    rc = h->hasH ? compute_wall_constants<true>(h) : compute_wall_constants<false>(h);
+    if (rc) return rc;
+    // the caller's arrays are borrowed for the call only: copies from pinned memory must have run
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    return h->hasH ? compute_wall_constants<true>(h) : compute_wall_constants<false>(h);
+    return 0;
 }
 
 extern "C" int dugks_get_wall_diag(dugks_handle_t* h, double* qWall, double* stressWall) {
@@ -1443,9 +1452,12 @@ extern "C" int dugks_courant(dugks_handle_t* h, double dt, double* maxCo, double
     if (h->nif == 0) { if (maxCo) *maxCo = 0; if (meanCo) *meanCo = 0; return 0; }
     CUDA_TRY(h, cudaSetDevice(h->device));
     StepArgs a = h->A;
-    k_courant<<<1, 1024, 0, h->stream>>>(a, std::sqrt((double)h->D) * h->xiMax, h->d_co);
+    const int nblk = std::max(1, std::min(COURANT_BLOCKS, (h->nif + 255) / 256));
+    k_courant<<<nblk, 256, 0, h->stream>>>(a, std::sqrt((double)h->D) * h->xiMax, h->d_co + 2);
     int rc = check_launch(h, "k_courant");
     if (rc) return rc;
+    k_courant_fold<<<1, 32, 0, h->stream>>>(h->d_co + 2, nblk, h->d_co);
+    if ((rc = check_launch(h, "k_courant_fold"))) return rc;
     double out[2];
     CUDA_TRY(h, cudaMemcpyAsync(out, h->d_co, sizeof out, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));

@@ -1027,8 +1027,10 @@ __global__ void k_init_tau(StepArgs a) {
     mc[5] = dugks_tau(a.gas, mc[4], mc[0]);
 }
 
-// fvDVM::getCoNum (fvDVM.C:1111-1119): out[0] = max, out[1] = sum over internal faces
-__global__ void k_courant(StepArgs a, double sqrtD_xiMax, double* out) {
+// fvDVM::getCoNum (fvDVM.C:1111-1119): out[0] = max, out[1] = sum over internal faces.
+// Two deterministic stages: every block reduces a fixed set of faces to part[2*blockIdx.x..], the last
+// launch (one block) folds the partials in index order.
+__global__ void k_courant(StepArgs a, double sqrtD_xiMax, double* part) {
     __shared__ double smax[32], ssum[32];
     double mx = 0.0, sm = 0.0;
     for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < a.m.nif; f += gridDim.x * blockDim.x) {
@@ -1047,7 +1049,22 @@ __global__ void k_courant(StepArgs a, double sqrtD_xiMax, double* out) {
     if (threadIdx.x == 0) {
         int nw = blockDim.x >> 5;
         for (int k = 1; k < nw; k++) { mx = fmax(mx, smax[k]); sm += ssum[k]; }
-        // one block only (grid = 1) keeps the sum deterministic
-        out[0] = mx; out[1] = sm;
+        part[2 * blockIdx.x] = mx; part[2 * blockIdx.x + 1] = sm;
     }
+}
+__global__ void k_courant_fold(const double* part, int nblocks, double* out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double mx = 0.0, sm = 0.0;
+    for (int k = 0; k < nblocks; k++) { mx = fmax(mx, part[2 * k]); sm += part[2 * k + 1]; }
+    out[0] = mx; out[1] = sm;
+}
+
+// dugks_set_boundary_macros: scatter the caller's boundary fields (any may be null) into bmac
+__global__ void k_set_bmac(StepArgs a, const double* rho_b, const double* U_b, const double* T_b) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.m.nbf) return;
+    double* bm = a.bmac + (size_t)b * 5;
+    if (rho_b) bm[0] = rho_b[b];
+    if (U_b) { bm[1] = U_b[3 * b]; bm[2] = U_b[3 * b + 1]; bm[3] = U_b[3 * b + 2]; }
+    if (T_b) bm[4] = T_b[b];
 }
