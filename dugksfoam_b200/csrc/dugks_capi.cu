@@ -527,7 +527,12 @@ static int compute_wall_constants(dugks_handle* h) {
     long long bitems = (long long)h->nbf * (h->Rs / 32);
     for (int s = 0; s < h->nslab; s++) {
         a.slab = s;
-        k_wall_constants<H><<<grid_for(bitems), WARPS_PER_CTA * 32, 0, h->stream>>>(a, h->wall_cin, h->wall_in);
+        if (h->use_hot && h->tabw <= 64) {
+            const int tw = h->tabw <= 32 ? 32 : 64;
+            const size_t sm = ((size_t)5 * h->ntab + (size_t)WARPS_PER_CTA * tw) * sizeof(double);
+            k_hot_wall_constants<H><<<grid_for(bitems), WARPS_PER_CTA * 32, sm, h->stream>>>(a, h->wall_cin, h->wall_in, tw);
+        } else
+            k_wall_constants<H><<<grid_for(bitems), WARPS_PER_CTA * 32, 0, h->stream>>>(a, h->wall_cin, h->wall_in);
         int rc;
         if ((rc = check_launch(h, "k_wall_constants"))) return rc;
     }

@@ -1404,3 +1404,75 @@ k_hot_bnd_relax(StepArgs a, int tw) {
         __syncwarp();
     }
 }
+
+// -------------------------------------------------------------------------------------------------
+// Wall constants with the separable Maxwellian (same sums as k_wall_constants, dugks_kernels.cuh;
+// fvDVM.C:263-309): moments of the incoming half-space Maxwellian per unit rho_w and inComingByRho.
+// Recomputed whenever the caller changes the wall velocity / temperature, so it is on the
+// end-to-end path of a time-varying boundary.
+template <bool HAS_H>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+k_hot_wall_constants(StepArgs a, double* cin, double* win, int tw) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    const DevDV& dv = a.dv;
+    double* txs = reinterpret_cast<double*>(dyn);                         // [5][ntab]
+    for (int k = threadIdx.x; k < 5 * dv.ntab; k += blockDim.x) txs[k] = dv.tx[k];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double* xtab = txs + 5 * dv.ntab + (size_t)wib * tw;                  // [tw] exp(-(x - U_x)^2 / 2RT)
+    const int nt = dv.ntab;
+    const int grow = a.slab * 32 + lane;
+    const double y = dv.row_y[grow], z = dv.row_z[grow], wr = dv.row_w[grow];
+    const int cb = dv.row_cbase[grow];
+    const int Ln = dv_len(dv, a.slab);
+    int tmin, span;
+    table_range(dv, cb, tmin, span, Ln);
+    const int nm = a.nm;
+    for (int b = blockIdx.x * WARPS_PER_CTA + wib; b < a.m.nbf; b += gridDim.x * WARPS_PER_CTA) {
+        if (a.m.b_kind[b] != K_MAXWELL_WALL) continue;   // warp-uniform
+        const double sx = a.m.b_Sf[(size_t)b * 3], sy = a.m.b_Sf[(size_t)b * 3 + 1], sz = a.m.b_Sf[(size_t)b * 3 + 2];
+        const double* bm = a.bmac + (size_t)b * 5;
+        const double RT = a.gas.R * bm[4], aw = 1.0 / RT;
+        const double sq = sqrt(2.0 * DUGKS_PI * RT);
+        const double p = (a.gas.D == 3) ? sq * sq * sq : ((a.gas.D == 2) ? sq * sq : sq);
+        for (int tt = lane; tt < span; tt += 32) {
+            const double cw = txs[tmin + tt] - bm[1];
+            xtab[tt] = exp(-0.5 * cw * cw * aw);
+        }
+        const double wy = y - bm[2], wz = z - bm[3];
+        const double EYZ = exp(-0.5 * (wy * wy + wz * wz) * aw) / p;
+        const double hfac = RT * (a.gas.K + 3 - a.gas.D);
+        const double ySy = __dmul_rn(y, sy), zSz = __dmul_rn(z, sz);
+        __syncwarp();
+        double A[4] = {0, 0, 0, 0}, B[2] = {0, 0}, inb = 0.0;
+        for (int i = 0; i < Ln; i++) {
+            const int t = cb + i;
+            const double phi = __dadd_rn(__dadd_rn(__dmul_rn(txs[t], sx), ySy), zSz);
+            if (phi <= 0) {                               // discreteVelocity.C:713
+                const double M = xtab[t - tmin] * EYZ;
+                A[0] = fma(txs[nt + t], M, A[0]);
+                A[1] = fma(txs[2 * nt + t], M, A[1]);
+                A[2] = fma(txs[3 * nt + t], M, A[2]);
+                A[3] = fma(txs[4 * nt + t], M, A[3]);
+                if (HAS_H) {
+                    B[0] = fma(txs[nt + t], M * hfac, B[0]);
+                    B[1] = fma(txs[2 * nt + t], M * hfac, B[1]);
+                }
+                if (phi < 0) inb += -(txs[nt + t] * wr) * phi * M;   // fvDVM.C:291-299
+            }
+        }
+        double v[16];
+        expand_g(A, wr, y, z, v);
+        double u[NM_H] = {0, 0, 0, 0};
+        if (HAS_H) expand_h(B, wr, y, z, u);
+        v[13] = u[0]; v[14] = u[1]; v[15] = u[2];
+        const double tot = warp_reduce16(v, lane);
+        const double t3 = warp_sum(u[3]);
+        const double tin = warp_sum(inb);
+        const int idx = reduce16_index(lane);
+        if ((lane & 1) == 0 && idx < nm) cin[(size_t)b * nm + idx] += tot;
+        if (HAS_H && lane == 0) cin[(size_t)b * nm + 16] += t3;
+        if (lane == 0) win[b] += tin;
+        __syncwarp();
+    }
+}
