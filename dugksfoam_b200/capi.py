@@ -30,7 +30,7 @@ EXPORTS = ["dugks_abi_version", "dugks_nccl_unique_id", "dugks_create", "dugks_d
            "dugks_get_face_macros", "dugks_get_boundary_macros", "dugks_get_wall_diag", "dugks_courant",
            "dugks_get_df", "dugks_get_state", "dugks_set_state", "dugks_local_dvs", "dugks_sizes",
            "dugks_get_stats", "dugks_stream", "dugks_kernel_timing", "dugks_partition",
-           "dugks_get_boundary_df"]
+           "dugks_get_boundary_df", "dugks_row_layout"]
 
 
 class DugksError(RuntimeError):
@@ -87,6 +87,7 @@ def load_library():
     L.dugks_kernel_timing.argtypes = [C.c_void_p, C.c_int, C.c_int, c_double_p, C.POINTER(C.c_uint64)]
     L.dugks_partition.argtypes = [C.c_int32] * 4 + [c_int32_p, c_int32_p]
     L.dugks_get_boundary_df.argtypes = [C.c_void_p, c_double_p, c_double_p]
+    L.dugks_row_layout.argtypes = [C.c_int32] * 4 + [c_int32_p] * 8
     _LIB = L
     return L
 
@@ -101,6 +102,22 @@ def partition(nXiPerDim: int, nSolutionD: int, nRanks: int, rank: int) -> np.nda
     ids = np.empty(n.value, dtype=np.int32)
     L.dugks_partition(nXiPerDim, nSolutionD, nRanks, rank, iptr(ids), C.byref(n))
     return ids
+
+
+def row_layout(nXiPerDim: int, nSolutionD: int, nRanks: int, rank: int) -> dict:
+    """Velocity-row layout of one rank (host-only, needs no device): see dugks_row_layout."""
+    L = load_library()
+    nch, ll, lt, nrows = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32(0)
+    rc = L.dugks_row_layout(nXiPerDim, nSolutionD, nRanks, rank, C.byref(nch), C.byref(ll), C.byref(lt), C.byref(nrows),
+                            None, None, None, None)
+    if rc:
+        raise DugksError(f"dugks_row_layout failed ({rc}): {L.dugks_last_error(None).decode()}")
+    n = nrows.value
+    arr = [np.empty(n, dtype=np.int32) for _ in range(4)]
+    cap = C.c_int32(n)
+    L.dugks_row_layout(nXiPerDim, nSolutionD, nRanks, rank, C.byref(nch), C.byref(ll), C.byref(lt), C.byref(cap),
+                       *[iptr(a) for a in arr])
+    return dict(nch=nch.value, L=ll.value, Lt=lt.value, iy=arr[0], iz=arr[1], first=arr[2], len=arr[3])
 
 
 def nccl_unique_id() -> bytes:

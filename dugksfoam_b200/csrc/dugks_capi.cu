@@ -624,6 +624,91 @@ static int row_begin_of(int nbase, int nranks, int r) {
     return (int)(r * q + std::min<long long>(r, m));
 }
 
+// Velocity-row layout of one rank (host only): rows of L = ceil(n / nch) points over the rank's block of
+// (iy, iz) base rows, sorted so that warps are sign-coherent, plus the optional short-row tail slab.
+struct RowLayout {
+    int nch = 1, L = 0, Lt = 0, ntab = 0;
+    std::vector<RowDesc> rows;
+};
+
+static int build_row_layout(int n, int D, int nranks, int rank, const double* Xis, const double* weights, RowLayout& out) {
+    const int ny = (D >= 2) ? n : 1, nz = (D == 3) ? n : 1;
+    const int nbase = ny * nz, Rs = 32;
+    if (nbase < nranks) return -1;
+    const int rb0 = row_begin_of(nbase, nranks, rank), rb1 = row_begin_of(nbase, nranks, rank + 1);
+    int max_nbl = 0;
+    for (int r = 0; r < nranks; r++) max_nbl = std::max(max_nbl, row_begin_of(nbase, nranks, r + 1) - row_begin_of(nbase, nranks, r));
+    int nch = choose_chunks(n, D, max_nbl);
+    if (const char* e = getenv("DUGKS_NCH")) {   // experiment hook: force the number of ix-chunks per row
+        const int want = atoi(e);
+        if (want >= 1 && (n + want - 1) / want <= MAX_L && (long long)want * ((n + want - 1) / want) <= NT_MAX) nch = want;
+    }
+    if (nch < 1) return -1;
+    const int L = (n + nch - 1) / nch;
+    out.nch = nch; out.L = L; out.ntab = nch * L; out.Lt = 0;
+    std::vector<RowDesc>& rows = out.rows;
+    rows.clear();
+    for (int ch = 0; ch < nch; ch++)
+        for (int br = rb0; br < rb1; br++) {
+            int iy = (D >= 2) ? br % n : 0, iz = (D == 3) ? br / n : 0;
+            RowDesc rd;
+            rd.iy = iy; rd.iz = iz; rd.chunk = ch;
+            rd.y = (D >= 2) ? Xis[iy] : 0.0;
+            rd.z = (D == 3) ? Xis[iz] : 0.0;
+            // weight = w[iz]*w[iy]*w[ix] (fvDVM.C:158,187,211): the row carries w[iz]*w[iy]
+            rd.w = (D == 3) ? weights[iz] * weights[iy] : ((D == 2) ? weights[iy] : 1.0);
+            rows.push_back(rd);
+        }
+    // keep warps sign-coherent in (xi_y, xi_z): less divergence in the upwind test
+    std::stable_sort(rows.begin(), rows.end(), [](const RowDesc& a, const RowDesc& b) {
+        if (a.chunk != b.chunk) return a.chunk < b.chunk;
+        int sa = (a.z < 0 ? 0 : 2) + (a.y < 0 ? 0 : 1), sb = (b.z < 0 ? 0 : 2) + (b.y < 0 ? 0 : 1);
+        return sa < sb;
+    });
+    for (auto& rd : rows) { rd.cbase = rd.chunk * L; rd.len = L; }
+    // short-row tail slab (dv_len, dugks_device.cuh): the rows that would leave the last slab mostly
+    // empty are cut into ix-chunks of Lt points and fill the lanes of one short slab
+    const int r_last = (int)rows.size() % Rs;
+    const bool allow = nch == 1 && getenv("DUGKS_NO_TAIL") == nullptr && getenv("DUGKS_NO_HOT") == nullptr;
+    if (allow && r_last > 0 && Rs / r_last >= 2 && n >= 2) {
+        int ncht = std::min(Rs / r_last, n);
+        const int Lt = (n + ncht - 1) / ncht;
+        ncht = (n + Lt - 1) / Lt;
+        if (r_last * ncht <= Rs && Lt < L && ncht * Lt <= NT_MAX) {
+            std::vector<RowDesc> tail(rows.end() - r_last, rows.end());
+            rows.resize(rows.size() - r_last);
+            for (int ct = 0; ct < ncht; ct++)
+                for (RowDesc rd : tail) { rd.chunk = ct; rd.cbase = ct * Lt; rd.len = Lt; rows.push_back(rd); }
+            out.Lt = Lt;
+            out.ntab = std::max(out.ntab, ncht * Lt);
+        }
+    }
+    return 0;
+}
+
+extern "C" int dugks_row_layout(int32_t nXiPerDim, int32_t nSolutionD, int32_t nRanks, int32_t rank, int32_t* nch,
+                                int32_t* L, int32_t* Lt, int32_t* nRows, int32_t* row_iy, int32_t* row_iz,
+                                int32_t* row_first, int32_t* row_len) {
+    if (nXiPerDim < 1 || nSolutionD < 1 || nSolutionD > 3 || nRanks < 1 || rank < 0 || rank >= nRanks || !nRows)
+        return fail(nullptr, DUGKS_ERR_INVALID, "dugks_row_layout: bad argument");
+    std::vector<double> x(nXiPerDim), w(nXiPerDim, 1.0);
+    for (int i = 0; i < nXiPerDim; i++) x[i] = i - 0.5 * (nXiPerDim - 1);   // symmetric placeholder abscissae
+    RowLayout lay;
+    if (build_row_layout(nXiPerDim, nSolutionD, nRanks, rank, x.data(), w.data(), lay) != 0)
+        return fail(nullptr, DUGKS_ERR_UNSUPPORTED, "nDV = %d cannot be laid out over %d ranks", nXiPerDim, nRanks);
+    if (nch) *nch = lay.nch;
+    if (L) *L = lay.L;
+    if (Lt) *Lt = lay.Lt;
+    const int cap = *nRows;
+    *nRows = (int)lay.rows.size();
+    if (row_iy && row_iz && row_first && row_len)
+        for (int k = 0; k < (int)lay.rows.size() && k < cap; k++) {
+            row_iy[k] = lay.rows[k].iy; row_iz[k] = lay.rows[k].iz;
+            row_first[k] = lay.rows[k].cbase; row_len[k] = lay.rows[k].len;
+        }
+    return 0;
+}
+
 extern "C" int dugks_abi_version(void) { return DUGKS_ABI_VERSION; }
 
 extern "C" int dugks_partition(int32_t nXiPerDim, int32_t nSolutionD, int32_t nRanks, int32_t rank, int32_t* ids,
@@ -778,56 +863,15 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
     for (int r = 0; r < nranks; r++)
         for (int br = row_begin(r); br < row_begin(r + 1); br++)
             for (int ix = 0; ix < n; ix++) h->owner_rank_of_gid[br * n + ix] = r;
-    int nch = choose_chunks(n, D, max_nbl);
-    if (const char* e = getenv("DUGKS_NCH")) {   // experiment hook: force the number of ix-chunks per row
-        const int want = atoi(e);
-        if (want >= 1 && (n + want - 1) / want <= MAX_L && (long long)want * ((n + want - 1) / want) <= NT_MAX) nch = want;
+    RowLayout lay;
+    if (build_row_layout(n, D, nranks, h->rank, dvset->Xis, dvset->weights, lay) != 0) {
+        fail(h, DUGKS_ERR_UNSUPPORTED, "nDV = %d cannot be laid out (needs ix-chunks of <= %d points, <= %d table entries)", n, MAX_L, NT_MAX);
+        return bail(DUGKS_ERR_UNSUPPORTED);
     }
-    if (nch < 1) { fail(h, DUGKS_ERR_UNSUPPORTED, "nDV = %d cannot be laid out (needs ix-chunks of <= %d points, <= %d table entries)", n, MAX_L, NT_MAX); return bail(DUGKS_ERR_UNSUPPORTED); }
-    const int L = (n + nch - 1) / nch;
-    h->nch = nch; h->L = L; h->ntab = nch * L;
+    const int nch = lay.nch, L = lay.L;
+    h->nch = nch; h->L = L; h->ntab = lay.ntab; h->Lt = lay.Lt;
     h->Rs = 32;
-    // par->dv_chunk is reserved: a slab is one warp of rows (32 rows x L points) because every
-    // moment slot is owned by exactly one warp per launch (atomic-free, deterministic)
-    std::vector<RowDesc> rows;
-    for (int ch = 0; ch < nch; ch++)
-        for (int br = rb0; br < rb1; br++) {
-            int iy = (D >= 2) ? br % n : 0, iz = (D == 3) ? br / n : 0;
-            RowDesc rd;
-            rd.iy = iy; rd.iz = iz; rd.chunk = ch;
-            rd.y = (D >= 2) ? dvset->Xis[iy] : 0.0;
-            rd.z = (D == 3) ? dvset->Xis[iz] : 0.0;
-            // weight = w[iz]*w[iy]*w[ix] (fvDVM.C:158,187,211): the row carries w[iz]*w[iy]
-            rd.w = (D == 3) ? dvset->weights[iz] * dvset->weights[iy] : ((D == 2) ? dvset->weights[iy] : 1.0);
-            rows.push_back(rd);
-        }
-    // keep warps sign-coherent in (xi_y, xi_z): less divergence in the upwind test
-    std::stable_sort(rows.begin(), rows.end(), [](const RowDesc& a, const RowDesc& b) {
-        if (a.chunk != b.chunk) return a.chunk < b.chunk;
-        int sa = (a.z < 0 ? 0 : 2) + (a.y < 0 ? 0 : 1), sb = (b.z < 0 ? 0 : 2) + (b.y < 0 ? 0 : 1);
-        return sa < sb;
-    });
-    for (auto& rd : rows) { rd.cbase = rd.chunk * L; rd.len = L; }
-    // short-row tail slab (dv_len, dugks_device.cuh): the rows that would leave the last slab mostly
-    // empty are cut into ix-chunks of Lt points and fill the lanes of one short slab
-    h->Lt = 0;
-    {
-        const int r_last = (int)rows.size() % h->Rs;
-        const bool allow = nch == 1 && getenv("DUGKS_NO_TAIL") == nullptr && getenv("DUGKS_NO_HOT") == nullptr;
-        if (allow && r_last > 0 && h->Rs / r_last >= 2 && n >= 2) {
-            int ncht = std::min(h->Rs / r_last, n);
-            const int Lt = (n + ncht - 1) / ncht;
-            ncht = (n + Lt - 1) / Lt;
-            if (r_last * ncht <= h->Rs && Lt < L && ncht * Lt <= NT_MAX) {
-                std::vector<RowDesc> tail(rows.end() - r_last, rows.end());
-                rows.resize(rows.size() - r_last);
-                for (int ct = 0; ct < ncht; ct++)
-                    for (RowDesc rd : tail) { rd.chunk = ct; rd.cbase = ct * Lt; rd.len = Lt; rows.push_back(rd); }
-                h->Lt = Lt;
-                h->ntab = std::max(h->ntab, ncht * Lt);
-            }
-        }
-    }
+    std::vector<RowDesc>& rows = lay.rows;
     const int nreal = (int)rows.size();
     h->nrows = (nreal + h->Rs - 1) / h->Rs * h->Rs;
     h->nslab = h->nrows / h->Rs;

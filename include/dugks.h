@@ -263,6 +263,15 @@ int dugks_set_state(dugks_handle_t* h, const double* g, const double* h_);
 int dugks_partition(int32_t nXiPerDim, int32_t nSolutionD, int32_t nRanks, int32_t rank,
                     int32_t* ids, int32_t* n);
 
+/* Host-only (no device needed): the velocity-row layout rank `rank` of `nRanks` uses for an
+ * nXiPerDim^D velocity grid: rows of *L consecutive ix points, 32 rows per slab;
+ * when *Lt > 0 the last slab holds short rows of *Lt points.  On entry *nRows is the capacity of the
+ * four arrays (any of which may be NULL), on return the number of rows; row k covers
+ * ix in [row_first[k], row_first[k] + row_len[k]) at (row_iy[k], row_iz[k]). */
+int dugks_row_layout(int32_t nXiPerDim, int32_t nSolutionD, int32_t nRanks, int32_t rank,
+                     int32_t* nch, int32_t* L, int32_t* Lt, int32_t* nRows,
+                     int32_t* row_iy, int32_t* row_iz, int32_t* row_first, int32_t* row_len);
+
 /* Boundary-face values gSurf/hSurf of the local DVs on all boundary faces,
  * g[j*nBoundaryFaces + b] for local DV j (DVi(j).gSurf().boundaryField(),
  * discreteVelocity.H:230-239).  Either pointer may be NULL. */

@@ -52,3 +52,44 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(abi.DvsetT) == 40
     assert ctypes.sizeof(abi.MeshT) == 16 + 10 * 8
     assert ctypes.sizeof(abi.StatsT) == 40
+
+
+def test_row_layout_covers_every_velocity_once():
+    """Host logic of the velocity-row layout (rows, slabs, short-row tail slab): over all ranks every
+    discrete velocity is in exactly one row, rows fit the slab rules, short rows only in the last slab."""
+    from dugksfoam_b200 import capi
+    import numpy as np
+    for D in (1, 2, 3):
+        for n in (2, 3, 8, 9, 16, 28, 32, 33, 101):
+            if D == 3 and n > 33:
+                continue
+            ny, nz = (n if D >= 2 else 1), (n if D == 3 else 1)
+            for nranks in (1, 2, 3, 4, 8):
+                if ny * nz < nranks:
+                    continue
+                seen = np.zeros((nz, ny, n), dtype=np.int32)
+                if n > 32 and (ny * nz) // nranks < 32:
+                    # rows longer than 32 points are cut into ix-chunks, which needs >= 32 rows per rank
+                    # (a warp's equilibrium tables span at most two chunks): refused, loudly
+                    with pytest.raises(capi.DugksError):
+                        capi.row_layout(n, D, nranks, 0)
+                    continue
+                for rank in range(nranks):
+                    lay = capi.row_layout(n, D, nranks, rank)
+                    L, Lt = lay["L"], lay["Lt"]
+                    assert 1 <= L <= 32 and 0 <= Lt < max(L, 1) + (Lt == 0)
+                    nrows = len(lay["iy"])
+                    nslab = (nrows + 31) // 32
+                    for k in range(nrows):
+                        ln, first = int(lay["len"][k]), int(lay["first"][k])
+                        in_last = k // 32 == nslab - 1
+                        assert ln == (Lt if (Lt > 0 and in_last) else L), (D, n, nranks, rank, k)
+                        hi = min(first + ln, n)
+                        seen[lay["iz"][k], lay["iy"][k], first:hi] += 1
+                    # the DVs of this rank are exactly its partition
+                    ids = capi.partition(n, D, nranks, rank)
+                    assert ids.size == sum(min(int(f) + int(l), n) - int(f) for f, l in zip(lay["first"], lay["len"]))
+                assert (seen == 1).all(), (D, n, nranks)
+    # the case that motivated the tail slab: 28^3 over 8 ranks = 98 rows = 3 slabs + 2 rows -> short rows of 2
+    lay = capi.row_layout(28, 3, 8, 0)
+    assert lay["L"] == 28 and lay["Lt"] == 2 and len(lay["iy"]) == 96 + 28
