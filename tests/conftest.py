@@ -19,3 +19,12 @@ def oracle_lib():
     from oracle import oracle as _o
     _o.build()
     return _o
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _product_library():
+    """The C-ABI library is built in tree (nvcc cross-compiles without a GPU); tests never fall back to
+    anything else when it is missing."""
+    from dugksfoam_b200 import capi
+    capi.build_library()
+    yield
