@@ -337,6 +337,9 @@ static int hot_configure(dugks_handle* h) {
     h->hot_grid_out1 = std::max(1, std::min(dev_sms * std::max(occ[0], 1), max_ctas));
     h->hot_grid_out2 = std::max(1, std::min(dev_sms * std::max(occ[1], 1), max_ctas));
     h->hot_grid_upd = std::max(1, std::min(dev_sms * std::max(occ[2], 1), max_ctas));
+    if (const char* e = getenv("DUGKS_RLX_CTAS")) occ[3] = std::max(1, std::min(occ[3], atoi(e)));   // experiment hook
+    if (const char* e = getenv("DUGKS_UPD_CTAS")) occ[2] = std::max(1, std::min(occ[2], atoi(e)));
+    h->hot_grid_upd = std::max(1, std::min(dev_sms * std::max(occ[2], 1), max_ctas));
     h->hot_grid_rlx = std::max(1, std::min(dev_sms * std::max(occ[3], 1), max_ctas));
     h->hot_grid_half = std::max(1, std::min(dev_sms * std::max(occ_half, 1), max_ctas));
     h->hot_grid_axis = std::max(1, std::min(dev_sms * std::max(occ_axis, 1), max_ctas));
