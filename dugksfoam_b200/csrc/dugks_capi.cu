@@ -121,8 +121,10 @@ struct dugks_handle {
     int hot_ne = 6, hot_grid_out1 = 148, hot_grid_out2 = 148, hot_grid_upd = 148, hot_grid_rlx = 148;
     size_t hsmem_rlx = 0, hsmem_half = 0;
     int hot_grid_half = 148, hot_grid_axis = 148;
-    bool split_axis = false;
-    int n_axis = 0;
+    bool split_axis = false, want_split = false;
+    size_t hsmem_axis = 0;
+    std::vector<char> slab_pair_ok;   // per slab: the axis-only launch of phase 1 is valid (hot_axis_item)
+    int n_axis = 0, axis_ne = 0;
     // face-storage slabs: phase 1 keeps the reconstructed face values of slabs [0, n_keep) so that
     // phase 2 is ONE fused relax+update pass for them (no second gradient, no flux-buffer round trip)
     int n_keep = 0;
@@ -227,6 +229,11 @@ static int do_allreduce(dugks_handle* h, double* buf, size_t n) {
 #define DUGKS_CI_OUT1 4
 #endif
 constexpr int CI_OUT1 = DUGKS_CI_OUT1, CI_OUT2 = 2, CI_RLX = 2;
+// axis-only launch of phase 1 (hot_axis_item): 2 points per chunk keep it at 160 registers = 3 CTAs/SM without spills
+#ifndef DUGKS_CI_AXIS
+#define DUGKS_CI_AXIS 2
+#endif
+constexpr int CI_AXIS = DUGKS_CI_AXIS;
 // update kernel of the flux-buffer path: 4 points per chunk, 2 when h doubles the streams (shared memory per CTA)
 #define CI_UPD (H ? 2 : 4)
 template <int PHASE, bool H>
@@ -234,17 +241,18 @@ static void launch_hot_outgoing(dugks_handle* h, const StepArgs& a) {
     const size_t sm = PHASE == 1 ? h->hsmem_out1 : h->hsmem_out2;
     const int tw = PHASE == 1 ? 32 : h->tma_tw;
     const int grid = PHASE == 1 ? h->hot_grid_out1 : h->hot_grid_out2;
-    if (PHASE == 1 && h->split_axis) {
-        // mostly axis-aligned mesh: the light variant alone runs 3 CTAs/SM, a second launch takes the rest
+    if (PHASE == 1 && h->split_axis && a.slab < (int)h->slab_pair_ok.size() && h->slab_pair_ok[a.slab]) {
+        // mostly axis-aligned mesh: the light variant (hot_axis_item) alone runs 3 CTAs/SM, a second launch
+        // takes the rest.  Slabs with a tie on a y/z face or rows that are not whole chunks take the unified launch.
         StepArgs a1 = a, a2 = a;
         a1.item0 = 0; a1.item1 = h->n_axis;
         a2.item0 = h->n_axis; a2.item1 = h->nc;
         const int grid2 = std::max(1, std::min(grid, (h->nc - h->n_axis + HOT_WARPS - 1) / HOT_WARPS));
         if (h->hot_ne == 4) {
-            k_hot_outgoing<1, H, 4, 32, CI_OUT1, 1><<<h->hot_grid_axis, HOT_WARPS * 32, sm, h->stream>>>(a1);
+            k_hot_outgoing<1, H, 4, 32, CI_AXIS, 1><<<h->hot_grid_axis, HOT_WARPS * 32, h->hsmem_axis, h->stream>>>(a1);
             if (h->n_axis < h->nc) k_hot_outgoing<1, H, 4, 32, CI_OUT1, 2><<<grid2, HOT_WARPS * 32, sm, h->stream>>>(a2);
         } else {
-            k_hot_outgoing<1, H, 6, 32, CI_OUT1, 1><<<h->hot_grid_axis, HOT_WARPS * 32, sm, h->stream>>>(a1);
+            k_hot_outgoing<1, H, 6, 32, CI_AXIS, 1><<<h->hot_grid_axis, HOT_WARPS * 32, h->hsmem_axis, h->stream>>>(a1);
             if (h->n_axis < h->nc) k_hot_outgoing<1, H, 6, 32, CI_OUT1, 2><<<grid2, HOT_WARPS * 32, sm, h->stream>>>(a2);
         }
         h->launches++;
@@ -310,16 +318,18 @@ static int hot_configure(dugks_handle* h) {
     if (e != cudaSuccess) return fail(h, DUGKS_ERR_CUDA, "cudaFuncSetAttribute (hot kernels): %s", cudaGetErrorString(e));
     int occ_axis = 1;
     h->split_axis = false;
-    if (e == cudaSuccess && (h->hot_ne == 4 || h->hot_ne == 6) && 2 * (long long)h->n_axis > h->nc &&
-        getenv("DUGKS_SPLIT_AXIS") != nullptr) {   // opt-in experiment: measured slower (27.7 vs 21.9 ms per step at 32^3)
+    if (e == cudaSuccess && (h->hot_ne == 4 || h->hot_ne == 6) && h->want_split && h->axis_ne == h->hot_ne) {
+        // axis-aligned cells in their own launch (hot_axis_item, 3 CTAs/SM): 64^3 x 28^3, phase 1 per step 73 -> see DESIGN.md
         if (h->hot_ne == 4) {
-            e = cudaFuncSetAttribute(k_hot_outgoing<1, H, 4, 32, CI_OUT1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->hsmem_out1);
+            h->hsmem_axis = HotPlan<1, H, 4, 32, CI_AXIS>::total(ntab);
+            e = cudaFuncSetAttribute(k_hot_outgoing<1, H, 4, 32, CI_AXIS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->hsmem_axis);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_hot_outgoing<1, H, 4, 32, CI_OUT1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->hsmem_out1);
-            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_axis, k_hot_outgoing<1, H, 4, 32, CI_OUT1, 1>, HOT_WARPS * 32, h->hsmem_out1);
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_axis, k_hot_outgoing<1, H, 4, 32, CI_AXIS, 1>, HOT_WARPS * 32, h->hsmem_axis);
         } else {
-            e = cudaFuncSetAttribute(k_hot_outgoing<1, H, 6, 32, CI_OUT1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->hsmem_out1);
+            h->hsmem_axis = HotPlan<1, H, 6, 32, CI_AXIS>::total(ntab);
+            e = cudaFuncSetAttribute(k_hot_outgoing<1, H, 6, 32, CI_AXIS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->hsmem_axis);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_hot_outgoing<1, H, 6, 32, CI_OUT1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->hsmem_out1);
-            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_axis, k_hot_outgoing<1, H, 6, 32, CI_OUT1, 1>, HOT_WARPS * 32, h->hsmem_out1);
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_axis, k_hot_outgoing<1, H, 6, 32, CI_AXIS, 1>, HOT_WARPS * 32, h->hsmem_axis);
         }
         if (e != cudaSuccess) return fail(h, DUGKS_ERR_CUDA, "axis-split kernel configuration: %s", cudaGetErrorString(e));
         h->split_axis = occ_axis >= 3;
@@ -1026,6 +1036,7 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
                 e_other[e] = tmp_i[j * 3]; e_face[e] = tmp_i[j * 3 + 1]; e_owner[e] = tmp_i[j * 3 + 2];
             }
             cell_cls[c] = 1;
+            h->axis_ne = (h->n_axis == 0 || h->axis_ne == n_e) ? n_e : -1;   // -1: mixed face counts
             h->n_axis++;
         }
     }
@@ -1098,7 +1109,8 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
             std::stable_sort(order.begin(), order.end(), [&](int x, int y2) { return key[x] < key[y2]; });
         }
         // split launches (DUGKS_SPLIT_AXIS): axis-aligned cells first, the others after them
-        if (getenv("DUGKS_SPLIT_AXIS") != nullptr)
+        h->want_split = 2 * (long long)h->n_axis > nc && getenv("DUGKS_NO_SPLIT_AXIS") == nullptr;
+        if (h->want_split)
             std::stable_partition(order.begin(), order.end(), [&](int c) { return cell_cls[c] != 0; });
         // per-cell record (CMETA_N ints) in traversal order: everything a warp needs to start a cell in one load level
         std::vector<int> cmeta((size_t)nc * CMETA_N, 0);
@@ -1320,14 +1332,18 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
         uint4* d_upw = nullptr;
         int* d_bad = nullptr;
         TRYB(dev_alloc(h, &d_upw, (size_t)h->nslab * nc * 32, false));
-        TRYB(dev_alloc(h, &d_bad, 1));
+        TRYB(dev_alloc(h, &d_bad, 1 + (size_t)h->nslab));   // [0]: not range shaped; [1 + slab]: tie on a y/z face of an axis-aligned cell
         long long total = (long long)h->nslab * nc * 32;
         int grid = (int)std::min<long long>((total + 255) / 256, 148LL * 64);
         k_build_upwind<<<grid, 256, 0, h->stream>>>(A, d_upw, d_bad);
         TRYB(check_launch(h, "k_build_upwind"));
-        int bad = 0;
-        CUDAB(cudaMemcpyAsync(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost, h->stream));
+        std::vector<int> flags(1 + (size_t)h->nslab, 0);
+        CUDAB(cudaMemcpyAsync(flags.data(), d_bad, flags.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CUDAB(cudaStreamSynchronize(h->stream));
+        const int bad = flags[0];
+        h->slab_pair_ok.assign(h->nslab, 0);
+        for (int s = 0; s < h->nslab; s++)
+            h->slab_pair_ok[s] = flags[1 + s] == 0 && dv_len(A.dv, s) % CI_AXIS == 0;
         // abscissae that are not ascending give upwind sets that are not ranges: first-generation kernels
         if (bad) h->use_hot = false;
         A.upw = d_upw;

@@ -62,7 +62,9 @@ __host__ __device__ __forceinline__ bool hot_encode(unsigned full, unsigned tie,
 
 // One thread per (slab, cell, lane): evaluates xi.Sf with the reference's operation order for every
 // face entry and every ix, classifies (discreteVelocity.C:495,506 internal; :562,580,614,675 boundary)
-// and stores the range codes.  *bad is raised if a set is not range shaped (unsorted abscissae).
+// and stores the range codes.  bad[0] is raised if a set is not range shaped (unsorted abscissae),
+// bad[1 + slab] if a row of the slab has a tie on a y/z face of an axis-aligned cell (hot_axis_item
+// cannot take that slab).
 __global__ void k_build_upwind(StepArgs a, uint4* out, int* bad) {
     const DevDV& dv = a.dv;
     const long long total = (long long)dv.nslab * a.m.nc * 32;
@@ -77,6 +79,7 @@ __global__ void k_build_upwind(StepArgs a, uint4* out, int* bad) {
         const int cb = dv.row_cbase[grow];
         const int e0 = a.m.cell_off[c], ne = a.m.cell_off[c + 1] - e0;
         unsigned short codes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const bool axis_cell = ((a.cmeta[(size_t)item * 24 + 1] >> 16) & 0xff) != 0;
         for (int j = 0; j < ne && j < 8; j++) {
             const double* g = a.m.e_geo + (size_t)(e0 + j) * 9;
             const int o = a.m.e_other[e0 + j];
@@ -100,6 +103,7 @@ __global__ void k_build_upwind(StepArgs a, uint4* out, int* bad) {
             }
             unsigned code = 0;
             if (!hot_encode(full, tie, dv_len(dv, slab), code)) atomicOr(bad, 1);
+            if (axis_cell && j >= 2 && tie != 0) atomicOr(bad + 1 + slab, 1);
             codes[j] = (unsigned short)code;
         }
         uint4 w;
@@ -599,6 +603,204 @@ __device__ __forceinline__ void hot_out_item(const StepArgs& a, const HotCtx& x,
     }
 }
 
+// One axis-aligned interior cell of PHASE 1 in the axis-only launch (SEL = 1).  Same arithmetic, in the
+// same order, as hot_out_item<1, ..., AXIS = true> (bit-identical face values and moment sums), built
+// around what the static upwind sets of such a cell look like:
+//   * x faces (entries 0, 1): xi.Sf = xi_x * Sx, the same for every lane -> warp-uniform per point;
+//   * y / z faces (entries 2.., in pairs): xi.Sf = xi_y * Sy (xi_z * Sz) does not depend on the point, so a
+//     lane is upwind of exactly ONE face of a pair for the whole row.  The lane reconstructs only that
+//     face (one face offset, one store address and ONE set of moment accumulators per pair, selected once
+//     per cell) and the two faces' moments are separated at the end by masking lanes.
+// Needs: no tie (|xi.Sf| < VSMALL) on a y / z face of an axis-aligned cell for any row of the slab
+// (k_build_upwind reports that per slab; such slabs take the unified launch) and rows that are whole chunks.
+template <bool HAS_H, int NE, int CI, class Prefetch>
+__device__ __forceinline__ void hot_axis_item(const StepArgs& a, const HotCtx& x, const HotMeta& cur, double* stages,
+                                              int stage_d, uint32_t& q, Prefetch&& prefetch) {
+    static_assert(NE == 4 || NE == 6, "axis-aligned cells have 4 or 6 faces");
+    constexpr int NSLOT = 1 + NE, NFLD = HAS_H ? 2 : 1, NP = NE / 2 - 1;   // NP: y (and z) pairs
+    const int lane = x.lane, L = x.L, blk = x.blk;
+    const double* gb_ = x.geo;
+    const double* txs = x.txs;
+    const unsigned ownmask = __ballot_sync(0xffffffffu, cur.own != 0);
+    const unsigned w4[4] = {cur.mw.x, cur.mw.y, cur.mw.z, cur.mw.w};
+    // ---- x faces: masks per point and their warp-uniform per-chunk summaries
+    unsigned fullx[2], tiex[2], anyx[2], allx[2];
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        hot_decode((w4[0] >> (j * 16)) & 0xffffu, L, fullx[j], tiex[j]);
+        anyx[j] = __reduce_or_sync(0xffffffffu, hot_spread_any<CI>(fullx[j] | tiex[j]));
+        allx[j] = __reduce_and_sync(0xffffffffu, hot_spread_all<CI>(fullx[j]));
+    }
+    // ---- face storage: element offsets of this lane's rows (the pair's face is chosen per lane)
+    double* const fk_g = a.fkeep_g ? a.fkeep_g + (size_t)a.slab * a.m.nif * blk : nullptr;
+    double* const fk_h = (HAS_H && a.fkeep_h) ? a.fkeep_h + (size_t)a.slab * a.m.nif * blk : nullptr;
+    const bool keep_on = fk_g != nullptr;
+    const ptrdiff_t fk_gh = HAS_H ? fk_h - fk_g : 0;   // the h copy of a face row sits this far behind the g copy
+    // running store pointers (advanced by one chunk per iteration): one 64-bit add per face and chunk
+    double* kx[2];
+    double* kp[NP];
+#pragma unroll
+    for (int j = 0; j < 2; j++) kx[j] = fk_g + ((size_t)__shfl_sync(0xffffffffu, cur.face, j) * blk + lane);
+    bool sel[NP], act[NP];
+    double rsel[NP];
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+        unsigned fa, ta, fb, tb2;
+        hot_decode((w4[1 + p] & 0xffffu), L, fa, ta);
+        hot_decode((w4[1 + p] >> 16) & 0xffffu, L, fb, tb2);
+        sel[p] = fa != 0;
+        act[p] = (fa | fb) != 0;
+        const int d = 1 + p;
+        const double ra = gb_[6 * (3 + 2 * p) + 3 + d], rb = gb_[6 * (4 + 2 * p) + 3 + d];
+        rsel[p] = sel[p] ? ra : rb;
+        const int fa_id = __shfl_sync(0xffffffffu, cur.face, 2 + 2 * p), fb_id = __shfl_sync(0xffffffffu, cur.face, 3 + 2 * p);
+        kp[p] = fk_g + ((size_t)(sel[p] ? fa_id : fb_id) * blk + lane);
+    }
+    // ---- moment accumulators: two x faces, one per pair
+    double ax[2][4], bx[2][2], ap[NP][4], bp[NP][2];
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        ax[j][0] = ax[j][1] = ax[j][2] = ax[j][3] = 0.0;
+        bx[j][0] = bx[j][1] = 0.0;
+    }
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+        ap[p][0] = ap[p][1] = ap[p][2] = ap[p][3] = 0.0;
+        bp[p][0] = bp[p][1] = 0.0;
+    }
+
+    for (int ch = 0; ch < x.nchunk; ch++) {
+        prefetch(ch);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncwarp();
+        const double* sg = stages + (q & 1) * stage_d;
+        const int i0 = ch * CI;
+        const int tb = x.cb + i0;
+#pragma unroll
+        for (int fld = 0; fld < NFLD; fld++) {
+            const double* sf = sg + fld * NSLOT * CI * 32 + lane;
+            // ---- gradient (stock leastSquaresGrad, zeroBoundaryGrad.C:90-99): one component per face
+            double v[CI], g[3][CI], base[CI];
+            {
+                const double2 G01 = lds2(gb_);
+                const double G2 = gb_[2];
+#pragma unroll
+                for (int u = 0; u < CI; u++) {
+                    v[u] = sf[u * 32];
+                    g[0][u] = G01.x * v[u]; g[1][u] = G01.y * v[u]; g[2][u] = G2 * v[u];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < NE; j++) {
+                const int d = j >> 1;
+                const double G = gb_[6 * (1 + j) + d];
+#pragma unroll
+                for (int u = 0; u < CI; u++) g[d][u] = fma(G, sf[((1 + j) * CI + u) * 32], g[d][u]);
+            }
+            // ---- value at the cell centre moved back by half a step (discreteVelocity.C:498-502)
+            double W[CI][4];
+#pragma unroll
+            for (int u = 0; u < CI; u++) {
+                const double2 t0 = lds2(txs + (tb + u) * 6), t1 = lds2(txs + (tb + u) * 6 + 2);
+                base[u] = NE == 4 ? fma(t0.x, g[0][u], fma(x.yh, g[1][u], v[u]))
+                                  : fma(t0.x, g[0][u], fma(x.yh, g[1][u], fma(x.zh, g[2][u], v[u])));
+                W[u][0] = t0.y; W[u][1] = t1.x; W[u][2] = t1.y; W[u][3] = txs[(tb + u) * 6 + 4];
+            }
+            // ---- x faces
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                if (!((anyx[j] >> i0) & 1u)) continue;                      // warp-uniform
+                const double r = gb_[6 * (1 + j) + 3];
+                double* const keep = fld == 0 ? kx[j] : kx[j] + fk_gh;
+                if ((allx[j] >> i0) & 1u) {                                  // warp-uniform
+#pragma unroll
+                    for (int u = 0; u < CI; u++) {
+                        const double val = fma(r, g[0][u], base[u]);
+                        if (keep_on) __stcs(keep + u * 32, val);
+                        if (fld == 0) {
+                            ax[j][0] = fma(W[u][0], val, ax[j][0]); ax[j][1] = fma(W[u][1], val, ax[j][1]);
+                            ax[j][2] = fma(W[u][2], val, ax[j][2]); ax[j][3] = fma(W[u][3], val, ax[j][3]);
+                        } else {
+                            bx[j][0] = fma(W[u][0], val, bx[j][0]); bx[j][1] = fma(W[u][1], val, bx[j][1]);
+                        }
+                    }
+                } else {
+                    // the chunk that holds the sign change of xi_x: this side's share is all, half (tie,
+                    // :513-529) or none; the owner keeps the value unless phi < -VSMALL
+                    const unsigned fb = fullx[j] >> i0, tbits = tiex[j] >> i0;
+                    const unsigned wbk = ((ownmask >> j) & 1u) ? (fb | tbits) : fb;
+#pragma unroll
+                    for (int u = 0; u < CI; u++) {
+                        double val = fma(r, g[0][u], base[u]);
+                        if (keep_on && ((wbk >> u) & 1u)) __stcs(keep + u * 32, val);
+                        const int hi = ((fb >> u) & 1u) ? 0x3ff00000 : (((tbits >> u) & 1u) ? 0x3fe00000 : 0);
+                        val *= __hiloint2double(hi, 0);
+                        if (fld == 0) {
+                            ax[j][0] = fma(W[u][0], val, ax[j][0]); ax[j][1] = fma(W[u][1], val, ax[j][1]);
+                            ax[j][2] = fma(W[u][2], val, ax[j][2]); ax[j][3] = fma(W[u][3], val, ax[j][3]);
+                        } else {
+                            bx[j][0] = fma(W[u][0], val, bx[j][0]); bx[j][1] = fma(W[u][1], val, bx[j][1]);
+                        }
+                    }
+                }
+            }
+            // ---- y / z pairs: the one face of the pair this lane is upwind of
+#pragma unroll
+            for (int p = 0; p < NP; p++) {
+                double* const keep = fld == 0 ? kp[p] : kp[p] + fk_gh;
+                const bool st = keep_on && act[p];
+#pragma unroll
+                for (int u = 0; u < CI; u++) {
+                    const double val = fma(rsel[p], g[1 + p][u], base[u]);
+                    if (st) __stcs(keep + u * 32, val);
+                    if (fld == 0) {
+                        ap[p][0] = fma(W[u][0], val, ap[p][0]); ap[p][1] = fma(W[u][1], val, ap[p][1]);
+                        ap[p][2] = fma(W[u][2], val, ap[p][2]); ap[p][3] = fma(W[u][3], val, ap[p][3]);
+                    } else {
+                        bp[p][0] = fma(W[u][0], val, bp[p][0]); bp[p][1] = fma(W[u][1], val, bp[p][1]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; j++) kx[j] += CI * 32;
+#pragma unroll
+        for (int p = 0; p < NP; p++) kp[p] += CI * 32;
+        __syncwarp();   // every lane is done with this stage before it is refilled
+        q++;
+    }
+
+    // ---- face moments: one reduction per face; a pair's accumulators go to the face the lane chose
+    double* const red = stage_d >= 32 * 17 ? stages + ((q & 1) ^ 1) * stage_d : x.red;
+#pragma unroll 1
+    for (int j = 0; j < NE; j++) {
+        double m[4], mh[2];
+        bool lane_on;
+        if (j == 0) { lane_on = true; m[0] = ax[0][0]; m[1] = ax[0][1]; m[2] = ax[0][2]; m[3] = ax[0][3]; mh[0] = bx[0][0]; mh[1] = bx[0][1]; }
+        else if (j == 1) { lane_on = true; m[0] = ax[1][0]; m[1] = ax[1][1]; m[2] = ax[1][2]; m[3] = ax[1][3]; mh[0] = bx[1][0]; mh[1] = bx[1][1]; }
+        else if (j < 4) { lane_on = act[0] && (sel[0] == (j == 2)); m[0] = ap[0][0]; m[1] = ap[0][1]; m[2] = ap[0][2]; m[3] = ap[0][3]; mh[0] = bp[0][0]; mh[1] = bp[0][1]; }
+        else { lane_on = act[NP - 1] && (sel[NP - 1] == (j == 4)); m[0] = ap[NP - 1][0]; m[1] = ap[NP - 1][1]; m[2] = ap[NP - 1][2]; m[3] = ap[NP - 1][3]; mh[0] = bp[NP - 1][0]; mh[1] = bp[NP - 1][1]; }
+        const unsigned on = j == 0 ? anyx[0] : (j == 1 ? anyx[1] : __ballot_sync(0xffffffffu, lane_on));
+        if (on == 0) continue;                                            // warp-uniform: nowhere upwind
+        if (!lane_on) { m[0] = m[1] = m[2] = m[3] = 0.0; mh[0] = mh[1] = 0.0; }
+        double vv[16];
+        expand_g(m, x.wr, x.y, x.z, vv);
+        double uu[NM_H] = {0, 0, 0, 0};
+        if (HAS_H) expand_h(mh, x.wr, x.y, x.z, uu);
+        vv[13] = uu[0]; vv[14] = uu[1]; vv[15] = uu[2];
+        const double tot = warp_reduce16_smem(vv, red, lane);
+        const int fj = __shfl_sync(0xffffffffu, cur.face, j);
+        const size_t slot = (size_t)2 * fj + (((ownmask >> j) & 1u) ? 0 : 1);
+        // one warp owns a slot per launch: the fire-and-forget add keeps the sum deterministic
+        if (lane < 16 && lane < x.nm) atomicAdd(a.fslot + slot * x.nm + lane, tot);
+        if (HAS_H) {
+            const double t3 = warp_sum(uu[3]);
+            if (lane == 0) atomicAdd(a.fslot + slot * x.nm + 16, t3);
+        }
+    }
+}
+
 // -------------------------------------------------------------------------------------------------
 // stages 2.1 + 3 (PHASE 1: face moments, boundary-face values, lagged boundary gradient) and
 // stage 4 (PHASE 2: relaxed internal-face values into the slab flux buffer).
@@ -720,7 +922,10 @@ k_hot_outgoing(StepArgs a) {
                     if (ch + 1 < x.nchunk) hot_stage_off<CI, P::NFLD, NSLOT>(gbs, hbs, soff, ch + 1, st, lane);
                     else stage_next_item(st);
                 };
-                hot_out_item<PHASE, HAS_H, NE, TW, CI, true, (NE == 4 || NE == 6)>(a, x, cur, stages, P::STAGE_D, q, prefetch);
+                if constexpr (SEL == 1 && PHASE == 1 && (NE == 4 || NE == 6))
+                    hot_axis_item<HAS_H, NE, CI>(a, x, cur, stages, P::STAGE_D, q, prefetch);
+                else
+                    hot_out_item<PHASE, HAS_H, NE, TW, CI, true, (NE == 4 || NE == 6)>(a, x, cur, stages, P::STAGE_D, q, prefetch);
             } else if (SEL != 1 && cur.ne == NE) {
                 // all NE entries exist; boundary entries (if any) stream the lagged gradient from another
                 // array, so only all-internal cells can use the register offsets
