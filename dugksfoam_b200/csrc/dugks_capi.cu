@@ -122,6 +122,12 @@ struct dugks_handle {
     size_t hsmem_rlx = 0, hsmem_half = 0;
     int hot_grid_half = 148, hot_grid_axis = 148;
     bool split_axis = false, want_split = false;
+    // gBarP storage: one block per slab, or (wmode) ONE transient block shared by the face-storage slabs
+    // (their update reads w, left in place of gTilde by the half-step kernel) + one block per other slab
+    double *gb_store = nullptr, *hb_store = nullptr;
+    bool wmode = false;
+    size_t hsmem_rlx_w = 0;
+    int hot_grid_rlx_w = 148;
     size_t hsmem_axis = 0;
     std::vector<char> slab_pair_ok;   // per slab: the axis-only launch of phase 1 is valid (hot_axis_item)
     int n_axis = 0, axis_ne = 0;
@@ -273,7 +279,11 @@ static void launch_hot_update(dugks_handle* h, const StepArgs& a) {
 template <bool H>
 static void launch_hot_relax(dugks_handle* h, const StepArgs& a) {
     const int tw = h->tma_tw;
-#define DUGKS_HOT_RLX(NE_, TW_) k_hot_relax_update<H, NE_, TW_, CI_RLX><<<h->hot_grid_rlx, HOT_WARPS * 32, h->hsmem_rlx, h->stream>>>(a)
+#define DUGKS_HOT_RLX(NE_, TW_)                                                                                            \
+    do {                                                                                                                   \
+        if (h->wmode) k_hot_relax_update<H, NE_, TW_, CI_RLX, true><<<h->hot_grid_rlx_w, HOT_WARPS * 32, h->hsmem_rlx_w, h->stream>>>(a); \
+        else k_hot_relax_update<H, NE_, TW_, CI_RLX, false><<<h->hot_grid_rlx, HOT_WARPS * 32, h->hsmem_rlx, h->stream>>>(a);             \
+    } while (0)
     if (h->hot_ne == 4) { if (tw == 32) DUGKS_HOT_RLX(4, 32); else DUGKS_HOT_RLX(4, 64); }
     else if (h->hot_ne == 6) { if (tw == 32) DUGKS_HOT_RLX(6, 32); else DUGKS_HOT_RLX(6, 64); }
     else { if (tw == 32) DUGKS_HOT_RLX(8, 32); else DUGKS_HOT_RLX(8, 64); }
@@ -281,9 +291,12 @@ static void launch_hot_relax(dugks_handle* h, const StepArgs& a) {
 }
 template <bool H, int NE, int TW>
 static cudaError_t hot_cfg_rlx(dugks_handle* h, int* occ) {
-    h->hsmem_rlx = HotRelaxPlan<H, NE, TW, CI_RLX>::total(h->ntab);
-    cudaError_t e = cudaFuncSetAttribute(k_hot_relax_update<H, NE, TW, CI_RLX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->hsmem_rlx);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_hot_relax_update<H, NE, TW, CI_RLX>, HOT_WARPS * 32, h->hsmem_rlx);
+    h->hsmem_rlx = HotRelaxPlan<H, NE, TW, CI_RLX, false>::total(h->ntab);
+    h->hsmem_rlx_w = HotRelaxPlan<H, NE, TW, CI_RLX, true>::total(h->ntab);
+    cudaError_t e = cudaFuncSetAttribute(k_hot_relax_update<H, NE, TW, CI_RLX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->hsmem_rlx);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_hot_relax_update<H, NE, TW, CI_RLX, false>, HOT_WARPS * 32, h->hsmem_rlx);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_hot_relax_update<H, NE, TW, CI_RLX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->hsmem_rlx_w);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ + 1, k_hot_relax_update<H, NE, TW, CI_RLX, true>, HOT_WARPS * 32, h->hsmem_rlx_w);
     return e;
 }
 template <int PHASE, bool H, int NE, int TW>
@@ -294,7 +307,7 @@ template <bool H>
 static int hot_configure(dugks_handle* h) {
     const int ntab = h->ntab, tw = h->tma_tw;
     cudaError_t e = cudaSuccess;
-    int occ[4] = {1, 1, 1, 1};
+    int occ[5] = {1, 1, 1, 1, 1};
 #define DUGKS_HOT_CFG(NE_)                                                                                   \
     do {                                                                                                     \
         h->hsmem_out1 = HotPlan<1, H, NE_, 32, CI_OUT1>::total(ntab);                                                 \
@@ -351,6 +364,7 @@ static int hot_configure(dugks_handle* h) {
     if (const char* e = getenv("DUGKS_UPD_CTAS")) occ[2] = std::max(1, std::min(occ[2], atoi(e)));
     h->hot_grid_upd = std::max(1, std::min(dev_sms * std::max(occ[2], 1), max_ctas));
     h->hot_grid_rlx = std::max(1, std::min(dev_sms * std::max(occ[3], 1), max_ctas));
+    h->hot_grid_rlx_w = std::max(1, std::min(dev_sms * std::max(occ[4], 1), max_ctas));
     h->hot_grid_half = std::max(1, std::min(dev_sms * std::max(occ_half, 1), max_ctas));
     h->hot_grid_axis = std::max(1, std::min(dev_sms * std::max(occ_axis, 1), max_ctas));
     if (getenv("DUGKS_VERBOSE"))
@@ -361,14 +375,25 @@ static int hot_configure(dugks_handle* h) {
     return 0;
 }
 
+// Where the gBarP block of slab a.slab lives: every kernel addresses it as a.gb + slab * nCells * L * 32,
+// so the base pointer is shifted instead of touching the kernels.
+static void map_gb(const dugks_handle* h, StepArgs& a) {
+    if (!h->wmode) return;
+    const long long block = a.slab < h->n_keep ? 0 : 1 + (a.slab - h->n_keep);
+    const long long shift = (block - a.slab) * (long long)h->nc * h->L * h->Rs;
+    a.gb = h->gb_store + shift;
+    if (h->hb_store) a.hb = h->hb_store + shift;
+}
+
 template <bool H>
 static int launch_slab_kernels_phase1(dugks_handle* h, StepArgs a) {
     int rc;
     long long items = (long long)h->nc * (h->Rs / 32);
+    map_gb(h, a);
     {
         Timed t(h, 2);
         if (h->use_hot && h->hsmem_half > 0)
-            k_hot_halfstep<H><<<h->hot_grid_half, HOT_WARPS * 32, h->hsmem_half, h->stream>>>(a, h->tma_tw);
+            k_hot_halfstep<H><<<h->hot_grid_half, HOT_WARPS * 32, h->hsmem_half, h->stream>>>(a, h->tma_tw, (h->wmode && a.slab < h->n_keep) ? 1 : 0);
         else
             k_cell_halfstep<H><<<grid_for(items), WARPS_PER_CTA * 32, 0, h->stream>>>(a, 0);
     }
@@ -423,6 +448,7 @@ template <bool H>
 static int launch_slab_kernels_phase2(dugks_handle* h, StepArgs a) {
     int rc;
     long long items = (long long)h->nc * (h->Rs / 32);
+    map_gb(h, a);
     if (h->nbf > 0) {
         long long bitems = (long long)h->nbf * (h->Rs / 32);
         if (h->use_hot) {
@@ -1243,7 +1269,8 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
     CUDAB(cudaMemGetInfo(&free_b, &total_b));
     const size_t ncell_dv = (size_t)nc * h->nflat, nb_dv = (size_t)nbf * h->nflat;
     const int nfld = h->hasH ? 2 : 1;
-    size_t need = (2 * ncell_dv + 3 * nb_dv + (h->has_sym ? nb_dv : 0) + (size_t)nif * L * h->Rs) * nfld * sizeof(double) +
+    // gBarP: at least one slab block (face-storage slabs share a transient one), at most one per slab
+    size_t need = (ncell_dv + (size_t)nc * L * h->Rs + 3 * nb_dv + (h->has_sym ? nb_dv : 0) + (size_t)nif * L * h->Rs) * nfld * sizeof(double) +
                   ((size_t)(2 * nif + nbf) + nc) * h->nm * sizeof(double);
     if (need > free_b) {
         fail(h, DUGKS_ERR_NOMEM, "state needs %.2f GB of device memory, only %.2f GB free (nCells=%d, local DVs=%d, h %s)",
@@ -1252,14 +1279,13 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
     }
     // HOT_PAD: the bulk copies of a tail chunk always fetch HOT_CI velocity points
     TRYB(dev_alloc(h, &A.gt, ncell_dv + HOT_PAD));
-    TRYB(dev_alloc(h, &A.gb, ncell_dv + HOT_PAD));
+    // gBarP (A.gb, A.hb) is allocated with the face storage below: how much of it must persist depends on it
     TRYB(dev_alloc(h, &A.gsb, nb_dv + HOT_PAD));
     TRYB(dev_alloc(h, &h->gam_a_g, nb_dv + HOT_PAD));
     TRYB(dev_alloc(h, &h->gam_b_g, nb_dv + HOT_PAD));
     TRYB(dev_alloc(h, &A.fbuf_g, (size_t)nif * L * h->Rs + HOT_PAD));
     if (h->hasH) {
         TRYB(dev_alloc(h, &A.ht, ncell_dv + HOT_PAD));
-        TRYB(dev_alloc(h, &A.hb, ncell_dv + HOT_PAD));
         TRYB(dev_alloc(h, &A.hsb, nb_dv + HOT_PAD));
         TRYB(dev_alloc(h, &h->gam_a_h, nb_dv + HOT_PAD));
         TRYB(dev_alloc(h, &h->gam_b_h, nb_dv + HOT_PAD));
@@ -1351,14 +1377,34 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
 
     // ---- face-storage slabs: as many as device memory allows (all of them from 2 GPUs up at the
     // 64^3 x 28^3 size; about half on one GPU).  Cells with too many faces need the flux-buffer path.
+    // A face-storage slab needs its gBarP only during phase 1 (its update reads w = -1/3 gTilde + 4/3 gBarP,
+    // which the half-step kernel leaves in place of gTilde), so all of them share ONE transient gBarP block
+    // (wmode); the other slabs keep theirs for the second gradient pass.
+    size_t gb_blocks = (size_t)h->nslab;
     if (h->use_hot && h->n_big == 0 && nif > 0) {
         size_t free2 = 0, total2 = 0;
         CUDAB(cudaMemGetInfo(&free2, &total2));
-        const size_t per_slab = (size_t)nif * L * h->Rs * sizeof(double) * nfld;
+        const size_t per_slab = (size_t)nif * L * h->Rs * sizeof(double) * nfld;      // face values of a slab
+        const size_t per_gb = (size_t)nc * L * h->Rs * sizeof(double) * nfld;          // gBarP of a slab
         const size_t reserve = (size_t)3 << 30;   // NCCL buffers, CUDA context growth, caller's own allocations
-        long long fit = free2 > reserve ? (long long)((free2 - reserve) / per_slab) : 0;
+        const bool can_w = h->hsmem_half > 0 && getenv("DUGKS_NO_WMODE") == nullptr;   // test hook: persistent gBarP everywhere
+        const long long avail = free2 > reserve ? (long long)(free2 - reserve) : 0;
+        long long fit = 0;
+        for (long long k = h->nslab; k > 0; k--) {
+            const long long blocks = can_w ? (h->nslab - k) + 1 : h->nslab;
+            if (blocks * (long long)per_gb + k * (long long)per_slab <= avail) { fit = k; break; }
+        }
         if (const char* e = getenv("DUGKS_KEEP_SLABS")) fit = std::min<long long>(fit, atoll(e));   // test hook
         h->n_keep = (int)std::max<long long>(0, std::min<long long>(fit, h->nslab));
+        h->wmode = can_w && h->n_keep > 0;
+        if (h->wmode) gb_blocks = (size_t)(h->nslab - h->n_keep) + 1;
+    }
+    TRYB(dev_alloc(h, &h->gb_store, gb_blocks * nc * L * h->Rs + HOT_PAD));
+    if (h->hasH) TRYB(dev_alloc(h, &h->hb_store, gb_blocks * nc * L * h->Rs + HOT_PAD));
+    A.gb = h->gb_store; A.hb = h->hb_store;
+    if (h->use_hot && h->n_big == 0 && nif > 0) {
+        const size_t per_slab = (size_t)nif * L * h->Rs * sizeof(double) * nfld;
+        (void)per_slab;
         if (h->n_keep > 0) {
             TRYB(dev_alloc(h, &h->fkeep_g, (size_t)h->n_keep * nif * L * h->Rs + HOT_PAD, false));
             if (h->hasH) TRYB(dev_alloc(h, &h->fkeep_h, (size_t)h->n_keep * nif * L * h->Rs + HOT_PAD, false));

@@ -278,9 +278,17 @@ __device__ __forceinline__ void hot_stage_off(const double* gbs, const double* h
     const uint32_t coff = (uint32_t)ch * (CI * 256u);
 #pragma unroll
     for (int fld = 0; fld < NFLD; fld++) {
+        // array base + chunk offset once per chunk (kept opaque: otherwise the compiler folds the chunk
+        // offset into every stream's 32-bit product and adds the 64-bit base per stream, 3 instructions each)
+        unsigned long long cbase = (unsigned long long)(fld ? hbs : gbs) + coff;
+        asm volatile("" : "+l"(cbase));
 #pragma unroll
-        for (int k = 0; k < NSLOT; k++)
-            hot_stage_one<CI>(sdst + (fld * NSLOT + k) * (CI * 256), fld ? hbs : gbs, soff[k], coff);
+        for (int k = 0; k < NSLOT; k++) {
+            const char* p = reinterpret_cast<const char*>(cbase + (unsigned long long)soff[k] * 16u);
+#pragma unroll
+            for (int part = 0; part < CI * 256 / 512; part++)
+                cp_async16(sdst + (fld * NSLOT + k) * (CI * 256) + part * 512, p + part * 512);
+        }
     }
 }
 
@@ -959,6 +967,11 @@ k_hot_outgoing(StepArgs a) {
 // -------------------------------------------------------------------------------------------------
 // stage 5 + the cell moments of stage 6: gTilde <- -1/3 gTilde + 4/3 gBarP - dt/V sum_f +-(xi.Sf) g_f
 // (discreteVelocity.C:934-978, fvDVM.C:612-622,712-721).  Streams: gTilde, gBarP, one per face.
+// w = -1/3 gTilde + 4/3 gBarP (discreteVelocity.C:937): the cell part of the update.  One definition, so that
+// the kernels that read (gTilde, gBarP) and the ones that read a stored w (face-storage slabs: the half-step
+// kernel leaves w in place of gTilde and gBarP in a transient slab buffer) give the same bits.
+__device__ __forceinline__ double hot_w_combine(double gt, double gb) { return fma(4.0 / 3, gb, (-1.0 / 3) * gt); }
+
 template <bool HAS_H, int NE, int CI>
 struct HotUpdPlan {
     static constexpr int NFLD = HAS_H ? 2 : 1;
@@ -975,7 +988,9 @@ struct HotUpdMeta {
     int so, sf;                  // this lane's stream slot (lane - 2): other cell / face id of that entry
 };
 
-// loads only (see hot_meta_issue)
+// loads only (see hot_meta_issue).  NPRE: cell streams ahead of the face streams (gTilde, gBarP: 2; or the
+// combination w = -1/3 gTilde + 4/3 gBarP alone: 1)
+template <int NPRE = 2>
 __device__ __forceinline__ void hot_upd_issue(const StepArgs& a, int item, int lane, HotUpdMeta& M) {
     const int* rec = a.cmeta + (size_t)item * CMETA_N;
     M.c = ldg_early(rec + 20);
@@ -983,28 +998,28 @@ __device__ __forceinline__ void hot_upd_issue(const StepArgs& a, int item, int l
     M.e0 = h2.x;
     M.ne = h2.y;
     M.face = ldg_early(rec + 10 + (lane & 7));
-    M.so = ldg_early(rec + 2 + ((lane - 2) & 7));
-    M.sf = ldg_early(rec + 10 + ((lane - 2) & 7));
+    M.so = ldg_early(rec + 2 + ((lane - NPRE) & 7));
+    M.sf = ldg_early(rec + 10 + ((lane - NPRE) & 7));
 }
 
 // fsrc_g/h: where internal-face values come from (flux buffer or kept face values of the slab)
-template <bool HAS_H>
+template <bool HAS_H, int NPRE = 2>
 __device__ __forceinline__ void hot_upd_commit(const StepArgs& a, int lane, const double* gts, const double* hts,
                                                const double* gbs, const double* hbs, const double* gsbs,
                                                const double* hsbs, const double* fsrc_g, const double* fsrc_h, int NE,
                                                unsigned long long* sp, HotUpdMeta& M) {
     const int blk = a.dv.L * 32;
-    const int NSLOT = 2 + NE;
+    const int NSLOT = NPRE + NE;
     const int pk = M.ne;
     M.ne = pk & 0xff; M.nint = (pk >> 8) & 0xff;
     M.face = (lane < M.ne && M.ne <= NE) ? (M.face & 0x7fffffff) : 0;
-    if (M.ne <= NE && lane < 2 + M.ne) {
+    if (M.ne <= NE && lane < NPRE + M.ne) {
         const int o = M.so, f = M.sf & 0x7fffffff;
 #pragma unroll
         for (int fld = 0; fld < (HAS_H ? 2 : 1); fld++) {
             const double* src;
             if (lane == 0) src = (fld ? hts : gts) + (size_t)M.c * blk;
-            else if (lane == 1) src = (fld ? hbs : gbs) + (size_t)M.c * blk;
+            else if (NPRE == 2 && lane == 1) src = (fld ? hbs : gbs) + (size_t)M.c * blk;
             else if (o >= 0) src = (fld ? fsrc_h : fsrc_g) + (size_t)f * blk;
             else src = (fld ? hsbs : gsbs) + (size_t)(-1 - o) * blk;
             sp[fld * NSLOT + lane] = (unsigned long long)src;
@@ -1142,7 +1157,7 @@ k_hot_update(StepArgs a) {
                 }
 #pragma unroll
                 for (int u = 0; u < CI; u++) {
-                    const double vnew = (-1.0 / 3) * sf[u * 32] + (4.0 / 3) * sf[(CI + u) * 32] - sum[u] * dtv;   // :937,952
+                    const double vnew = fma(-sum[u], dtv, hot_w_combine(sf[u * 32], sf[(CI + u) * 32]));   // :937,952
                     if (i0 + u >= Ln) continue;   // tail chunk (warp-uniform)
                     __stcs((fld == 0 ? gdst : hdst) + (i0 + u) * 32, vnew);
                     if (fld == 0) {
@@ -1177,10 +1192,13 @@ k_hot_update(StepArgs a) {
 // by the two cells that share the face; each relaxes it to g_f with the face equilibrium
 // (discreteVelocity.C:867-881) and adds its flux (:934-978).  Boundary-face values come relaxed from
 // k_bnd_relax.  Replaces k_hot_outgoing<2> + k_hot_update and their flux buffer round trip.
-template <bool HAS_H, int NE, int TW, int CI>
+// WMODE: the cell stream is w = -1/3 gTilde + 4/3 gBarP, left in place of gTilde by the half-step kernel
+// (one stream and 8 bytes per update less; gBarP of the slab need not outlive phase 1).
+template <bool HAS_H, int NE, int TW, int CI, bool WMODE = false>
 struct HotRelaxPlan {
     static constexpr int NFLD = HAS_H ? 2 : 1;
-    static constexpr int NSLOT = 2 + NE;
+    static constexpr int NPRE = WMODE ? 1 : 2;
+    static constexpr int NSLOT = NPRE + NE;
     static constexpr int STAGE_D = NFLD * NSLOT * CI * 32;
     // the moment reduction (32 x 17 doubles) runs through the face tables, which are dead by then
     static constexpr int TAB_D = (NE * 4 * TW + NE * 2) > 32 * 17 ? (NE * 4 * TW + NE * 2) : 32 * 17;
@@ -1191,11 +1209,11 @@ struct HotRelaxPlan {
     static __host__ size_t total(int ntab) { return txs_bytes(ntab) + HOT_WARPS * PER_WARP; }
 };
 
-template <bool HAS_H, int NE, int TW, int CI>
+template <bool HAS_H, int NE, int TW, int CI, bool WMODE>
 __global__ void __launch_bounds__(HOT_WARPS * 32, HOT_MINB(CI))
 k_hot_relax_update(StepArgs a) {
-    using P = HotRelaxPlan<HAS_H, NE, TW, CI>;
-    constexpr int NSLOT = P::NSLOT, NTOT = P::NFLD * P::NSLOT;
+    using P = HotRelaxPlan<HAS_H, NE, TW, CI, WMODE>;
+    constexpr int NSLOT = P::NSLOT, NTOT = P::NFLD * P::NSLOT, NPRE = P::NPRE;
     extern __shared__ __align__(128) unsigned char dyn[];
     const DevDV& dv = a.dv;
     const int L = dv.L, nc = a.m.nc, blk = L * 32;
@@ -1256,10 +1274,10 @@ k_hot_relax_update(StepArgs a) {
     int gsel = 0;
     HotUpdMeta cur{}, nxt{};
     if (item < nc) {
-        hot_upd_issue(a, item, lane, cur);
-        hot_upd_commit<HAS_H>(a, lane, gts, hts, gbs, hbs, gsbs, hsbs, fk_g, fk_h, NE, sptr, cur);
+        hot_upd_issue<NPRE>(a, item, lane, cur);
+        hot_upd_commit<HAS_H, NPRE>(a, lane, gts, hts, gbs, hbs, gsbs, hsbs, fk_g, fk_h, NE, sptr, cur);
         if (cur.ne <= NE) {
-            hot_stage<CI, NTOT, NSLOT, false>(sptr, cur.ne + 1, 0, stages, lane);
+            hot_stage<CI, NTOT, NSLOT, false>(sptr, cur.ne + NPRE - 1, 0, stages, lane);
             stage_records(cur, recs);
         }
         cp_async_commit();
@@ -1269,13 +1287,13 @@ k_hot_relax_update(StepArgs a) {
         const bool has_next = nitem < nc;
         unsigned long long* sp_cur = sptr + gsel * HOT_PTRS;
         unsigned long long* sp_nxt = sptr + (gsel ^ 1) * HOT_PTRS;
-        if (has_next) hot_upd_issue(a, nitem, lane, nxt);
+        if (has_next) hot_upd_issue<NPRE>(a, nitem, lane, nxt);
         // called once, right before the last chunk of the current cell is computed
         auto stage_next_item = [&](double* st) {
             if (!has_next) return;
-            hot_upd_commit<HAS_H>(a, lane, gts, hts, gbs, hbs, gsbs, hsbs, fk_g, fk_h, NE, sp_nxt, nxt);
+            hot_upd_commit<HAS_H, NPRE>(a, lane, gts, hts, gbs, hbs, gsbs, hsbs, fk_g, fk_h, NE, sp_nxt, nxt);
             if (nxt.ne <= NE) {
-                hot_stage<CI, NTOT, NSLOT, false>(sp_nxt, nxt.ne + 1, 0, st, lane);
+                hot_stage<CI, NTOT, NSLOT, false>(sp_nxt, nxt.ne + NPRE - 1, 0, st, lane);
                 stage_records(nxt, recs + (gsel ^ 1) * P::REC_D);
             }
         };
@@ -1300,10 +1318,10 @@ k_hot_relax_update(StepArgs a) {
 #pragma unroll
             for (int fld = 0; fld < P::NFLD; fld++) {
                 hot_stage_one_ef<CI>(sdst + (fld * NSLOT + 0) * (CI * 256), fld ? hts : gts, offc, coff, pol_ef);
-                hot_stage_one_ef<CI>(sdst + (fld * NSLOT + 1) * (CI * 256), fld ? hbs : gbs, offc, coff, pol_ef);
+                if (!WMODE) hot_stage_one_ef<CI>(sdst + (fld * NSLOT + 1) * (CI * 256), fld ? hbs : gbs, offc, coff, pol_ef);
 #pragma unroll
                 for (int j = 0; j < NE; j++)   // every face block is read by two cells: keep it in L2 for the second one
-                    hot_stage_one_ef<CI>(sdst + (fld * NSLOT + 2 + j) * (CI * 256), fld ? fk_h : fk_g, offf[j], coff, pol_el);
+                    hot_stage_one_ef<CI>(sdst + (fld * NSLOT + NPRE + j) * (CI * 256), fld ? fk_h : fk_g, offf[j], coff, pol_el);
             }
         };
         // outward area vectors (sign folded in) and the face equilibria of the internal faces
@@ -1349,7 +1367,7 @@ k_hot_relax_update(StepArgs a) {
                 double* st = stages + ((q & 1) ^ 1) * P::STAGE_D;
                 if (ch + 1 < nchunk) {
                     if (interior) stage_interior(ch + 1, st);
-                    else hot_stage<CI, NTOT, NSLOT, false>(sp_cur, ne + 1, ch + 1, st, lane);
+                    else hot_stage<CI, NTOT, NSLOT, false>(sp_cur, ne + NPRE - 1, ch + 1, st, lane);
                 } else stage_next_item(st);
             }
             cp_async_commit();
@@ -1383,18 +1401,19 @@ k_hot_relax_update(StepArgs a) {
                             double eq;
                             if (fld == 0) eq = fma(cq, cc, 1.0) * gM;                                  // :1042
                             else eq = (kd + cq * ((cc + 2.0) * kd - 2.0 * a.gas.K)) * gM * frt;        // :1043
-                            const double gf = fma(omrf, sf[((2 + j) * CI + u) * 32], eq);             // :880-881
+                            const double gf = fma(omrf, sf[((NPRE + j) * CI + u) * 32], eq);          // :880-881
                             sum[u] = fma(fma(xx[u], Sx[j], cyz[j]), gf, sum[u]);                       // :952-955
                         }
                     } else if (j < ne) {
 #pragma unroll
                         for (int u = 0; u < CI; u++)
-                            sum[u] = fma(fma(xx[u], Sx[j], cyz[j]), sf[((2 + j) * CI + u) * 32], sum[u]);
+                            sum[u] = fma(fma(xx[u], Sx[j], cyz[j]), sf[((NPRE + j) * CI + u) * 32], sum[u]);
                     }
                 }
 #pragma unroll
                 for (int u = 0; u < CI; u++) {
-                    const double vnew = (-1.0 / 3) * sf[u * 32] + (4.0 / 3) * sf[(CI + u) * 32] - sum[u] * dtv;   // :937,952
+                    const double wcell = WMODE ? sf[u * 32] : hot_w_combine(sf[u * 32], sf[(CI + u) * 32]);
+                    const double vnew = fma(-sum[u], dtv, wcell);                                      // :937,952
                     if (i0 + u >= Ln) continue;   // tail chunk (warp-uniform)
                     __stcs((fld == 0 ? gdst : hdst) + (i0 + u) * 32, vnew);
                     if (fld == 0) {
@@ -1444,7 +1463,7 @@ struct HotHalfPlan {
 
 template <bool HAS_H>
 __global__ void __launch_bounds__(HOT_WARPS * 32, 4)
-k_hot_halfstep(StepArgs a, int tw) {
+k_hot_halfstep(StepArgs a, int tw, int wmode /* also leave w = -1/3 gTilde + 4/3 gBarP in place of gTilde */) {
     using P = HotHalfPlan<HAS_H>;
     extern __shared__ __align__(128) unsigned char dyn[];
     const DevDV& dv = a.dv;
@@ -1512,6 +1531,8 @@ k_hot_halfstep(StepArgs a, int tw) {
         const double* sg = stages + buf * stage_d + lane;
         double* dg = gbs + (size_t)c * blk + lane;
         double* dh = HAS_H ? hbs + (size_t)c * blk + lane : nullptr;
+        double* wg = a.gt + slab_c + (size_t)c * blk + lane;
+        double* wh = HAS_H ? a.ht + slab_c + (size_t)c * blk + lane : nullptr;
         const double* xt0 = xtab + (cb - tmin) * 4;
 #pragma unroll 4
         for (int i = 0; i < Ln; i++) {
@@ -1519,9 +1540,16 @@ k_hot_halfstep(StepArgs a, int tw) {
             const double cc = x01.y + YZ2;                           // cSqrByRT - D - 2
             const double cq = xt0[i * 4 + 2] + QYZ;                  // (1-Pr) cqBy5pRT
             const double gM = x01.x * EYZ;                           // rf * gEqBGK
-            __stcs(dg + i * 32, fma(omrf, sg[i * 32], fma(cq, cc, 1.0) * gM));                                  // :405,1042
-            if (HAS_H)
-                __stcs(dh + i * 32, fma(omrf, sg[(Ln + i) * 32], (kd + cq * ((cc + 2.0) * kd - 2.0 * a.gas.K)) * gM * e.RT));   // :406,1043
+            const double gt_i = sg[i * 32];
+            const double gb_i = fma(omrf, gt_i, fma(cq, cc, 1.0) * gM);                                          // :405,1042
+            __stcs(dg + i * 32, gb_i);
+            if (wmode) __stcs(wg + i * 32, hot_w_combine(gt_i, gb_i));
+            if (HAS_H) {
+                const double ht_i = sg[(Ln + i) * 32];
+                const double hb_i = fma(omrf, ht_i, (kd + cq * ((cc + 2.0) * kd - 2.0 * a.gas.K)) * gM * e.RT);  // :406,1043
+                __stcs(dh + i * 32, hb_i);
+                if (wmode) __stcs(wh + i * 32, hot_w_combine(ht_i, hb_i));
+            }
         }
         __syncwarp();   // stage and tables are free again
     }

@@ -104,6 +104,9 @@ _PATHS = [
     ("keep_one", {"DUGKS_KEEP_SLABS": "1"}),            # both kinds of slab in one step
     ("no_axis", {"DUGKS_NO_AXIS": "1"}),                # general path also for axis-aligned cells
     ("no_axis_keep_none", {"DUGKS_NO_AXIS": "1", "DUGKS_KEEP_SLABS": "0"}),
+    ("no_split", {"DUGKS_NO_SPLIT_AXIS": "1"}),         # axis-aligned cells inside the unified phase-1 launch
+    ("no_wmode", {"DUGKS_NO_WMODE": "1"}),              # face-storage slabs with persistent gBarP (update reads gTilde, gBarP)
+    ("no_wmode_keep_one", {"DUGKS_NO_WMODE": "1", "DUGKS_KEEP_SLABS": "1"}),
     ("gen1_tma", {"DUGKS_NO_HOT": "1"}),                # first-generation bulk-copy kernels
     ("gen1_ldg", {"DUGKS_NO_HOT": "1", "DUGKS_NO_TMA": "1"}),
     ("generic", {"DUGKS_NO_HOT": "1", "DUGKS_FORCE_GENERIC": "1"}),   # cells with many faces
@@ -113,12 +116,15 @@ _PATHS = [
 @pytest.mark.parametrize("path,env", _PATHS, ids=[p[0] for p in _PATHS])
 def test_every_kernel_path(oracle_lib, monkeypatch, path, env):
     """Every device code path that can carry the step gives the oracle's answer."""
-    for k in ("DUGKS_KEEP_SLABS", "DUGKS_NO_HOT", "DUGKS_NO_TMA", "DUGKS_FORCE_GENERIC", "DUGKS_NO_AXIS"):
+    for k in ("DUGKS_KEEP_SLABS", "DUGKS_NO_HOT", "DUGKS_NO_TMA", "DUGKS_FORCE_GENERIC", "DUGKS_NO_AXIS",
+              "DUGKS_NO_SPLIT_AXIS", "DUGKS_NO_WMODE"):
         monkeypatch.delenv(k, raising=False)
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     zoo = [("cavity3d_5_gh8_distort", cs.cavity3d_case(5, 8, distort=0.15, perturb=0.01), False),
            ("cavity3d_6_gh28", cs.cavity3d_case(6, 28, perturb=0.01), False),      # two slabs
+           ("cavity3d_10_gh8", cs.cavity3d_case(10, 8, perturb=0.01), False),      # mostly interior cells: axis-only launch
+           ("cavity2d_12_gh28", cs.cavity2d_case(12, 28, perturb=0.01), False),    # same in 2-D, with h
            ("cavity2d_9_nc9_ties", cs.cavity2d_case(9, 9, quad="NC", perturb=0.01), False),
            ("tri_8_gh8", cs.tri_cavity_case(8, 8, perturb=0.01), False),
            ("cavity3d_4_gh8_storeh", cs.cavity3d_case(4, 8, perturb=0.01), True)]
