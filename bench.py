@@ -288,7 +288,11 @@ def main():
     # algorithmic bytes per update of each kernel family: half-step 8+8; outgoing reads 8 and
     # writes F*8 (kept face values or out-flux); update/relax reads 8+8+F*8 and writes 8
     F8 = 8.0 * nf * case.faces_per_cell()
-    alg = {"k_cell_halfstep": 16.0 * nf, "k_cell_outgoing": 8.0 * nf + F8, "k_cell_update": 24.0 * nf + F8}
+    # face-storage slabs: the half-step kernel also leaves w = -1/3 gTilde + 4/3 gBarP in place of gTilde
+    # (+8 B written), their update reads w instead of gTilde and gBarP (-8 B); kf = their share of the slabs
+    kf = st0["keep_slabs"] / max(st0["n_slabs"], 1)
+    alg = {"k_cell_halfstep": (16.0 + 8.0 * kf) * nf, "k_cell_outgoing": 8.0 * nf + F8,
+           "k_cell_update": (24.0 - 8.0 * kf) * nf + F8}
     for name, v in fam.items():
         if v["launches_per_step"] > 0 and v["ms_per_step"] > 0:
             upd = updates_per_step / world * (v["launches_per_step"] / st0["n_slabs"])   # updates this family touches per step

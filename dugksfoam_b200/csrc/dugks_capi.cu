@@ -125,7 +125,7 @@ struct dugks_handle {
     // gBarP storage: one block per slab, or (wmode) ONE transient block shared by the face-storage slabs
     // (their update reads w, left in place of gTilde by the half-step kernel) + one block per other slab
     double *gb_store = nullptr, *hb_store = nullptr;
-    bool wmode = false;
+    bool wmode = false, gb_in_fbuf = false;
     size_t hsmem_rlx_w = 0;
     int hot_grid_rlx_w = 148;
     size_t hsmem_axis = 0;
@@ -235,9 +235,10 @@ static int do_allreduce(dugks_handle* h, double* buf, size_t n) {
 #define DUGKS_CI_OUT1 4
 #endif
 constexpr int CI_OUT1 = DUGKS_CI_OUT1, CI_OUT2 = 2, CI_RLX = 2;
-// axis-only launch of phase 1 (hot_axis_item): 2 points per chunk keep it at 160 registers = 3 CTAs/SM without spills
+// axis-only launch of phase 1 (hot_axis_item): chunks of 4 points are staged, HOT_AXIS_CU = 2 points are advanced
+// together, which keeps it at 3 CTAs/SM without spills
 #ifndef DUGKS_CI_AXIS
-#define DUGKS_CI_AXIS 2
+#define DUGKS_CI_AXIS 4
 #endif
 constexpr int CI_AXIS = DUGKS_CI_AXIS;
 // update kernel of the flux-buffer path: 4 points per chunk, 2 when h doubles the streams (shared memory per CTA)
@@ -379,10 +380,17 @@ static int hot_configure(dugks_handle* h) {
 // so the base pointer is shifted instead of touching the kernels.
 static void map_gb(const dugks_handle* h, StepArgs& a) {
     if (!h->wmode) return;
-    const long long block = a.slab < h->n_keep ? 0 : 1 + (a.slab - h->n_keep);
-    const long long shift = (block - a.slab) * (long long)h->nc * h->L * h->Rs;
-    a.gb = h->gb_store + shift;
-    if (h->hb_store) a.hb = h->hb_store + shift;
+    const long long stride = (long long)h->nc * h->L * h->Rs;
+    if (a.slab < h->n_keep) {
+        // transient block of the face-storage slabs: the flux buffer when it is large enough (it is only
+        // used in phase 2 of the OTHER slabs, never while a phase-1 kernel runs), else block 0 of the store
+        a.gb = (h->gb_in_fbuf ? h->A.fbuf_g : h->gb_store) - a.slab * stride;
+        if (h->hb_store) a.hb = (h->gb_in_fbuf ? h->A.fbuf_h : h->hb_store) - a.slab * stride;
+    } else {
+        const long long block = (h->gb_in_fbuf ? 0 : 1) + (a.slab - h->n_keep);
+        a.gb = h->gb_store + (block - a.slab) * stride;
+        if (h->hb_store) a.hb = h->hb_store + (block - a.slab) * stride;
+    }
 }
 
 template <bool H>
@@ -1369,7 +1377,7 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
         const int bad = flags[0];
         h->slab_pair_ok.assign(h->nslab, 0);
         for (int s = 0; s < h->nslab; s++)
-            h->slab_pair_ok[s] = flags[1 + s] == 0 && dv_len(A.dv, s) % CI_AXIS == 0;
+            h->slab_pair_ok[s] = flags[1 + s] == 0 && dv_len(A.dv, s) % HOT_AXIS_CU == 0;
         // abscissae that are not ascending give upwind sets that are not ranges: first-generation kernels
         if (bad) h->use_hot = false;
         A.upw = d_upw;
@@ -1386,18 +1394,21 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
         CUDAB(cudaMemGetInfo(&free2, &total2));
         const size_t per_slab = (size_t)nif * L * h->Rs * sizeof(double) * nfld;      // face values of a slab
         const size_t per_gb = (size_t)nc * L * h->Rs * sizeof(double) * nfld;          // gBarP of a slab
-        const size_t reserve = (size_t)3 << 30;   // NCCL buffers, CUDA context growth, caller's own allocations
+        // left free: CUDA context growth and the caller's own allocations; NCCL buffers when there are peers
+        const size_t reserve = nranks > 1 ? (size_t)3 << 30 : (size_t)3 << 29;
         const bool can_w = h->hsmem_half > 0 && getenv("DUGKS_NO_WMODE") == nullptr;   // test hook: persistent gBarP everywhere
+        h->gb_in_fbuf = can_w && nif >= nc;
         const long long avail = free2 > reserve ? (long long)(free2 - reserve) : 0;
         long long fit = 0;
         for (long long k = h->nslab; k > 0; k--) {
-            const long long blocks = can_w ? (h->nslab - k) + 1 : h->nslab;
+            const long long blocks = can_w ? (h->nslab - k) + (h->gb_in_fbuf ? 0 : 1) : h->nslab;
             if (blocks * (long long)per_gb + k * (long long)per_slab <= avail) { fit = k; break; }
         }
         if (const char* e = getenv("DUGKS_KEEP_SLABS")) fit = std::min<long long>(fit, atoll(e));   // test hook
         h->n_keep = (int)std::max<long long>(0, std::min<long long>(fit, h->nslab));
         h->wmode = can_w && h->n_keep > 0;
-        if (h->wmode) gb_blocks = (size_t)(h->nslab - h->n_keep) + 1;
+        h->gb_in_fbuf = h->gb_in_fbuf && h->wmode;
+        if (h->wmode) gb_blocks = (size_t)(h->nslab - h->n_keep) + (h->gb_in_fbuf ? 0 : 1);
     }
     TRYB(dev_alloc(h, &h->gb_store, gb_blocks * nc * L * h->Rs + HOT_PAD));
     if (h->hasH) TRYB(dev_alloc(h, &h->hb_store, gb_blocks * nc * L * h->Rs + HOT_PAD));

@@ -27,6 +27,9 @@
 // 4 amortises the geometry reads best (phase 1, 2 CTAs/SM at ~240 registers); 2 halves the stages
 // and the working set so that the table-heavy phase-2 kernels run 3 CTAs/SM (12 warps)
 #define HOT_CI_MAX 4
+#ifndef HOT_AXIS_CU
+#define HOT_AXIS_CU 2     // points advanced together by hot_axis_item (its staged chunk may hold more)
+#endif
 #define HOT_STAGES 2
 #define HOT_PAD (HOT_CI_MAX * 32)   // doubles of slack behind every streamed array (tail chunks copy full size)
 #define FCOEF_N 12        // per-face equilibrium record: Ux Uy Uz a pre qx qy qz omrf RT 0 0
@@ -271,9 +274,11 @@ __device__ __forceinline__ void hot_stage_one_ef(uint32_t sdst, const double* ba
 // interior cells: every stream lives in the same slab array, so 32-bit offsets (16-byte units, already
 // including the lane's 16 bytes) in registers replace the pointer table: one 64-bit multiply-add + CI/2
 // LDGSTS per stream
-template <int CI, int NFLD, int NSLOT>
+// EVL: mark the lines evict-last in L2 (row blocks that six neighbours read again while a stream of
+// single-use stores passes through the same cache)
+template <int CI, int NFLD, int NSLOT, bool EVL = false>
 __device__ __forceinline__ void hot_stage_off(const double* gbs, const double* hbs, const uint32_t (&soff)[NSLOT],
-                                              int ch, double* stage, int lane) {
+                                              int ch, double* stage, int lane, unsigned long long pol = 0) {
     const uint32_t sdst = smem_u32(stage) + (uint32_t)lane * 16u;
     const uint32_t coff = (uint32_t)ch * (CI * 256u);
 #pragma unroll
@@ -286,8 +291,10 @@ __device__ __forceinline__ void hot_stage_off(const double* gbs, const double* h
         for (int k = 0; k < NSLOT; k++) {
             const char* p = reinterpret_cast<const char*>(cbase + (unsigned long long)soff[k] * 16u);
 #pragma unroll
-            for (int part = 0; part < CI * 256 / 512; part++)
-                cp_async16(sdst + (fld * NSLOT + k) * (CI * 256) + part * 512, p + part * 512);
+            for (int part = 0; part < CI * 256 / 512; part++) {
+                if (EVL) cp_async16_ef(sdst + (fld * NSLOT + k) * (CI * 256) + part * 512, p + part * 512, pol);
+                else cp_async16(sdst + (fld * NSLOT + k) * (CI * 256) + part * 512, p + part * 512);
+            }
         }
     }
 }
@@ -304,10 +311,12 @@ struct HotPlan {
     static constexpr int NSLOT = 1 + NE;
     static constexpr int STAGE_D = NFLD * NSLOT * CI * 32;
     static constexpr int GEO_D = NSLOT * 6;
-    // PHASE 1 reduces its moments through the stage that was consumed last (STAGE_D >= 32 * 17)
-    static constexpr bool RED_IN_STAGE = STAGE_D >= 32 * 17;
+    // PHASE 1 reduces its moments through the stage that was consumed last when that is large enough
+    // (32 x 17 doubles for one face at a time, 32 x (2 NV + 1) for hot_reduce_faces2)
+    static constexpr int RED_D = 32 * (2 * (HAS_H ? 17 : 13) + 1);
+    static constexpr bool RED_IN_STAGE = STAGE_D >= RED_D;
     static constexpr int FREC_D = NE * FCOEF_N;   // PHASE 2: face equilibrium records of a cell (double-buffered)
-    static constexpr int EXTRA_D = (PHASE == 1) ? (RED_IN_STAGE ? 0 : 32 * 17) : (NE * 4 * TW + NE * 2 + 2 * FREC_D);
+    static constexpr int EXTRA_D = (PHASE == 1) ? (RED_IN_STAGE ? 0 : RED_D) : (NE * 4 * TW + NE * 2 + 2 * FREC_D);
     static constexpr int PER_WARP_D = 2 * HOT_PTRS + 2 * GEO_D + HOT_STAGES * STAGE_D + EXTRA_D;
     static constexpr size_t PER_WARP = ((size_t)PER_WARP_D * 8 + 127) / 128 * 128;
     static __host__ __device__ size_t txs_bytes(int ntab) { return ((size_t)(ntab + HOT_CI_MAX) * 48 + 127) / 128 * 128; }
@@ -621,30 +630,84 @@ __device__ __forceinline__ void hot_out_item(const StepArgs& a, const HotCtx& x,
 //     per cell) and the two faces' moments are separated at the end by masking lanes.
 // Needs: no tie (|xi.Sf| < VSMALL) on a y / z face of an axis-aligned cell for any row of the slab
 // (k_build_upwind reports that per slab; such slabs take the unified launch) and rows that are whole chunks.
-template <bool HAS_H, int NE, int CI, class Prefetch>
+// Moments of two faces in one pass through shared memory.  Every lane brings raw accumulators for face A
+// and face B (zeros where it takes no part); 2 x NV columns, row stride 2 NV + 1 doubles (odd: no bank
+// conflicts), every lane sums half a column (16 rows) per round of 16 columns.  red: 32 x (2 NV + 1) doubles.
+template <bool HAS_H>
+__device__ __forceinline__ void hot_reduce_faces2(const StepArgs& a, const HotCtx& x, const double (&mA)[4],
+                                                  const double (&mB)[4], const double (&hA)[2], const double (&hB)[2],
+                                                  size_t slotA, size_t slotB, bool onA, bool onB, double* red, int lane) {
+    constexpr int NV = HAS_H ? 17 : 13, NCOL = 2 * NV, RS = NCOL + 1;
+    double* row = red + lane * RS;
+#pragma unroll
+    for (int f = 0; f < 2; f++) {
+        double vv[NM_G];
+        expand_g(f ? mB : mA, x.wr, x.y, x.z, vv);
+#pragma unroll
+        for (int k = 0; k < 13; k++) row[f * NV + k] = vv[k];
+        if (HAS_H) {
+            double uu[NM_H];
+            expand_h(f ? hB : hA, x.wr, x.y, x.z, uu);
+#pragma unroll
+            for (int k = 0; k < 4; k++) row[f * NV + 13 + k] = uu[k];
+        }
+    }
+    __syncwarp();
+    const int col = lane & 15, half = lane >> 4;
+#pragma unroll
+    for (int c0 = 0; c0 < NCOL; c0 += 16) {
+        const int c = c0 + col;
+        const bool live = c < NCOL;                    // compile-time true except in the last round
+        const double* src = red + (half * 16) * RS + (live ? c : 0);
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int rr = 0; rr < 16; rr += 2) {
+            s0 += src[rr * RS];
+            s1 += src[(rr + 1) * RS];
+        }
+        double t = s0 + s1;
+        t += __shfl_xor_sync(0xffffffffu, t, 16);
+        // one warp owns a slot per launch: the fire-and-forget add keeps the sum deterministic
+        const bool second = c >= NV;
+        const size_t slot = second ? slotB : slotA;
+        if (half == 0 && live && (second ? onB : onA)) atomicAdd(a.fslot + slot * x.nm + (second ? c - NV : c), t);
+    }
+    __syncwarp();
+}
+
+// CI: points per staged chunk (copy granularity, kernel template parameter); CU: points advanced together
+// (2 keeps the function at 3 CTAs/SM; a 4-point stage doubles the bytes in flight per warp and halves the
+// per-chunk bookkeeping).
+template <bool HAS_H, int NE, int CI, int CU, class Prefetch>
 __device__ __forceinline__ void hot_axis_item(const StepArgs& a, const HotCtx& x, const HotMeta& cur, double* stages,
-                                              int stage_d, uint32_t& q, Prefetch&& prefetch) {
+                                              int stage_d, uint32_t& q, double* red, Prefetch&& prefetch) {
     static_assert(NE == 4 || NE == 6, "axis-aligned cells have 4 or 6 faces");
+    static_assert(CI % CU == 0, "a staged chunk is a whole number of compute groups");
     constexpr int NSLOT = 1 + NE, NFLD = HAS_H ? 2 : 1, NP = NE / 2 - 1;   // NP: y (and z) pairs
     const int lane = x.lane, L = x.L, blk = x.blk;
     const double* gb_ = x.geo;
     const double* txs = x.txs;
+    // The cell's first chunk and its geometry record are one commit group, possibly still in flight: stage
+    // the second chunk, then wait for the first BEFORE the set-up below reads the record.
+    prefetch(0);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncwarp();
     const unsigned ownmask = __ballot_sync(0xffffffffu, cur.own != 0);
     const unsigned w4[4] = {cur.mw.x, cur.mw.y, cur.mw.z, cur.mw.w};
-    // ---- x faces: masks per point and their warp-uniform per-chunk summaries
+    // ---- x faces: masks per point and their warp-uniform summaries per compute group
     unsigned fullx[2], tiex[2], anyx[2], allx[2];
 #pragma unroll
     for (int j = 0; j < 2; j++) {
         hot_decode((w4[0] >> (j * 16)) & 0xffffu, L, fullx[j], tiex[j]);
-        anyx[j] = __reduce_or_sync(0xffffffffu, hot_spread_any<CI>(fullx[j] | tiex[j]));
-        allx[j] = __reduce_and_sync(0xffffffffu, hot_spread_all<CI>(fullx[j]));
+        anyx[j] = __reduce_or_sync(0xffffffffu, hot_spread_any<CU>(fullx[j] | tiex[j]));
+        allx[j] = __reduce_and_sync(0xffffffffu, hot_spread_all<CU>(fullx[j]));
     }
-    // ---- face storage: element offsets of this lane's rows (the pair's face is chosen per lane)
+    // ---- face storage: running store pointers of this lane's rows (the pair's face is chosen per lane)
     double* const fk_g = a.fkeep_g ? a.fkeep_g + (size_t)a.slab * a.m.nif * blk : nullptr;
     double* const fk_h = (HAS_H && a.fkeep_h) ? a.fkeep_h + (size_t)a.slab * a.m.nif * blk : nullptr;
     const bool keep_on = fk_g != nullptr;
     const ptrdiff_t fk_gh = HAS_H ? fk_h - fk_g : 0;   // the h copy of a face row sits this far behind the g copy
-    // running store pointers (advanced by one chunk per iteration): one 64-bit add per face and chunk
     double* kx[2];
     double* kp[NP];
 #pragma unroll
@@ -678,23 +741,28 @@ __device__ __forceinline__ void hot_axis_item(const StepArgs& a, const HotCtx& x
     }
 
     for (int ch = 0; ch < x.nchunk; ch++) {
-        prefetch(ch);
-        cp_async_commit();
-        cp_async_wait<1>();
-        __syncwarp();
-        const double* sg = stages + (q & 1) * stage_d;
-        const int i0 = ch * CI;
+        if (ch > 0) {
+            prefetch(ch);
+            cp_async_commit();
+            cp_async_wait<1>();
+            __syncwarp();
+        }
+        const double* sg = stages + (q & 1) * stage_d + lane;
+        const int nsub = min(CI / CU, (L - ch * CI) / CU);   // the last chunk of a row may be short (rows are whole groups)
+#pragma unroll 1
+        for (int sub = 0; sub < nsub; sub++) {
+        const int i0 = ch * CI + sub * CU;
         const int tb = x.cb + i0;
 #pragma unroll
         for (int fld = 0; fld < NFLD; fld++) {
-            const double* sf = sg + fld * NSLOT * CI * 32 + lane;
+            const double* sf = sg + fld * NSLOT * CI * 32 + sub * CU * 32;
             // ---- gradient (stock leastSquaresGrad, zeroBoundaryGrad.C:90-99): one component per face
-            double v[CI], g[3][CI], base[CI];
+            double v[CU], g[3][CU], base[CU];
             {
                 const double2 G01 = lds2(gb_);
                 const double G2 = gb_[2];
 #pragma unroll
-                for (int u = 0; u < CI; u++) {
+                for (int u = 0; u < CU; u++) {
                     v[u] = sf[u * 32];
                     g[0][u] = G01.x * v[u]; g[1][u] = G01.y * v[u]; g[2][u] = G2 * v[u];
                 }
@@ -704,12 +772,12 @@ __device__ __forceinline__ void hot_axis_item(const StepArgs& a, const HotCtx& x
                 const int d = j >> 1;
                 const double G = gb_[6 * (1 + j) + d];
 #pragma unroll
-                for (int u = 0; u < CI; u++) g[d][u] = fma(G, sf[((1 + j) * CI + u) * 32], g[d][u]);
+                for (int u = 0; u < CU; u++) g[d][u] = fma(G, sf[((1 + j) * CI + u) * 32], g[d][u]);
             }
             // ---- value at the cell centre moved back by half a step (discreteVelocity.C:498-502)
-            double W[CI][4];
+            double W[CU][4];
 #pragma unroll
-            for (int u = 0; u < CI; u++) {
+            for (int u = 0; u < CU; u++) {
                 const double2 t0 = lds2(txs + (tb + u) * 6), t1 = lds2(txs + (tb + u) * 6 + 2);
                 base[u] = NE == 4 ? fma(t0.x, g[0][u], fma(x.yh, g[1][u], v[u]))
                                   : fma(t0.x, g[0][u], fma(x.yh, g[1][u], fma(x.zh, g[2][u], v[u])));
@@ -723,7 +791,7 @@ __device__ __forceinline__ void hot_axis_item(const StepArgs& a, const HotCtx& x
                 double* const keep = fld == 0 ? kx[j] : kx[j] + fk_gh;
                 if ((allx[j] >> i0) & 1u) {                                  // warp-uniform
 #pragma unroll
-                    for (int u = 0; u < CI; u++) {
+                    for (int u = 0; u < CU; u++) {
                         const double val = fma(r, g[0][u], base[u]);
                         if (keep_on) __stcs(keep + u * 32, val);
                         if (fld == 0) {
@@ -734,12 +802,12 @@ __device__ __forceinline__ void hot_axis_item(const StepArgs& a, const HotCtx& x
                         }
                     }
                 } else {
-                    // the chunk that holds the sign change of xi_x: this side's share is all, half (tie,
+                    // the group that holds the sign change of xi_x: this side's share is all, half (tie,
                     // :513-529) or none; the owner keeps the value unless phi < -VSMALL
                     const unsigned fb = fullx[j] >> i0, tbits = tiex[j] >> i0;
                     const unsigned wbk = ((ownmask >> j) & 1u) ? (fb | tbits) : fb;
 #pragma unroll
-                    for (int u = 0; u < CI; u++) {
+                    for (int u = 0; u < CU; u++) {
                         double val = fma(r, g[0][u], base[u]);
                         if (keep_on && ((wbk >> u) & 1u)) __stcs(keep + u * 32, val);
                         const int hi = ((fb >> u) & 1u) ? 0x3ff00000 : (((tbits >> u) & 1u) ? 0x3fe00000 : 0);
@@ -759,7 +827,7 @@ __device__ __forceinline__ void hot_axis_item(const StepArgs& a, const HotCtx& x
                 double* const keep = fld == 0 ? kp[p] : kp[p] + fk_gh;
                 const bool st = keep_on && act[p];
 #pragma unroll
-                for (int u = 0; u < CI; u++) {
+                for (int u = 0; u < CU; u++) {
                     const double val = fma(rsel[p], g[1 + p][u], base[u]);
                     if (st) __stcs(keep + u * 32, val);
                     if (fld == 0) {
@@ -772,40 +840,32 @@ __device__ __forceinline__ void hot_axis_item(const StepArgs& a, const HotCtx& x
             }
         }
 #pragma unroll
-        for (int j = 0; j < 2; j++) kx[j] += CI * 32;
+        for (int j = 0; j < 2; j++) kx[j] += CU * 32;
 #pragma unroll
-        for (int p = 0; p < NP; p++) kp[p] += CI * 32;
+        for (int p = 0; p < NP; p++) kp[p] += CU * 32;
+        }
         __syncwarp();   // every lane is done with this stage before it is refilled
         q++;
     }
 
-    // ---- face moments: one reduction per face; a pair's accumulators go to the face the lane chose
-    double* const red = stage_d >= 32 * 17 ? stages + ((q & 1) ^ 1) * stage_d : x.red;
-#pragma unroll 1
-    for (int j = 0; j < NE; j++) {
-        double m[4], mh[2];
-        bool lane_on;
-        if (j == 0) { lane_on = true; m[0] = ax[0][0]; m[1] = ax[0][1]; m[2] = ax[0][2]; m[3] = ax[0][3]; mh[0] = bx[0][0]; mh[1] = bx[0][1]; }
-        else if (j == 1) { lane_on = true; m[0] = ax[1][0]; m[1] = ax[1][1]; m[2] = ax[1][2]; m[3] = ax[1][3]; mh[0] = bx[1][0]; mh[1] = bx[1][1]; }
-        else if (j < 4) { lane_on = act[0] && (sel[0] == (j == 2)); m[0] = ap[0][0]; m[1] = ap[0][1]; m[2] = ap[0][2]; m[3] = ap[0][3]; mh[0] = bp[0][0]; mh[1] = bp[0][1]; }
-        else { lane_on = act[NP - 1] && (sel[NP - 1] == (j == 4)); m[0] = ap[NP - 1][0]; m[1] = ap[NP - 1][1]; m[2] = ap[NP - 1][2]; m[3] = ap[NP - 1][3]; mh[0] = bp[NP - 1][0]; mh[1] = bp[NP - 1][1]; }
-        const unsigned on = j == 0 ? anyx[0] : (j == 1 ? anyx[1] : __ballot_sync(0xffffffffu, lane_on));
-        if (on == 0) continue;                                            // warp-uniform: nowhere upwind
-        if (!lane_on) { m[0] = m[1] = m[2] = m[3] = 0.0; mh[0] = mh[1] = 0.0; }
-        double vv[16];
-        expand_g(m, x.wr, x.y, x.z, vv);
-        double uu[NM_H] = {0, 0, 0, 0};
-        if (HAS_H) expand_h(mh, x.wr, x.y, x.z, uu);
-        vv[13] = uu[0]; vv[14] = uu[1]; vv[15] = uu[2];
-        const double tot = warp_reduce16_smem(vv, red, lane);
-        const int fj = __shfl_sync(0xffffffffu, cur.face, j);
-        const size_t slot = (size_t)2 * fj + (((ownmask >> j) & 1u) ? 0 : 1);
-        // one warp owns a slot per launch: the fire-and-forget add keeps the sum deterministic
-        if (lane < 16 && lane < x.nm) atomicAdd(a.fslot + slot * x.nm + lane, tot);
-        if (HAS_H) {
-            const double t3 = warp_sum(uu[3]);
-            if (lane == 0) atomicAdd(a.fslot + slot * x.nm + 16, t3);
-        }
+    // ---- face moments, two faces per pass: (x-, x+), then each pair with its lanes split by the face they chose
+    {
+        const int f0 = __shfl_sync(0xffffffffu, cur.face, 0), f1 = __shfl_sync(0xffffffffu, cur.face, 1);
+        hot_reduce_faces2<HAS_H>(a, x, ax[0], ax[1], bx[0], bx[1], (size_t)2 * f0 + ((ownmask & 1u) ? 0 : 1),
+                                 (size_t)2 * f1 + ((ownmask & 2u) ? 0 : 1), anyx[0] != 0, anyx[1] != 0, red, lane);
+    }
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+        const bool la = act[p] && sel[p], lb = act[p] && !sel[p];
+        double mA[4], mB[4], hA[2], hB[2];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { mA[k] = la ? ap[p][k] : 0.0; mB[k] = lb ? ap[p][k] : 0.0; }
+#pragma unroll
+        for (int k = 0; k < 2; k++) { hA[k] = la ? bp[p][k] : 0.0; hB[k] = lb ? bp[p][k] : 0.0; }
+        const bool onA = __any_sync(0xffffffffu, la), onB = __any_sync(0xffffffffu, lb);
+        const int fa_id = __shfl_sync(0xffffffffu, cur.face, 2 + 2 * p), fb_id = __shfl_sync(0xffffffffu, cur.face, 3 + 2 * p);
+        hot_reduce_faces2<HAS_H>(a, x, mA, mB, hA, hB, (size_t)2 * fa_id + (((ownmask >> (2 + 2 * p)) & 1u) ? 0 : 1),
+                                 (size_t)2 * fb_id + (((ownmask >> (3 + 2 * p)) & 1u) ? 0 : 1), onA, onB, red, lane);
     }
 }
 
@@ -875,6 +935,7 @@ k_hot_outgoing(StepArgs a) {
     x.nchunk = (Ln + CI - 1) / CI;
     x.slab_b = slab_b;
 
+    const unsigned long long pol_el = l2_evict_last_policy();
     const int nw = gridDim.x * HOT_WARPS;
     // items [a.item0, a.item1) of the traversal order (the whole mesh unless the launch is split by cell class)
     const int item_end = a.item1 > 0 ? a.item1 : nc;
@@ -925,13 +986,22 @@ k_hot_outgoing(StepArgs a) {
 #pragma unroll
                 for (int j = 0; j < NE; j++)
                     soff[1 + j] = (uint32_t)__shfl_sync(0xffffffffu, cur.other, j) * (uint32_t)(blk / 2) + (uint32_t)lane;
+#ifdef HOT_P1_EVICT_LAST
+                constexpr bool EVL = SEL == 1 && PHASE == 1;
+#else
+                constexpr bool EVL = false;
+#endif
                 auto prefetch = [&](int ch) {
                     double* st = stages + ((q & 1) ^ 1) * P::STAGE_D;
-                    if (ch + 1 < x.nchunk) hot_stage_off<CI, P::NFLD, NSLOT>(gbs, hbs, soff, ch + 1, st, lane);
+                    if (ch + 1 < x.nchunk) hot_stage_off<CI, P::NFLD, NSLOT, EVL>(gbs, hbs, soff, ch + 1, st, lane, pol_el);
                     else stage_next_item(st);
                 };
-                if constexpr (SEL == 1 && PHASE == 1 && (NE == 4 || NE == 6))
-                    hot_axis_item<HAS_H, NE, CI>(a, x, cur, stages, P::STAGE_D, q, prefetch);
+                if constexpr (SEL == 1 && PHASE == 1 && (NE == 4 || NE == 6)) {
+                    // reduction scratch: the stage consumed last (the chunk count per cell is fixed, so its
+                    // parity after the loop is known now) or the plan's own scratch
+                    double* red = P::RED_IN_STAGE ? stages + (((q + x.nchunk) & 1) ^ 1) * P::STAGE_D : x.red;
+                    hot_axis_item<HAS_H, NE, CI, HOT_AXIS_CU>(a, x, cur, stages, P::STAGE_D, q, red, prefetch);
+                }
                 else
                     hot_out_item<PHASE, HAS_H, NE, TW, CI, true, (NE == 4 || NE == 6)>(a, x, cur, stages, P::STAGE_D, q, prefetch);
             } else if (SEL != 1 && cur.ne == NE) {

@@ -48,7 +48,7 @@ def worker(workload, steps):
     st = dv.stats()
     print(json.dumps({"gups": round(case.nCells * case.nXi / ms / 1e6, 2), "ms": round(ms, 2), "fam": fam,
                       "rho_sum": float(cm["rho"].sum()), "T_sum": float(cm["T"].sum()),
-                      "q_abs": float(np.abs(cm["q"]).sum()), "keep": st.get("n_keep_slabs", -1),
+                      "q_abs": float(np.abs(cm["q"]).sum()), "keep": st.get("keep_slabs", -1),
                       "slabs": st.get("n_slabs", -1)}))
     dv.close()
 

@@ -125,6 +125,9 @@ def test_every_kernel_path(oracle_lib, monkeypatch, path, env):
            ("cavity3d_6_gh28", cs.cavity3d_case(6, 28, perturb=0.01), False),      # two slabs
            ("cavity3d_10_gh8", cs.cavity3d_case(10, 8, perturb=0.01), False),      # mostly interior cells: axis-only launch
            ("cavity2d_12_gh28", cs.cavity2d_case(12, 28, perturb=0.01), False),    # same in 2-D, with h
+           # more cells than resident warps (148 SMs x 12): persistent warps carry state from cell to cell
+           ("cavity3d_20_gh8", cs.cavity3d_case(20, 8, perturb=0.01), False),
+           ("cavity2d_48_gh28", cs.cavity2d_case(48, 28, perturb=0.01), False),
            ("cavity2d_9_nc9_ties", cs.cavity2d_case(9, 9, quad="NC", perturb=0.01), False),
            ("tri_8_gh8", cs.tri_cavity_case(8, 8, perturb=0.01), False),
            ("cavity3d_4_gh8_storeh", cs.cavity3d_case(4, 8, perturb=0.01), True)]
