@@ -30,7 +30,7 @@ EXPORTS = ["dugks_abi_version", "dugks_nccl_unique_id", "dugks_create", "dugks_d
            "dugks_get_face_macros", "dugks_get_boundary_macros", "dugks_get_wall_diag", "dugks_courant",
            "dugks_get_df", "dugks_get_state", "dugks_set_state", "dugks_local_dvs", "dugks_sizes",
            "dugks_get_stats", "dugks_stream", "dugks_kernel_timing", "dugks_partition",
-           "dugks_get_boundary_df", "dugks_row_layout"]
+           "dugks_get_boundary_df", "dugks_row_layout", "dugks_convergence"]
 
 
 class DugksError(RuntimeError):
@@ -76,6 +76,7 @@ def load_library():
     L.dugks_get_boundary_macros.argtypes = [C.c_void_p] + [c_double_p] * 3
     L.dugks_get_wall_diag.argtypes = [C.c_void_p] + [c_double_p] * 2
     L.dugks_courant.argtypes = [C.c_void_p, C.c_double, c_double_p, c_double_p]
+    L.dugks_convergence.argtypes = [C.c_void_p, c_double_p]
     L.dugks_get_df.argtypes = [C.c_void_p, C.c_int32, c_double_p, c_double_p]
     L.dugks_get_state.argtypes = [C.c_void_p, c_double_p, c_double_p]
     L.dugks_set_state.argtypes = [C.c_void_p, c_double_p, c_double_p]
@@ -206,6 +207,13 @@ class fvDVM:
         a, b = C.c_double(), C.c_double()
         self._chk(self.L.dugks_courant(self.h, float(dt), C.byref(a), C.byref(b)), "dugks_courant")
         return a.value, b.value
+
+    def convergence(self):
+        """(TemperatureChange, rhoChange, Uchange) of the time loop's convergence monitor
+        (dugksFoam.C:88-107) since the previous call; the first call compares with the initial fields."""
+        out = np.empty(3)
+        self._chk(self.L.dugks_convergence(self.h, dptr(out)), "dugks_convergence")
+        return tuple(float(v) for v in out)
 
     # -- accessors (fvDVM.H:309-364) -----------------------------------------
     def nXi(self) -> int:

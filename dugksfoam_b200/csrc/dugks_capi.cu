@@ -91,6 +91,7 @@ struct dugks_handle {
     int* d_mirror = nullptr;           // [3][nflat]
     double *snap_g = nullptr, *snap_h = nullptr;
     double* d_co = nullptr;
+    double *d_conv_old = nullptr, *d_conv = nullptr;   // convergence monitor: snapshot [nc][5], sums [6] + partials
     double* d_bstage = nullptr;        // [5 nbf] staging of dugks_set_boundary_macros
     bool has_sym = false, has_wall = false;
     size_t nflat = 0;                  // nslab*L*Rs
@@ -1310,6 +1311,8 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
     TRYB(dev_alloc(h, &h->wall_in, (size_t)nbf));
     TRYB(dev_alloc(h, &A.wall_diag, (size_t)nbf * 12));
     TRYB(dev_alloc(h, &h->d_co, 2 + 2 * COURANT_BLOCKS));
+    TRYB(dev_alloc(h, &h->d_conv_old, (size_t)5 * nc));
+    TRYB(dev_alloc(h, &h->d_conv, 6 + 6 * COURANT_BLOCKS));
     TRYB(dev_alloc(h, &h->d_bstage, (size_t)5 * nbf));
     A.wall_cin = h->wall_cin; A.wall_in = h->wall_in;
     A.gam_old_g = h->gam_a_g; A.gam_old_h = h->gam_a_h; A.gam_new_g = h->gam_b_g; A.gam_new_h = h->gam_b_h;
@@ -1437,6 +1440,9 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
     }
 
     TRYB(h->hasH ? init_state<true>(h) : init_state<false>(h));
+    // Told = T; rhoOld = rho; Uold = U (createFields.H:80-82)
+    k_convergence_init<<<(nc + 255) / 256, 256, 0, h->stream>>>(h->A, h->d_conv_old);
+    TRYB(check_launch(h, "k_convergence_init"));
     CUDAB(cudaStreamSynchronize(h->stream));
     CUDAB(cudaGetLastError());
 #undef TRYB
@@ -1588,6 +1594,24 @@ extern "C" int dugks_courant(dugks_handle_t* h, double dt, double* maxCo, double
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     if (maxCo) *maxCo = out[0] * dt;
     if (meanCo) *meanCo = out[1] / h->nif * dt;
+    return 0;
+}
+
+extern "C" int dugks_convergence(dugks_handle_t* h, double change[3]) {
+    if (!h || !change) return DUGKS_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int nblk = std::max(1, std::min(COURANT_BLOCKS, (h->nc + 255) / 256));
+    k_convergence<<<nblk, 256, 0, h->stream>>>(h->A, h->d_conv_old, h->d_conv + 6);
+    int rc = check_launch(h, "k_convergence");
+    if (rc) return rc;
+    k_convergence_fold<<<1, 32, 0, h->stream>>>(h->d_conv + 6, nblk, h->d_conv);
+    if ((rc = check_launch(h, "k_convergence_fold"))) return rc;
+    double out[6];
+    CUDA_TRY(h, cudaMemcpyAsync(out, h->d_conv, sizeof out, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    change[0] = out[0] / out[1];   // dugksFoam.C:97
+    change[1] = out[2] / out[3];   // :98
+    change[2] = out[4] / out[5];   // :99
     return 0;
 }
 

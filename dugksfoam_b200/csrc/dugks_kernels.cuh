@@ -1059,6 +1059,50 @@ __global__ void k_courant_fold(const double* part, int nblocks, double* out) {
     out[0] = mx; out[1] = sm;
 }
 
+// Convergence monitor (dugksFoam.C:88-107): per block the six sums over a fixed set of cells
+// { |T - Told|, T, |rho - rhoOld|, rho, |U - Uold|, |U| } -> part[6 * blockIdx.x ..], and the snapshot
+// old[c] = { rho, Ux, Uy, Uz, T } is replaced by the current macros in the same pass.  k_convergence_fold
+// adds the partials in index order (deterministic).
+__global__ void k_convergence(StepArgs a, double* old, double* part) {
+    __shared__ double sh[6][32];
+    double s[6] = {0, 0, 0, 0, 0, 0};
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < a.m.nc; c += gridDim.x * blockDim.x) {
+        const double* mc = a.cmac + (size_t)c * MAC_N;     // rho, U(3), T, tau, q(3)
+        double* o = old + (size_t)c * 5;
+        const double rho = mc[0], ux = mc[1], uy = mc[2], uz = mc[3], T = mc[4];
+        const double dx = ux - o[1], dy = uy - o[2], dz = uz - o[3];
+        s[0] += fabs(T - o[4]); s[1] += T;
+        s[2] += fabs(rho - o[0]); s[3] += rho;
+        s[4] += sqrt(dx * dx + dy * dy + dz * dz); s[5] += sqrt(ux * ux + uy * uy + uz * uz);
+        o[0] = rho; o[1] = ux; o[2] = uy; o[3] = uz; o[4] = T;
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        for (int off = 16; off > 0; off >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], off);
+        if (lane == 0) sh[k][w] = s[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double t = 0.0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); k++) t += sh[threadIdx.x][k];
+        part[6 * blockIdx.x + threadIdx.x] = t;
+    }
+}
+__global__ void k_convergence_fold(const double* part, int nblocks, double* out) {
+    if (blockIdx.x != 0 || threadIdx.x >= 6) return;
+    double t = 0.0;
+    for (int k = 0; k < nblocks; k++) t += part[6 * k + threadIdx.x];
+    out[threadIdx.x] = t;
+}
+__global__ void k_convergence_init(StepArgs a, double* old) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.m.nc) return;
+    const double* mc = a.cmac + (size_t)c * MAC_N;
+    double* o = old + (size_t)c * 5;
+    o[0] = mc[0]; o[1] = mc[1]; o[2] = mc[2]; o[3] = mc[3]; o[4] = mc[4];
+}
+
 // dugks_set_boundary_macros: scatter the caller's boundary fields (any may be null) into bmac
 __global__ void k_set_bmac(StepArgs a, const double* rho_b, const double* U_b, const double* T_b) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;

@@ -79,6 +79,11 @@ int main(int argc, char** argv) {
             if (step == nSteps - 1 || step % 10 == 0)
                 std::printf("step %d  deltaT = %.9e  Courant max %.6f mean %.6f\n", step + 1, dt, maxCoNum, meanCoNum);
         }
+        {   // dugksFoam.C:88-107 (one check over the whole run)
+            double dT = 0, dRho = 0, dU = 0;
+            dvm.convergence(dT, dRho, dU);
+            std::printf("Temperature changes = %.6e\nDensity     changes = %.6e\nVelocity    changes = %.6e\n", dT, dRho, dU);
+        }
         std::ofstream o(argv[4], std::ios::binary);
         auto put = [&](const std::vector<double>& v) { o.write((const char*)v.data(), (std::streamsize)(v.size() * 8)); };
         put(dvm.rhoVol()); put(dvm.Uvol()); put(dvm.Tvol()); put(dvm.qVol());

@@ -61,6 +61,12 @@ class fvDVM {
     void getCoNum(double dt, double& maxCoNum, double& meanCoNum) {
         check(dugks_courant(h_, dt, &maxCoNum, &meanCoNum), "fvDVM::getCoNum");
     }
+    // convergence monitor of the time loop (dugksFoam.C:88-107) since the previous call, evaluated on the device
+    void convergence(double& TemperatureChange, double& rhoChange, double& Uchange) {
+        double c[3];
+        check(dugks_convergence(h_, c), "fvDVM::convergence");
+        TemperatureChange = c[0]; rhoChange = c[1]; Uchange = c[2];
+    }
     // fvDVM.H:309-322 (cells) and :324-338 (faces: internal then boundary)
     const std::vector<double>& rhoVol() { sync(); return rho_; }
     const std::vector<double>& Uvol() { sync(); return U_; }

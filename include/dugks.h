@@ -245,6 +245,15 @@ int dugks_get_wall_diag(dugks_handle_t* h, double* qWall, double* stressWall);
 /* fvDVM::getCoNum (fvDVM.C:1111-1119) evaluated on the device. */
 int dugks_courant(dugks_handle_t* h, double dt, double* maxCo, double* meanCo);
 
+/* Convergence monitor of the time loop (dugksFoam.C:88-107, fields of createFields.H:40-82) on the
+ * device: change[0] = gSum(mag(T - Told)) / gSum(T), change[1] = gSum(mag(rho - rhoOld)) / gSum(rho),
+ * change[2] = gSum(mag(U - Uold)) / gSum(mag(U)) over the cells, where the "old" fields are the cell macros
+ * at the previous call (at dugks_create for the first one); then Told = T, rhoOld = rho, Uold = U as in
+ * the reference.  Replaces the D2H of three macro fields per check by one of 24 bytes; the macros are
+ * replicated over ranks, so there is no collective.  A zero denominator gives the IEEE quotient, as in
+ * the reference.  Synchronises. */
+int dugks_convergence(dugks_handle_t* h, double change[3]);
+
 /* gTildeVol/hTildeVol of one cell for all GLOBAL discrete velocities, gathered
  * over ranks (fvDVM::writeDFonCell, fvDVM.C:820-875; every rank must call).
  * g,h: [nXi] each, h_ may be NULL. */

@@ -62,6 +62,7 @@ typedef struct oracle {
     double *inByRho, *outGoing;              /* calculatedMaxwell patch data */
     double *qWall, *stressWall;              /* [nbf][3], [nbf][9] */
     double *part;                            /* scratch for rank partials */
+    double *Told, *rhoOld, *Uold;            /* convergence monitor snapshot, createFields.H:40-82 */
     long steps;
 } oracle_t;
 
@@ -320,6 +321,13 @@ oracle_t *oracle_create(const dugks_mesh_t *m, const dugks_patch_t *patches, int
     }
     for (int b = 0; b < nbf; b++)
         for (int d = 0; d < 3; d++) o->US[3 * (nif + b) + d] = o->U_b[3 * b + d];
+    /* Told = T; rhoOld = rho; Uold = U, createFields.H:80-82 */
+    o->Told = (double *)malloc(sizeof(double) * nc);
+    o->rhoOld = (double *)malloc(sizeof(double) * nc);
+    o->Uold = (double *)malloc(sizeof(double) * 3 * nc);
+    memcpy(o->Told, o->T, sizeof(double) * nc);
+    memcpy(o->rhoOld, o->rho, sizeof(double) * nc);
+    memcpy(o->Uold, o->U, sizeof(double) * 3 * nc);
     return o;
 }
 
@@ -330,7 +338,7 @@ void oracle_destroy(oracle_t *o) {
                     o->gTilde, o->hTilde, o->gBarP, o->hBarP, o->gSurf, o->hSurf, o->gGrad, o->hGrad,
                     o->gamG, o->gamH, o->rho, o->U, o->T, o->q, o->tau, o->rhoS, o->US, o->TS, o->qS,
                     o->tauS, o->rho_b, o->U_b, o->T_b, o->inByRho, o->outGoing, o->qWall,
-                    o->stressWall, o->part};
+                    o->stressWall, o->part, o->Told, o->rhoOld, o->Uold};
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) free(ptrs[i]);
     free(o);
 }
@@ -769,6 +777,29 @@ void oracle_courant(const oracle_t *o, double dt, double *maxCo, double *meanCo)
     }
     *maxCo = mx * dt;
     *meanCo = sum / o->nif * dt;
+}
+
+/* Convergence monitor of the time loop, dugksFoam.C:88-107: relative change of T, rho and U since the
+ * previous check (gSum(mag(T - Told)) / gSum(T), ..., gSum(mag(U - Uold)) / gSum(mag(U))), then
+ * Told = T; rhoOld = rho; Uold = U.  out = {TemperatureChange, rhoChange, Uchange}. */
+void oracle_convergence(oracle_t *o, double *out) {
+    double dT = 0, sT = 0, dR = 0, sR = 0, dU = 0, sU = 0;
+    for (int c = 0; c < o->nc; c++) {
+        dT += fabs(o->T[c] - o->Told[c]);
+        sT += o->T[c];
+        dR += fabs(o->rho[c] - o->rhoOld[c]);
+        sR += o->rho[c];
+        const double *u = o->U + 3 * c, *v = o->Uold + 3 * c;
+        double d[3] = {u[0] - v[0], u[1] - v[1], u[2] - v[2]};
+        dU += sqrt(dot3(d, d));
+        sU += sqrt(dot3(u, u));
+    }
+    out[0] = dT / sT;
+    out[1] = dR / sR;
+    out[2] = dU / sU;
+    memcpy(o->Told, o->T, sizeof(double) * o->nc);
+    memcpy(o->rhoOld, o->rho, sizeof(double) * o->nc);
+    memcpy(o->Uold, o->U, sizeof(double) * 3 * o->nc);
 }
 
 /* ---- accessors ---------------------------------------------------------- */

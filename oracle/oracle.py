@@ -41,6 +41,7 @@ def lib():
         L.oracle_destroy.argtypes = [C.c_void_p]
         L.oracle_step.argtypes = [C.c_void_p, C.c_double]
         L.oracle_courant.argtypes = [C.c_void_p, C.c_double, c_double_p, c_double_p]
+        L.oracle_convergence.argtypes = [C.c_void_p, c_double_p]
         L.oracle_nxi.argtypes = [C.c_void_p]
         L.oracle_nxi.restype = C.c_int
         for name, n in (("oracle_get_cell_macros", 5), ("oracle_get_face_macros", 5),
@@ -86,6 +87,12 @@ class Oracle:
         a, b = C.c_double(), C.c_double()
         lib().oracle_courant(self.h, dt, C.byref(a), C.byref(b))
         return a.value, b.value
+
+    def convergence(self):
+        """(TemperatureChange, rhoChange, Uchange) since the previous call (dugksFoam.C:88-107); first call: since create."""
+        out = np.empty(3)
+        lib().oracle_convergence(self.h, dptr(out))
+        return tuple(float(v) for v in out)
 
     def cell_macros(self):
         nc = self.nc

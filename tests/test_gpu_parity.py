@@ -128,6 +128,7 @@ def test_every_kernel_path(oracle_lib, monkeypatch, path, env):
            # more cells than resident warps (148 SMs x 12): persistent warps carry state from cell to cell
            ("cavity3d_20_gh8", cs.cavity3d_case(20, 8, perturb=0.01), False),
            ("cavity2d_48_gh28", cs.cavity2d_case(48, 28, perturb=0.01), False),
+           ("cavity3d_10_gh8_storeh", cs.cavity3d_case(10, 8, perturb=0.01), True),   # axis-only launch, 6 faces, with h
            ("cavity2d_9_nc9_ties", cs.cavity2d_case(9, 9, quad="NC", perturb=0.01), False),
            ("tri_8_gh8", cs.tri_cavity_case(8, 8, perturb=0.01), False),
            ("cavity3d_4_gh8_storeh", cs.cavity3d_case(4, 8, perturb=0.01), True)]
@@ -162,6 +163,31 @@ def test_thousand_steps(oracle_lib):
     assert util.rel_err(a["T"], b["T"]) <= util.TOL_LONG
     assert util.rel_err(a["U"], b["U"], np.abs(b["U"]).max()) <= util.TOL_LONG
     assert util.rel_err(a["q"], b["q"], np.abs(b["q"]).max()) <= util.TOL_LONG
+    dv.close(); orc.close()
+
+
+def test_convergence_monitor(oracle_lib):
+    """dugks_convergence (dugksFoam.C:88-107 on the device) against the oracle: change since create, change
+    between two checks, and zero right after a check."""
+    case = cs.cavity3d_case(6, 8, perturb=0.01)
+    dv = capi.fvDVM(case)
+    orc = oracle_lib.Oracle(case)
+    dt = case.courant_dt(0.5)
+    sc = util.macro_scales(case)
+    done = 0
+    for nsteps in (2, 3):
+        for _ in range(nsteps):
+            dv.evolution(dt)
+            orc.step(dt)
+        done += nsteps
+        got, want = dv.convergence(), orc.convergence()
+        assert all(w > 0 for w in want)
+        # the fields agree to TOL_STEP * steps of their scale; a sum of |differences| over a sum inherits twice that
+        m = orc.cell_macros()
+        den = (m["T"].sum(), m["rho"].sum(), np.linalg.norm(m["U"], axis=1).sum())
+        for g, w, scale, d in zip(got, want, (sc["T"], sc["rho"], sc["U"]), den):
+            assert abs(g - w) <= 2 * util.TOL_STEP * done * scale * case.nCells / d + 1e-13 * abs(w), (got, want)
+    assert dv.convergence() == (0.0, 0.0, 0.0)
     dv.close(); orc.close()
 
 

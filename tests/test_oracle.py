@@ -203,3 +203,22 @@ def test_courant_number(oracle_lib):
     mx, mean = o.courant(dt)
     assert abs(mx - 0.8) < 1e-12 and abs(mean - 0.8) < 1e-12          # uniform mesh, U = 0
     o.close()
+
+
+def test_convergence_monitor(oracle_lib):
+    """dugksFoam.C:88-107: relative change of T, rho, U since the previous check; Told = T etc. afterwards."""
+    case = cs.cavity2d_case(8, 8, perturb=0.01)
+    orc = oracle_lib.Oracle(case)
+    m0 = orc.cell_macros()
+    dt = case.courant_dt(0.5)
+    for _ in range(3):
+        orc.step(dt)
+    m1 = orc.cell_macros()
+    got = orc.convergence()
+    want = (np.abs(m1["T"] - m0["T"]).sum() / m1["T"].sum(),
+            np.abs(m1["rho"] - m0["rho"]).sum() / m1["rho"].sum(),
+            np.linalg.norm(m1["U"] - m0["U"], axis=1).sum() / np.linalg.norm(m1["U"], axis=1).sum())
+    assert np.allclose(got, want, rtol=1e-12, atol=0)
+    assert all(v > 0 for v in got)
+    assert orc.convergence() == (0.0, 0.0, 0.0)      # the snapshot was replaced by the current fields
+    orc.close()
