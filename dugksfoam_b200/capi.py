@@ -30,7 +30,7 @@ EXPORTS = ["dugks_abi_version", "dugks_nccl_unique_id", "dugks_create", "dugks_d
            "dugks_get_face_macros", "dugks_get_boundary_macros", "dugks_get_wall_diag", "dugks_courant",
            "dugks_get_df", "dugks_get_state", "dugks_set_state", "dugks_local_dvs", "dugks_sizes",
            "dugks_get_stats", "dugks_stream", "dugks_kernel_timing", "dugks_partition",
-           "dugks_get_boundary_df", "dugks_row_layout", "dugks_convergence"]
+           "dugks_get_boundary_df", "dugks_row_layout", "dugks_convergence", "dugks_cell_order"]
 
 
 class DugksError(RuntimeError):
@@ -89,6 +89,7 @@ def load_library():
     L.dugks_partition.argtypes = [C.c_int32] * 4 + [c_int32_p, c_int32_p]
     L.dugks_get_boundary_df.argtypes = [C.c_void_p, c_double_p, c_double_p]
     L.dugks_row_layout.argtypes = [C.c_int32] * 4 + [c_int32_p] * 8
+    L.dugks_cell_order.argtypes = [C.c_int32, C.c_int32, c_double_p, C.POINTER(C.c_uint8), C.c_char_p, C.c_int32, c_int32_p]
     _LIB = L
     return L
 
@@ -119,6 +120,23 @@ def row_layout(nXiPerDim: int, nSolutionD: int, nRanks: int, rank: int) -> dict:
     L.dugks_row_layout(nXiPerDim, nSolutionD, nRanks, rank, C.byref(nch), C.byref(ll), C.byref(lt), C.byref(cap),
                        *[iptr(a) for a in arr])
     return dict(nch=nch.value, L=ll.value, Lt=lt.value, iy=arr[0], iz=arr[1], first=arr[2], len=arr[3])
+
+
+def cell_order(centres: np.ndarray, nSolutionD: int, kind: str = "tiled", nWarps: int = 1776,
+               first_class: Optional[np.ndarray] = None) -> np.ndarray:
+    """Traversal order of the cell kernels (host-only, needs no device): see dugks_cell_order."""
+    L = load_library()
+    Cc = np.ascontiguousarray(centres, dtype=np.float64)
+    n = Cc.shape[0]
+    out = np.empty(n, dtype=np.int32)
+    fc = None
+    if first_class is not None:
+        fc = np.ascontiguousarray(first_class, dtype=np.uint8)
+    rc = L.dugks_cell_order(n, nSolutionD, dptr(Cc), None if fc is None else fc.ctypes.data_as(C.POINTER(C.c_uint8)),
+                            kind.encode(), nWarps, iptr(out))
+    if rc:
+        raise DugksError(f"dugks_cell_order failed ({rc}): {L.dugks_last_error(None).decode()}")
+    return out
 
 
 def nccl_unique_id() -> bytes:

@@ -757,6 +757,112 @@ extern "C" int dugks_row_layout(int32_t nXiPerDim, int32_t nSolutionD, int32_t n
     return 0;
 }
 
+// ------------------------------------------------------------------------------
+// Traversal order of the cell kernels: a permutation of the cells, computed from the cell centres, so it
+// applies to unstructured meshes as well.  Persistent warps take items w, w + nWarps, w + 2 nWarps, ...
+//   tiled (default): strips of T rows in y, swept layer by layer in z, x fastest inside a row: the +-z
+//     neighbours of a cell are nx*T cells apart instead of nx*ny (64^3: 512 instead of 4096), so that every
+//     neighbour block is touched again within about one wave of warps; the rows on strip borders (2 in T)
+//     are fetched twice.
+//   wave: lines of cells along x are dealt to the warps in flight, nWarps lines at a time, and the order
+//     runs through all of them x position by x position: at any time the warps work on one y-z patch of
+//     cells at the SAME x, so that the y/z neighbours of a cell are in flight together with it and its x
+//     neighbours are the previous / next cell of the same warp (reuse window of a row block: about one cell
+//     time instead of one to two waves).  Opt-in until measured.
+//   morton, natural: for comparison.
+// first != nullptr: cells with first[c] != 0 come first (the axis-only launch takes them as one item range);
+// the pattern is built inside that class, the other cells follow in tiled order.
+static void build_cell_order(int nc, int D, const double* C, const unsigned char* first, const std::string& ord,
+                             int tile, int nwarps, std::vector<int>& order) {
+    order.resize(nc);
+    for (int c = 0; c < nc; c++) order[c] = c;
+    if (nc > 1 && ord != "natural") {
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        for (int c = 0; c < nc; c++)
+            for (int d = 0; d < 3; d++) {
+                lo[d] = std::min(lo[d], C[(size_t)c * 3 + d]);
+                hi[d] = std::max(hi[d], C[(size_t)c * 3 + d]);
+            }
+        std::vector<unsigned long long> key(nc);
+        // cells per direction if the mesh were a uniform block
+        const int n1 = std::max(1, (int)std::lround(std::pow((double)nc, 1.0 / std::max(D, 1))));
+        auto quant = [&](int c, int d) -> unsigned long long {
+            const double w = hi[d] - lo[d];
+            if (!(w > 0)) return 0ull;
+            // centres of a uniform block sit at (i + 0.5) / n1 of the centre-to-centre extent + half a cell
+            const double t = (C[(size_t)c * 3 + d] - lo[d]) / w * (n1 - 1) + 0.5;
+            return (unsigned long long)std::min<double>(n1 - 1, std::max(0.0, std::floor(t)));
+        };
+        if (ord == "morton") {
+            auto spread = [](unsigned v) {   // 10 bits -> every third bit
+                unsigned long long x = v & 0x3ff;
+                x = (x | (x << 16)) & 0x30000ffull;
+                x = (x | (x << 8)) & 0x300f00full;
+                x = (x | (x << 4)) & 0x30c30c3ull;
+                x = (x | (x << 2)) & 0x9249249ull;
+                return x;
+            };
+            for (int c = 0; c < nc; c++) {
+                unsigned long long k = 0;
+                for (int d = 0; d < 3; d++) {
+                    const double w = hi[d] - lo[d];
+                    unsigned q = w > 0 ? (unsigned)std::min(1023.0, (C[(size_t)c * 3 + d] - lo[d]) / w * 1024.0) : 0u;
+                    k |= spread(q) << d;
+                }
+                key[c] = k;
+            }
+        } else {
+            // strip height for ~512 cells per layer
+            const int T = tile > 0 ? tile : std::max(1, 512 / n1);
+            for (int c = 0; c < nc; c++) {
+                const unsigned long long qx = quant(c, 0), qy = quant(c, 1), qz = quant(c, 2);
+                key[c] = (((qy / T) * n1 + qz) * T + (qy % T)) * n1 + qx;
+            }
+        }
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y2) { return key[x] < key[y2]; });
+        if (ord == "wave" && nwarps > 0) {
+            // the cells the pattern is built over, line by line (z, y), x ascending inside a line
+            std::vector<int> sub;
+            for (int c = 0; c < nc; c++) if (!first || first[c]) sub.push_back(c);
+            std::vector<unsigned long long> line(nc, 0), qxs(nc, 0);
+            for (int c : sub) { line[c] = quant(c, 2) * (unsigned long long)n1 + quant(c, 1); qxs[c] = quant(c, 0); }
+            std::stable_sort(sub.begin(), sub.end(), [&](int x, int y2) {
+                return line[x] != line[y2] ? line[x] < line[y2] : qxs[x] < qxs[y2];
+            });
+            // key = (round of nWarps lines, position inside the line, line inside the round)
+            long long li = -1, pos = 0;
+            unsigned long long prev = ~0ull;
+            for (int c : sub) {
+                if (line[c] != prev) { li++; pos = 0; prev = line[c]; }
+                key[c] = ((unsigned long long)(li / nwarps) << 44) | ((unsigned long long)pos << 22) | (unsigned long long)(li % nwarps);
+                pos++;
+            }
+            std::stable_sort(sub.begin(), sub.end(), [&](int x, int y2) { return key[x] < key[y2]; });
+            if (!first) order = sub;
+            else {
+                // the other cells keep their tiled order, behind the pattern
+                std::vector<int> rest;
+                for (int c : order) if (!first[c]) rest.push_back(c);
+                order = sub;
+                order.insert(order.end(), rest.begin(), rest.end());
+            }
+            return;
+        }
+    }
+    if (first) std::stable_partition(order.begin(), order.end(), [&](int c) { return first[c] != 0; });
+}
+
+// introspection (host only, no device needed): the traversal order dugks_create would use
+extern "C" int dugks_cell_order(int32_t nCells, int32_t nSolutionD, const double* C, const uint8_t* first_class,
+                                const char* kind, int32_t nWarps, int32_t* order) {
+    if (nCells <= 0 || !C || !order || !kind || nWarps <= 0 || nSolutionD < 1 || nSolutionD > 3)
+        return fail(nullptr, DUGKS_ERR_INVALID, "dugks_cell_order: bad argument");
+    std::vector<int> o;
+    build_cell_order(nCells, nSolutionD, C, first_class, kind, 0, nWarps, o);
+    for (int i = 0; i < nCells; i++) order[i] = o[i];
+    return 0;
+}
+
 extern "C" int dugks_abi_version(void) { return DUGKS_ABI_VERSION; }
 
 extern "C" int dugks_partition(int32_t nXiPerDim, int32_t nSolutionD, int32_t nRanks, int32_t rank, int32_t* ids,
@@ -1088,65 +1194,17 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
     {
         unsigned char* d_c = nullptr;
         TRYB(dev_upload(h, &d_c, cell_cls)); A.cell_cls = d_c;
-        // traversal order.  Default "tiled": strips of T rows in y, swept layer by layer in z, x fastest
-        // inside a row: the +-z neighbours of a cell are then nx*T cells apart instead of nx*ny (64^3: 512
-        // instead of 4096, i.e. 3.7 MB of row blocks instead of 29 MB), so that every neighbour block is
-        // still in L2 when it is needed again; only the rows on strip borders (2 in T) are fetched twice.
-        // Computed from the cell centres, so it applies to unstructured meshes as well.
-        // DUGKS_ORDER = tiled | morton | natural.
-        std::vector<int> order(nc);
-        for (int c = 0; c < nc; c++) order[c] = c;
-        const char* ord_env = getenv("DUGKS_ORDER");
-        const std::string ord = ord_env ? ord_env : "tiled";
-        if (ord != "natural" && nc > 1) {
-            double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-            for (int c = 0; c < nc; c++)
-                for (int d = 0; d < 3; d++) {
-                    lo[d] = std::min(lo[d], mesh->C[(size_t)c * 3 + d]);
-                    hi[d] = std::max(hi[d], mesh->C[(size_t)c * 3 + d]);
-                }
-            std::vector<unsigned long long> key(nc);
-            if (ord == "morton") {
-                auto spread = [](unsigned v) {   // 10 bits -> every third bit
-                    unsigned long long x = v & 0x3ff;
-                    x = (x | (x << 16)) & 0x30000ffull;
-                    x = (x | (x << 8)) & 0x300f00full;
-                    x = (x | (x << 4)) & 0x30c30c3ull;
-                    x = (x | (x << 2)) & 0x9249249ull;
-                    return x;
-                };
-                for (int c = 0; c < nc; c++) {
-                    unsigned long long k = 0;
-                    for (int d = 0; d < 3; d++) {
-                        const double w = hi[d] - lo[d];
-                        unsigned q = w > 0 ? (unsigned)std::min(1023.0, (mesh->C[(size_t)c * 3 + d] - lo[d]) / w * 1024.0) : 0u;
-                        k |= spread(q) << d;
-                    }
-                    key[c] = k;
-                }
-            } else {
-                // cells per direction if the mesh were a uniform block; strip height for ~512 cells per layer
-                const int n1 = std::max(1, (int)std::lround(std::pow((double)nc, 1.0 / D)));
-                int T = std::max(1, 512 / n1);
-                if (const char* e = getenv("DUGKS_TILE")) T = std::max(1, atoi(e));
-                auto quant = [&](int c, int d) -> unsigned long long {
-                    const double w = hi[d] - lo[d];
-                    if (!(w > 0)) return 0ull;
-                    // centres of a uniform block sit at (i + 0.5) / n1 of the centre-to-centre extent + half a cell
-                    const double t = (mesh->C[(size_t)c * 3 + d] - lo[d]) / w * (n1 - 1) + 0.5;
-                    return (unsigned long long)std::min<double>(n1 - 1, std::max(0.0, std::floor(t)));
-                };
-                for (int c = 0; c < nc; c++) {
-                    const unsigned long long qx = quant(c, 0), qy = quant(c, 1), qz = quant(c, 2);
-                    key[c] = (((qy / T) * n1 + qz) * T + (qy % T)) * n1 + qx;
-                }
-            }
-            std::stable_sort(order.begin(), order.end(), [&](int x, int y2) { return key[x] < key[y2]; });
-        }
-        // split launches (DUGKS_SPLIT_AXIS): axis-aligned cells first, the others after them
+        // traversal order of the cell kernels (build_cell_order): DUGKS_ORDER = tiled (default) | wave | morton | natural
         h->want_split = 2 * (long long)h->n_axis > nc && getenv("DUGKS_NO_SPLIT_AXIS") == nullptr;
-        if (h->want_split)
-            std::stable_partition(order.begin(), order.end(), [&](int c) { return cell_cls[c] != 0; });
+        const char* ord_env = getenv("DUGKS_ORDER");
+        int dev_sms = 148;
+        cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->device);
+        int nwarps = dev_sms * 3 * HOT_WARPS;   // warps in flight of the 3-CTAs/SM kernels (phase 1 axis-only, relax+update)
+        if (const char* e = getenv("DUGKS_WAVE")) nwarps = std::max(1, atoi(e));
+        int tile = 0;
+        if (const char* e = getenv("DUGKS_TILE")) tile = std::max(1, atoi(e));
+        std::vector<int> order;
+        build_cell_order(nc, D, mesh->C, h->want_split ? cell_cls.data() : nullptr, ord_env ? ord_env : "tiled", tile, nwarps, order);
         // per-cell record (CMETA_N ints) in traversal order: everything a warp needs to start a cell in one load level
         std::vector<int> cmeta((size_t)nc * CMETA_N, 0);
         for (int item = 0; item < nc; item++) {

@@ -281,6 +281,15 @@ int dugks_row_layout(int32_t nXiPerDim, int32_t nSolutionD, int32_t nRanks, int3
                      int32_t* nch, int32_t* L, int32_t* Lt, int32_t* nRows,
                      int32_t* row_iy, int32_t* row_iz, int32_t* row_first, int32_t* row_len);
 
+/* Host-only (no device needed): the order in which the cell kernels walk the mesh, a
+ * permutation of the cells computed from the cell centres C [nCells][3].  kind: "tiled" (what dugks_create
+ * uses unless DUGKS_ORDER says otherwise), "wave", "morton" or "natural"; nWarps: persistent warps in flight
+ * (only "wave" uses it); first_class (may be NULL): cells with a non-zero entry come first, as the axis-only
+ * launch of phase 1 needs them.  The reference walks cells in label order (discreteVelocity.C:346-410 and the
+ * face loops :491-530, :948-956); any order gives the same result. */
+int dugks_cell_order(int32_t nCells, int32_t nSolutionD, const double* C, const uint8_t* first_class,
+                     const char* kind, int32_t nWarps, int32_t* order);
+
 /* Boundary-face values gSurf/hSurf of the local DVs on all boundary faces,
  * g[j*nBoundaryFaces + b] for local DV j (DVi(j).gSurf().boundaryField(),
  * discreteVelocity.H:230-239).  Either pointer may be NULL. */

@@ -4,6 +4,7 @@ import ctypes
 import os
 import re
 
+import numpy as np
 import pytest
 
 from dugksfoam_b200 import capi
@@ -93,3 +94,33 @@ def test_row_layout_covers_every_velocity_once():
     # the case that motivated the tail slab: 28^3 over 8 ranks = 98 rows = 3 slabs + 2 rows -> short rows of 2
     lay = capi.row_layout(28, 3, 8, 0)
     assert lay["L"] == 28 and lay["Lt"] == 2 and len(lay["iy"]) == 96 + 28
+
+
+def test_cell_order_is_a_permutation_with_the_promised_structure():
+    """dugks_cell_order (host only): every kind is a permutation; the first class comes first; the wave
+    order runs through nWarps lines of cells x position by x position."""
+    nx, ny, nz = 12, 10, 8
+    iz, iy, ix = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    centres = np.stack([(ix.ravel() + 0.5) / nx, (iy.ravel() + 0.5) / ny * 0.9, (iz.ravel() + 0.5) / nz * 0.7], axis=1)
+    n = nx * ny * nz
+    interior = ((ix > 0) & (ix < nx - 1) & (iy > 0) & (iy < ny - 1) & (iz > 0) & (iz < nz - 1)).ravel().astype(np.uint8)
+    for kind in ("tiled", "wave", "morton", "natural"):
+        for first in (None, interior):
+            o = capi.cell_order(centres, 3, kind, nWarps=16, first_class=first)
+            assert np.array_equal(np.sort(o), np.arange(n)), kind
+            if first is not None:
+                k = int(interior.sum())
+                assert interior[o[:k]].all() and not interior[o[k:]].any(), kind
+    assert np.array_equal(capi.cell_order(centres, 3, "natural"), np.arange(n))
+    # wave, whole mesh, 16 warps: ny * nz = 80 lines = 5 rounds of 16; inside a round the items
+    # [s * 16, (s + 1) * 16) are the 16 lines' cells at x position s, line by line
+    o = capi.cell_order(centres, 3, "wave", nWarps=16)
+    X, Y, Z = ix.ravel()[o], iy.ravel()[o], iz.ravel()[o]
+    for r in range(5):
+        blk = slice(r * 16 * nx, (r + 1) * 16 * nx)
+        xs = X[blk].reshape(nx, 16)
+        assert (xs == np.arange(nx)[:, None]).all()
+        lines = (Z[blk] * ny + Y[blk]).reshape(nx, 16)
+        assert (lines == lines[0]).all() and len(set(lines[0])) == 16
+    # a warp (item w, w + 16, ...) walks ONE line along x
+    assert len(set((Z * ny + Y)[3:16 * nx:16])) == 1

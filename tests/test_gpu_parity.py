@@ -107,6 +107,8 @@ _PATHS = [
     ("no_split", {"DUGKS_NO_SPLIT_AXIS": "1"}),         # axis-aligned cells inside the unified phase-1 launch
     ("no_wmode", {"DUGKS_NO_WMODE": "1"}),              # face-storage slabs with persistent gBarP (update reads gTilde, gBarP)
     ("no_wmode_keep_one", {"DUGKS_NO_WMODE": "1", "DUGKS_KEEP_SLABS": "1"}),
+    ("order_wave", {"DUGKS_ORDER": "wave"}),            # x-wavefront traversal (opt-in, dugks_cell_order)
+    ("order_natural", {"DUGKS_ORDER": "natural"}),
     ("gen1_tma", {"DUGKS_NO_HOT": "1"}),                # first-generation bulk-copy kernels
     ("gen1_ldg", {"DUGKS_NO_HOT": "1", "DUGKS_NO_TMA": "1"}),
     ("generic", {"DUGKS_NO_HOT": "1", "DUGKS_FORCE_GENERIC": "1"}),   # cells with many faces
@@ -117,7 +119,7 @@ _PATHS = [
 def test_every_kernel_path(oracle_lib, monkeypatch, path, env):
     """Every device code path that can carry the step gives the oracle's answer."""
     for k in ("DUGKS_KEEP_SLABS", "DUGKS_NO_HOT", "DUGKS_NO_TMA", "DUGKS_FORCE_GENERIC", "DUGKS_NO_AXIS",
-              "DUGKS_NO_SPLIT_AXIS", "DUGKS_NO_WMODE"):
+              "DUGKS_NO_SPLIT_AXIS", "DUGKS_NO_WMODE", "DUGKS_ORDER"):
         monkeypatch.delenv(k, raising=False)
     for k, v in env.items():
         monkeypatch.setenv(k, v)
