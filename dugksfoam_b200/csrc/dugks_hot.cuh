@@ -620,16 +620,6 @@ __device__ __forceinline__ void hot_out_item(const StepArgs& a, const HotCtx& x,
     }
 }
 
-// One axis-aligned interior cell of PHASE 1 in the axis-only launch (SEL = 1).  Same arithmetic, in the
-// same order, as hot_out_item<1, ..., AXIS = true> (bit-identical face values and moment sums), built
-// around what the static upwind sets of such a cell look like:
-//   * x faces (entries 0, 1): xi.Sf = xi_x * Sx, the same for every lane -> warp-uniform per point;
-//   * y / z faces (entries 2.., in pairs): xi.Sf = xi_y * Sy (xi_z * Sz) does not depend on the point, so a
-//     lane is upwind of exactly ONE face of a pair for the whole row.  The lane reconstructs only that
-//     face (one face offset, one store address and ONE set of moment accumulators per pair, selected once
-//     per cell) and the two faces' moments are separated at the end by masking lanes.
-// Needs: no tie (|xi.Sf| < VSMALL) on a y / z face of an axis-aligned cell for any row of the slab
-// (k_build_upwind reports that per slab; such slabs take the unified launch) and rows that are whole chunks.
 // Moments of two faces in one pass through shared memory.  Every lane brings raw accumulators for face A
 // and face B (zeros where it takes no part); 2 x NV columns, row stride 2 NV + 1 doubles (odd: no bank
 // conflicts), every lane sums half a column (16 rows) per round of 16 columns.  red: 32 x (2 NV + 1) doubles.
@@ -675,6 +665,16 @@ __device__ __forceinline__ void hot_reduce_faces2(const StepArgs& a, const HotCt
     __syncwarp();
 }
 
+// One axis-aligned interior cell of PHASE 1 in the axis-only launch (SEL = 1).  Same arithmetic, in the
+// same order, as hot_out_item<1, ..., AXIS = true> (bit-identical face values and moment sums), built
+// around what the static upwind sets of such a cell look like:
+//   * x faces (entries 0, 1): xi.Sf = xi_x * Sx, the same for every lane -> warp-uniform per point;
+//   * y / z faces (entries 2.., in pairs): xi.Sf = xi_y * Sy (xi_z * Sz) does not depend on the point, so a
+//     lane is upwind of exactly ONE face of a pair for the whole row.  The lane reconstructs only that
+//     face (one face offset, one store address and ONE set of moment accumulators per pair, selected once
+//     per cell) and the two faces' moments are separated at the end by masking lanes.
+// Needs: no tie (|xi.Sf| < VSMALL) on a y / z face of an axis-aligned cell for any row of the slab
+// (k_build_upwind reports that per slab; such slabs take the unified launch) and rows that are whole CU-point groups.
 // CI: points per staged chunk (copy granularity, kernel template parameter); CU: points advanced together
 // (2 keeps the function at 3 CTAs/SM; a 4-point stage doubles the bytes in flight per warp and halves the
 // per-chunk bookkeeping).
