@@ -261,7 +261,10 @@ int dugks_get_df(dugks_handle_t* h, int32_t cell, double* g, double* h_);
 
 /* The rank-local slice of the full state, DV-major like the reference's
  * PtrList<discreteVelocity>: g[i*nCells + c] for local DV i.  For parity
- * tests and lossless checkpoints.  Either pointer may be NULL. */
+ * tests and checkpoints that keep the distribution functions (the reference's
+ * restart drops them, discreteVelocity.C:220-249).  A bit-exact resume would also
+ * need the lagged boundary gradient, the wall densities and q/tau of the cells,
+ * which these two calls do not carry yet.  Either pointer may be NULL. */
 int dugks_get_state(dugks_handle_t* h, double* g, double* h_);
 int dugks_set_state(dugks_handle_t* h, const double* g, const double* h_);
 
