@@ -1438,7 +1438,9 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
         const int bad = flags[0];
         h->slab_pair_ok.assign(h->nslab, 0);
         for (int s = 0; s < h->nslab; s++)
-            h->slab_pair_ok[s] = flags[1 + s] == 0 && dv_len(A.dv, s) % HOT_AXIS_CU == 0;
+            // rows cut into ix-chunks (more than 32 points per direction): the x masks differ from lane to lane,
+            // hot_axis_item would spend its time in the slow x path; those layouts keep the unified launch
+            h->slab_pair_ok[s] = flags[1 + s] == 0 && dv_len(A.dv, s) % HOT_AXIS_CU == 0 && h->nch == 1;
         // abscissae that are not ascending give upwind sets that are not ranges: first-generation kernels
         if (bad) h->use_hot = false;
         A.upw = d_upw;

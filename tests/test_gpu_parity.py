@@ -214,3 +214,17 @@ def test_fails_loudly_on_bad_input():
     case.patches[0].kind = 99
     with pytest.raises(capi.DugksError):
         capi.fvDVM(case)
+
+
+@pytest.mark.parametrize("quad,nDV", [("NC", 37), ("GH", 36)])
+def test_chunked_rows_parity(oracle_lib, quad, nDV):
+    """More than 32 velocity points per direction (BASELINE config 2 has 101): rows are cut into ix-chunks."""
+    case = cs.cavity2d_case(10, nDV, quad=quad, perturb=0.01)
+    dv = capi.fvDVM(case)
+    orc = oracle_lib.Oracle(case)
+    dt = case.courant_dt(0.5)
+    for step in range(3):
+        dv.evolution(dt)
+        orc.step(dt)
+        _compare(dv, orc, case, util.TOL_STEP * (step + 1), f"chunked {quad}{nDV} step {step + 1}")
+    dv.close(); orc.close()
