@@ -216,6 +216,8 @@ def test_fails_loudly_on_bad_input():
         capi.fvDVM(case)
 
 
+@pytest.mark.xfail(strict=False, reason="written after this round's GPU budget was spent: not yet run on a device "
+                                        "(XPASS = parity holds for chunked rows; remove the mark then)")
 @pytest.mark.parametrize("quad,nDV", [("NC", 37), ("GH", 36)])
 def test_chunked_rows_parity(oracle_lib, quad, nDV):
     """More than 32 velocity points per direction (BASELINE config 2 has 101): rows are cut into ix-chunks."""
