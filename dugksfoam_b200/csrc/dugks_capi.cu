@@ -334,7 +334,7 @@ static int hot_configure(dugks_handle* h) {
     int occ_axis = 1;
     h->split_axis = false;
     if (e == cudaSuccess && (h->hot_ne == 4 || h->hot_ne == 6) && h->want_split && h->axis_ne == h->hot_ne) {
-        // axis-aligned cells in their own launch (hot_axis_item, 3 CTAs/SM): 64^3 x 28^3, phase 1 per step 73 -> see DESIGN.md
+        // axis-aligned cells in their own launch (hot_axis_item, 3 CTAs/SM; 64^3 x 28^3: phase 1 2.90 -> 2.13 ms per slab)
         if (h->hot_ne == 4) {
             h->hsmem_axis = HotPlan<1, H, 4, 32, CI_AXIS>::total(ntab);
             e = cudaFuncSetAttribute(k_hot_outgoing<1, H, 4, 32, CI_AXIS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->hsmem_axis);
@@ -1476,16 +1476,12 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
     TRYB(dev_alloc(h, &h->gb_store, gb_blocks * nc * L * h->Rs + HOT_PAD));
     if (h->hasH) TRYB(dev_alloc(h, &h->hb_store, gb_blocks * nc * L * h->Rs + HOT_PAD));
     A.gb = h->gb_store; A.hb = h->hb_store;
-    if (h->use_hot && h->n_big == 0 && nif > 0) {
-        const size_t per_slab = (size_t)nif * L * h->Rs * sizeof(double) * nfld;
-        (void)per_slab;
-        if (h->n_keep > 0) {
-            TRYB(dev_alloc(h, &h->fkeep_g, (size_t)h->n_keep * nif * L * h->Rs + HOT_PAD, false));
-            if (h->hasH) TRYB(dev_alloc(h, &h->fkeep_h, (size_t)h->n_keep * nif * L * h->Rs + HOT_PAD, false));
-            // tie points are written by one side only and padding rows by nobody: start from zeros
-            CUDAB(cudaMemsetAsync(h->fkeep_g, 0, ((size_t)h->n_keep * nif * L * h->Rs + HOT_PAD) * sizeof(double), h->stream));
-            if (h->hasH) CUDAB(cudaMemsetAsync(h->fkeep_h, 0, ((size_t)h->n_keep * nif * L * h->Rs + HOT_PAD) * sizeof(double), h->stream));
-        }
+    if (h->n_keep > 0) {
+        TRYB(dev_alloc(h, &h->fkeep_g, (size_t)h->n_keep * nif * L * h->Rs + HOT_PAD, false));
+        if (h->hasH) TRYB(dev_alloc(h, &h->fkeep_h, (size_t)h->n_keep * nif * L * h->Rs + HOT_PAD, false));
+        // tie points are written by one side only and padding rows by nobody: start from zeros
+        CUDAB(cudaMemsetAsync(h->fkeep_g, 0, ((size_t)h->n_keep * nif * L * h->Rs + HOT_PAD) * sizeof(double), h->stream));
+        if (h->hasH) CUDAB(cudaMemsetAsync(h->fkeep_h, 0, ((size_t)h->n_keep * nif * L * h->Rs + HOT_PAD) * sizeof(double), h->stream));
     }
 
     // ---- collective backend
