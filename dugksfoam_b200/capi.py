@@ -21,8 +21,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DUGKS_LIB", os.path.join(_HERE, "libdugks.so"))   # DUGKS_LIB: A/B builds
 _LIB = None
 
+# 1886: the dynamic shared-memory array is declared with 16- and 128-byte alignment in different kernels of the
+# one translation unit (a warning per instantiation, nothing else)
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-diag-suppress", "1886", "-Xcompiler", "-fPIC", "-shared"]
 
 # every symbol include/dugks.h declares
 EXPORTS = ["dugks_abi_version", "dugks_nccl_unique_id", "dugks_create", "dugks_destroy", "dugks_last_error",
