@@ -767,8 +767,8 @@ extern "C" int dugks_row_layout(int32_t nXiPerDim, int32_t nSolutionD, int32_t n
 //   wave: lines of cells along x are dealt to the warps in flight, nWarps lines at a time, and the order
 //     runs through all of them x position by x position: at any time the warps work on one y-z patch of
 //     cells at the SAME x, so that the y/z neighbours of a cell are in flight together with it and its x
-//     neighbours are the previous / next cell of the same warp (reuse window of a row block: about one cell
-//     time instead of one to two waves).  Opt-in until measured.
+//     neighbours are the previous / next cell of the same warp.  A probe of where the L2 misses of the row
+//     blocks come from; opt-in until measured.
 //   morton, natural: for comparison.
 // first != nullptr: cells with first[c] != 0 come first (the axis-only launch takes them as one item range);
 // the pattern is built inside that class, the other cells follow in tiled order.
