@@ -35,6 +35,8 @@ WORKLOADS = {
     "cavity2d_60_gh28": ("cavity2d", dict(n=60, nDV=28)),            # demo/cavity shape
     "tri2d_316_gh28": ("tri2d", dict(n=316, nDV=28)),                # BASELINE configs[3] shape: ~200k triangles
 }
+CHECK_STEPS = 3          # the checksum is taken after this many steps (W >= 3 always)
+CHECKSUMS = os.path.join(ROOT, "profiles", "bench_checksums.json")
 # bounded CPU sample of the same workload shape (3-D cavity, 28^3 GH velocities, same gas/BCs)
 CPU_SAMPLE = ("cavity3d", dict(n=8, nDV=28))
 
@@ -140,6 +142,7 @@ def main():
     ap.add_argument("--workload", default="cavity3d_64_gh28", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--record-checksum", action="store_true", help="one GPU: store this run's checksums as the reference")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -202,8 +205,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(W):
+    # ---- correctness evidence at every N: checksums of the cell macros after exactly CHECK_STEPS steps from the
+    # initial state (inside the warm-up, outside every timed region).  The velocity sums commute, so the fields do
+    # not depend on how velocity space is split: every N must reproduce the one-GPU values
+    # (profiles/bench_checksums.json, written by a one-GPU run with --record-checksum) to 1e-12.
+    checksum = None
+    for k in range(W):
         dv.evolution(dt)
+        if k + 1 == CHECK_STEPS:
+            cm3 = dv.cell_macros()
+            checksum = {"steps": CHECK_STEPS, "rho_sum": float(cm3["rho"].sum()), "T_sum": float(cm3["T"].sum()),
+                        "U_abs_sum": float(np.abs(cm3["U"]).sum()), "q_abs_sum": float(np.abs(cm3["q"]).sum())}
     dv.sync()
 
     # ---- device-timed region: K steps, state resident in HBM, CUDA events on the library's stream
@@ -256,7 +268,8 @@ def main():
         torch.mul(U0, 1.0 + 1e-9 * (k + 1), out=pin["U"])
         dv.set_boundary_macros(None, pin["U"].numpy(), pin["T"].numpy())
         dv.evolution(dt)
-        cm = dv.cell_macros()
+        if rank == 0:
+            cm = dv.cell_macros()      # the macro fields go to the host where they are written (dugksFoam.C:63,109: rank 0)
         co = dv.getCoNum(dt)
     dv.sync()
     barrier()
@@ -266,7 +279,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_gups = updates_per_step * K / e2e_s / 1e9
-    assert np.isfinite(cm["rho"]).all() and co[0] > 0
+    assert co[0] > 0 and (rank != 0 or np.isfinite(cm["rho"]).all())
 
     if rank != 0:
         dv.close()
@@ -274,6 +287,20 @@ def main():
             dist.destroy_process_group()
         return
 
+    # partition independence: compare with the one-GPU checksums
+    ref_ck, ck_diff = None, None
+    try:
+        ref_ck = json.load(open(CHECKSUMS)).get(args.workload)
+    except Exception:
+        ref_ck = None
+    if args.record_checksum and world == 1 and checksum is not None:
+        allck = json.load(open(CHECKSUMS)) if os.path.exists(CHECKSUMS) else {}
+        allck[args.workload] = checksum
+        json.dump(allck, open(CHECKSUMS, "w"), indent=1, sort_keys=True)
+        ref_ck = checksum
+    if ref_ck is not None and checksum is not None and ref_ck.get("steps") == checksum["steps"]:
+        ck_diff = max(abs(checksum[k] - ref_ck[k]) / abs(ref_ck[k]) for k in ("rho_sum", "T_sum", "U_abs_sum", "q_abs_sum"))
+        assert ck_diff <= 1e-12, f"cell macros after {CHECK_STEPS} steps differ from the one-GPU reference by {ck_diff:.3e}: {checksum} vs {ref_ck}"
     peak, peak_src = peaks()
     balg = b_alg(case, nf)
     achieved = gups / world * balg   # GB/s per GPU (each GPU advances 1/world of the updates) vs one GPU's HBM peak
@@ -313,6 +340,8 @@ def main():
         "e2e": {"value": e2e_gups, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s / K * 1e3},
         "gpu_launches": launches,
+        "checksum": checksum, "checksum_rel_diff": ck_diff,
+        "checksum_reference": "profiles/bench_checksums.json (one-GPU run)" if ref_ck is not None else None,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_unit": "GB of DRAM reads+writes per step (ncu)", "traffic_source": traffic_src,

@@ -32,7 +32,8 @@ EXPORTS = ["dugks_abi_version", "dugks_nccl_unique_id", "dugks_create", "dugks_d
            "dugks_get_face_macros", "dugks_get_boundary_macros", "dugks_get_wall_diag", "dugks_courant",
            "dugks_get_df", "dugks_get_state", "dugks_set_state", "dugks_local_dvs", "dugks_sizes",
            "dugks_get_stats", "dugks_stream", "dugks_kernel_timing", "dugks_partition",
-           "dugks_get_boundary_df", "dugks_row_layout", "dugks_convergence", "dugks_cell_order"]
+           "dugks_get_boundary_df", "dugks_row_layout", "dugks_convergence", "dugks_cell_order",
+           "dugks_checkpoint_size", "dugks_checkpoint_save", "dugks_checkpoint_load"]
 
 
 class DugksError(RuntimeError):
@@ -92,6 +93,9 @@ def load_library():
     L.dugks_get_boundary_df.argtypes = [C.c_void_p, c_double_p, c_double_p]
     L.dugks_row_layout.argtypes = [C.c_int32] * 4 + [c_int32_p] * 8
     L.dugks_cell_order.argtypes = [C.c_int32, C.c_int32, c_double_p, C.POINTER(C.c_uint8), C.c_char_p, C.c_int32, c_int32_p]
+    L.dugks_checkpoint_size.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    L.dugks_checkpoint_save.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    L.dugks_checkpoint_load.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
     _LIB = L
     return L
 
@@ -162,16 +166,16 @@ class fvDVM:
 
     def __init__(self, case: Case, *, rank: int = 0, nranks: int = 1, device: int = -1,
                  nccl_id: Optional[bytes] = None, reduce: Optional[Callable[[int, int, int], int]] = None,
-                 store_h: bool = False, dv_chunk: int = 0):
+                 store_h: bool = False, scratch_bytes: int = 0):
         self.L = load_library()
         self.case = case
         self._m = Marshalled(case)
         self._cb = None
         par = ParT()
         par.rank, par.nRanks, par.device, par.partition = rank, nranks, device, 0
-        par.scratch_bytes = 0
+        par.scratch_bytes = int(scratch_bytes)
         par.store_h = 1 if store_h else 0
-        par.dv_chunk = dv_chunk
+        par.dv_chunk = 0
         if reduce is not None:
             def _cb(user, ptr, n, stream):
                 try:
@@ -297,6 +301,18 @@ class fvDVM:
         g = np.ascontiguousarray(g, dtype=np.float64)
         h = None if h is None else np.ascontiguousarray(h, dtype=np.float64)
         self._chk(self.L.dugks_set_state(self.h, dptr(g), dptr(h)), "dugks_set_state")
+
+    def checkpoint(self) -> np.ndarray:
+        """Everything the next evolution() reads, as one opaque rank-local blob (dugks_checkpoint_save)."""
+        n = C.c_uint64()
+        self._chk(self.L.dugks_checkpoint_size(self.h, C.byref(n)), "dugks_checkpoint_size")
+        buf = np.empty(n.value, dtype=np.uint8)
+        self._chk(self.L.dugks_checkpoint_save(self.h, buf.ctypes.data_as(C.c_void_p), n.value), "dugks_checkpoint_save")
+        return buf
+
+    def restore(self, blob: np.ndarray):
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        self._chk(self.L.dugks_checkpoint_load(self.h, blob.ctypes.data_as(C.c_void_p), blob.size), "dugks_checkpoint_load")
 
     def writeDFonCell(self, cell: int):
         """fvDVM::writeDFonCell (fvDVM.C:820-875): gTilde (and hTilde) of one cell for all global DVs."""

@@ -154,16 +154,16 @@ def read_case(case_dir: str) -> Case:
 
 def _uniform_case(mesh: PolyMesh, Xis, weights, kinds: Dict[str, int], *, lid_patch="movingWall",
                   lid_U=(50.0, 0.0, 0.0), wall_T: Optional[Dict[str, float]] = None, gas=None,
-                  rho0=RHO0, T0_=T0, name="", bc_overrides: Optional[Dict[str, dict]] = None,
+                  rho0=RHO0, T0_=T0, U0=(0.0, 0.0, 0.0), name="", bc_overrides: Optional[Dict[str, dict]] = None,
                   perturb: float = 0.0, seed: int = 20260101) -> Case:
     geom = compute_geometry(mesh)
     nc, nbf = geom.nCells, geom.nBoundaryFaces
-    rho = np.full(nc, rho0); U = np.zeros((nc, 3)); T = np.full(nc, T0_)
+    rho = np.full(nc, rho0); U = np.tile(np.asarray(U0, dtype=np.float64), (nc, 1)); T = np.full(nc, T0_)
     if perturb > 0:
         rng = np.random.default_rng(seed)
         rho *= 1.0 + perturb * (rng.random(nc) - 0.5) * 2
         T *= 1.0 + perturb * (rng.random(nc) - 0.5) * 2
-        U[:, : geom.nSolutionD] = (rng.random((nc, geom.nSolutionD)) - 0.5) * 2 * 5.0
+        U[:, : geom.nSolutionD] += (rng.random((nc, geom.nSolutionD)) - 0.5) * 2 * 5.0
     rho_b = np.full(nbf, rho0); U_b = np.zeros((nbf, 3)); T_b = np.full(nbf, T0_)
     patches = []
     for pname, ptype, start, size in zip(geom.patch_names, geom.patch_types, geom.patch_start, geom.patch_size):
@@ -194,9 +194,9 @@ def _uniform_case(mesh: PolyMesh, Xis, weights, kinds: Dict[str, int], *, lid_pa
                 U_b=U_b, T_b=T_b, name=name, mesh=mesh)
 
 
-def gh_set(nDV: int, gas=None, T=T0):
+def gh_set(nDV: int, gas=None, T=T0, stable: bool = False):
     g = gas or ARGON
-    return _dvset.dvGH(float(np.sqrt(2.0 * g["R"] * T)), nDV)
+    return _dvset.dvGH(float(np.sqrt(2.0 * g["R"] * T)), nDV, stable=stable)
 
 
 def cavity2d_case(n: int, nDV: int = 28, quad: str = "GH", *, distort: float = 0.0, perturb: float = 0.0,
@@ -204,8 +204,8 @@ def cavity2d_case(n: int, nDV: int = 28, quad: str = "GH", *, distort: float = 0
     """2-D lid-driven cavity n x n hexes on [0,1]^2 x [0,0.1], Maxwell walls, lid on top
     (the shape of demo/cavity and of BASELINE config 2)."""
     mesh = hex_block(n, n, 1, (1.0, 1.0, 0.1), two_d=True, distort=distort)
-    if quad == "GH":
-        Xis, w = gh_set(nDV)
+    if quad in ("GH", "GHs"):     # GHs: extended-precision recurrence (sets setDV.py itself cannot produce, nDV > 32)
+        Xis, w = gh_set(nDV, stable=quad == "GHs")
     else:
         Xis, w = _dvset.dvNC(xiMax if xiMax is not None else 4.0 * np.sqrt(2 * ARGON["R"] * T0), nDV)
     c = _uniform_case(mesh, Xis, w, {}, name=name or f"cavity2d_{n}x{n}_{quad}{nDV}", perturb=perturb)

@@ -88,11 +88,17 @@ struct dugks_handle {
     double *wall_cin = nullptr, *wall_in = nullptr;
     int* d_bc = nullptr;
     double* d_pres = nullptr;
-    int* d_mirror = nullptr;           // [3][nflat]
-    double *snap_g = nullptr, *snap_h = nullptr;
+    // symmetry patches (k_sym_pack / k_sym_apply): X = the reference's dfContainer (fvDVM.C:398-449)
+    int *d_xrow = nullptr, *d_xmir = nullptr;   // [nflat], [3][nflat]: row of X of a local DV / of its x, y, z mirror DV
+    int* d_symface = nullptr;                   // [nsym] boundary faces of all symmetry patches
+    double *sym_Xg = nullptr, *sym_Xh = nullptr;
+    int nsym = 0, sym_rows = 0;
+    bool sym_exchange = false;                  // mirror partners on other ranks: X is indexed by global DV id and all-reduced
+    std::vector<SymPatch> sym_patches;
     double* d_co = nullptr;
     double *d_conv_old = nullptr, *d_conv = nullptr;   // convergence monitor: snapshot [nc][5], sums [6] + partials
     double* d_bstage = nullptr;        // [5 nbf] staging of dugks_set_boundary_macros
+    double* fslot_fold = nullptr;      // [nf][nm] sharded runs: face moment slots with both sides added (what the all-reduce carries)
     bool has_sym = false, has_wall = false;
     size_t nflat = 0;                  // nslab*L*Rs
     // collective
@@ -539,29 +545,26 @@ static int launch_slab_kernels_phase2(dugks_handle* h, StepArgs a) {
 
 template <bool H>
 static int symmetry_stage(dugks_handle* h, StepArgs a) {
-    // snapshot = the reference's dfContainer (fvDVM.C:423-449)
-    size_t n = (size_t)h->nbf * h->nflat;
-    CUDA_TRY(h, cudaMemcpyAsync(h->snap_g, a.gsb, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    if (H) CUDA_TRY(h, cudaMemcpyAsync(h->snap_h, a.hsb, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    for (const auto& p : h->patches) {
-        if ((p.kind != DUGKS_PATCH_DVM_SYMMETRY && p.kind != DUGKS_PATCH_SYMMETRY_PLANE) || p.size <= 0) continue;
-        // mirror axis from the first face normal (discreteVelocity.C:777-779)
-        double s0[3];
-        CUDA_TRY(h, cudaMemcpyAsync(s0, a.m.b_Sf + (size_t)p.start * 3, sizeof s0, cudaMemcpyDeviceToHost, h->stream));
-        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-        double mag = std::sqrt(s0[0] * s0[0] + s0[1] * s0[1] + s0[2] * s0[2]);
-        int axis = 0;
-        double best = -1;
-        for (int d = 0; d < 3; d++)
-            if (std::fabs(s0[d] / mag) > best) { best = std::fabs(s0[d] / mag); axis = d; }
-        if (best < 1.0 - 1e-9)
-            return fail(h, DUGKS_ERR_UNSUPPORTED, "symmetry patch normal is not axis aligned (the reference's mirror-id rule, discreteVelocity.C:777-779, needs it)");
-        long long total = (long long)p.size * (long long)h->nflat;
-        int grid = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
-        k_bnd_symmetry<H><<<grid, 256, 0, h->stream>>>(a, h->snap_g, h->snap_h, h->d_mirror, (int)h->nflat, p.start,
-                                                         p.size, axis, s0[0], s0[1], s0[2]);
-        int rc;
-        if ((rc = check_launch(h, "k_bnd_symmetry"))) return rc;
+    // X = the reference's dfContainer (fvDVM.C:398-431); the MPI_Allgatherv of :439-449 is a sum all-reduce of
+    // the rows every rank owns (zeros elsewhere), and only when mirror partners live on other ranks.
+    // Nothing here synchronises with the host: mirror axes and Sf0 were fixed at create.
+    const size_t nx = (size_t)h->sym_rows * h->nsym;
+    int rc;
+    if (h->sym_exchange) {
+        CUDA_TRY(h, cudaMemsetAsync(h->sym_Xg, 0, nx * (H ? 2 : 1) * sizeof(double), h->stream));
+    }
+    {
+        const long long total = (long long)h->nsym * (long long)h->nflat;
+        const int grid = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
+        k_sym_pack<H><<<grid, 256, 0, h->stream>>>(a, h->d_symface, h->nsym, h->d_xrow, (int)h->nflat, h->sym_Xg, h->sym_Xh);
+        if ((rc = check_launch(h, "k_sym_pack"))) return rc;
+    }
+    if (h->sym_exchange && (rc = do_allreduce(h, h->sym_Xg, nx * (H ? 2 : 1)))) return rc;   // g and h rows are one buffer
+    for (const SymPatch& P : h->sym_patches) {
+        const long long total = (long long)P.size * (long long)h->nflat;
+        const int grid = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
+        k_sym_apply<H><<<grid, 256, 0, h->stream>>>(a, P, h->nsym, h->d_xrow, h->d_xmir, (int)h->nflat, h->sym_Xg, h->sym_Xh);
+        if ((rc = check_launch(h, "k_sym_apply"))) return rc;
     }
     return 0;
 }
@@ -619,8 +622,15 @@ static int step_impl(dugks_handle* h, double dt) {
             if ((rc = check_launch(h, "k_bnd_moments"))) return rc;
         }
     }
-    if ((rc = do_allreduce(h, a.fslot, nslots * h->nm))) return rc;          // fvDVM.C:363,487-489,519
-    k_face_macros<<<(h->nf + 127) / 128, 128, 0, h->stream>>>(a);
+    const double* fsum = nullptr;
+    if (h->nranks > 1) {
+        // the two sides of an internal face are added before the collective: nf instead of 2 nif + nbf slots on the wire
+        k_fold_fslot<<<148 * 8, 256, 0, h->stream>>>(a, h->fslot_fold);
+        if ((rc = check_launch(h, "k_fold_fslot"))) return rc;
+        if ((rc = do_allreduce(h, h->fslot_fold, (size_t)h->nf * h->nm))) return rc;   // fvDVM.C:363,487-489,519
+        fsum = h->fslot_fold;
+    }
+    k_face_macros<<<(h->nf + 127) / 128, 128, 0, h->stream>>>(a, fsum);
     if ((rc = check_launch(h, "k_face_macros"))) return rc;
     for (int s = 0; s < h->nslab; s++) {
         a.slab = s;
@@ -643,7 +653,25 @@ struct RowDesc {
     int iy, iz, chunk;
     double y, z, w;
     int cbase = 0, len = 0;   // first ix of the row and its number of points
+    bool pad = false;         // filler row (weight 0, owns no velocity): keeps a slab to two adjacent ix-chunks
 };
+
+// Slabs needed by nch ix-chunks of nbl rows each when a slab (32 rows, one warp) may only hold rows of at
+// most two ADJACENT chunks (the equilibrium tables of a warp then span at most 2 L <= 64 entries): chunks are
+// laid down one after the other and a slab is padded out as soon as a third chunk would enter it.
+static long long packed_slabs(long long nbl, int nch) {
+    if (nch == 1 || nbl >= 32) return (nbl * nch + 31) / 32;   // 32+ rows per chunk: never three chunks in a slab
+    long long slabs = 0, fill = 0;
+    int c0 = -1;
+    for (int ch = 0; ch < nch; ch++)
+        for (long long r = 0; r < nbl; r++) {
+            if (fill == 32) { fill = 0; c0 = -1; }
+            if (c0 >= 0 && ch > c0 + 1) { fill = 0; c0 = -1; }
+            if (c0 < 0) { c0 = ch; slabs++; }
+            fill++;
+        }
+    return slabs;
+}
 
 static int choose_chunks(int n, int D, long long base_rows_local) {
     // Number of ix-chunks per row: rows of L = ceil(n / nch) <= MAX_L points, 32 rows per slab.
@@ -657,9 +685,7 @@ static int choose_chunks(int n, int D, long long base_rows_local) {
         if (L > MAX_L) continue;
         if (L < 4 && nch > 1) break;
         if ((long long)nch * L > NT_MAX) continue;
-        if (nch > 1 && base_rows_local < 32) continue;   // a warp must not span more than two chunks
-        long long rows = base_rows_local * nch;
-        long long slabs = (rows + 31) / 32;
+        long long slabs = packed_slabs(base_rows_local, nch);
         double cost = (double)slabs * (8.0 + L);
         if (cost < best_cost * 0.98) { best_cost = cost; best = nch; }   // ties: the longer rows
     }
@@ -714,6 +740,22 @@ static int build_row_layout(int n, int D, int nranks, int rank, const double* Xi
         return sa < sb;
     });
     for (auto& rd : rows) { rd.cbase = rd.chunk * L; rd.len = L; }
+    if (nch > 1) {
+        // a slab holds rows of at most two adjacent ix-chunks (packed_slabs): pad it out before a third one enters
+        std::vector<RowDesc> packed;
+        int fill = 0, c0 = -1;
+        for (const RowDesc& rd : rows) {
+            if (fill == Rs) { fill = 0; c0 = -1; }
+            if (c0 >= 0 && rd.chunk > c0 + 1) {
+                for (; fill < Rs; fill++) { RowDesc p = packed.back(); p.w = 0.0; p.pad = true; packed.push_back(p); }
+                fill = 0; c0 = -1;
+            }
+            if (c0 < 0) c0 = rd.chunk;
+            packed.push_back(rd);
+            fill++;
+        }
+        rows.swap(packed);
+    }
     // short-row tail slab (dv_len, dugks_device.cuh): the rows that would leave the last slab mostly
     // empty are cut into ix-chunks of Lt points and fill the lanes of one short slab
     const int r_last = (int)rows.size() % Rs;
@@ -752,7 +794,7 @@ extern "C" int dugks_row_layout(int32_t nXiPerDim, int32_t nSolutionD, int32_t n
     if (row_iy && row_iz && row_first && row_len)
         for (int k = 0; k < (int)lay.rows.size() && k < cap; k++) {
             row_iy[k] = lay.rows[k].iy; row_iz[k] = lay.rows[k].iz;
-            row_first[k] = lay.rows[k].cbase; row_len[k] = lay.rows[k].len;
+            row_first[k] = lay.rows[k].cbase; row_len[k] = lay.rows[k].pad ? 0 : lay.rows[k].len;   // filler rows own nothing
         }
     return 0;
 }
@@ -954,6 +996,8 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
     if (!par) par = &pdef;
     int nranks = par->nRanks < 1 ? 1 : par->nRanks;
     if (par->rank < 0 || par->rank >= nranks) return fail(nullptr, DUGKS_ERR_INVALID, "dugks_create: bad rank");
+    if (par->partition != 0 || par->dv_chunk != 0)
+        return fail(nullptr, DUGKS_ERR_INVALID, "dugks_create: dugks_par_t.partition and .dv_chunk are reserved and must be 0");
 
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);
@@ -1019,7 +1063,7 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
             for (int ix = 0; ix < n; ix++) h->owner_rank_of_gid[br * n + ix] = r;
     RowLayout lay;
     if (build_row_layout(n, D, nranks, h->rank, dvset->Xis, dvset->weights, lay) != 0) {
-        fail(h, DUGKS_ERR_UNSUPPORTED, "nDV = %d cannot be laid out (needs ix-chunks of <= %d points, <= %d table entries)", n, MAX_L, NT_MAX);
+        fail(h, DUGKS_ERR_UNSUPPORTED, "nDV = %d cannot be laid out (rows are cut into ix-chunks of <= %d points, <= %d table entries in all)", n, MAX_L, NT_MAX);
         return bail(DUGKS_ERR_UNSUPPORTED);
     }
     const int nch = lay.nch, L = lay.L;
@@ -1035,7 +1079,7 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
     for (int k = 0; k < h->nrows; k++) {
         const RowDesc& rd = rows[std::min(k, nreal - 1)];   // padding rows duplicate the last row with weight 0
         row_y[k] = rd.y; row_z[k] = rd.z; row_cb[k] = rd.cbase;
-        if (k < nreal) row_w[k] = rd.w;
+        if (k < nreal && !rd.pad) row_w[k] = rd.w;
     }
     // tables along x: entries beyond n duplicate the last abscissa with weight 0
     std::vector<double> tx((size_t)5 * h->ntab);
@@ -1058,6 +1102,7 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
     for (int k = 0; k < nreal; k++) {
         int s = k / h->Rs, r = k % h->Rs;
         const RowDesc& rd = rows[k];
+        if (rd.pad) continue;
         for (int i = 0; i < rd.len; i++) {
             int ix = rd.cbase + i;
             if (ix >= n) continue;
@@ -1070,8 +1115,9 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
     for (int g = 0; g < h->nxi; g++)
         if (gid_flat[g] >= 0) { h->local_gids.push_back(g); h->local_flat.push_back(gid_flat[g]); }
     h->nvl = (int)h->local_gids.size();
-    std::vector<int> mirror((size_t)3 * h->nflat, -1);
-    bool mirror_local = true;
+    // mirror partners (fvDVM.C:162-164), as rows of the symmetry exchange buffer X: local flat indices when every
+    // partner is local, global DV ids otherwise (the partner's values then arrive by the all-reduce of X)
+    std::vector<int> mir_gid((size_t)3 * h->nflat, -1);
     for (size_t flat = 0; flat < h->nflat; flat++) {
         int g = h->flat_gid[flat];
         if (g < 0) continue;
@@ -1079,14 +1125,51 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
         int mg[3] = {(iz * ny + iy) * n + (n - 1 - ix),                       // fvDVM.C:162
                      (D >= 2) ? (iz * ny + (ny - 1 - iy)) * n + ix : 0,        // :163
                      (D == 3) ? ((nz - 1 - iz) * ny + iy) * n + ix : 0};       // :164
-        for (int d = 0; d < 3; d++) {
-            mirror[(size_t)d * h->nflat + flat] = gid_flat[mg[d]];
-            if (d < D && gid_flat[mg[d]] < 0) mirror_local = false;
-        }
+        for (int d = 0; d < 3; d++) mir_gid[(size_t)d * h->nflat + flat] = mg[d];
     }
-    if (h->has_sym && !mirror_local) {
-        fail(h, DUGKS_ERR_UNSUPPORTED, "symmetry patches with a velocity partition that separates mirror partners are not supported yet (use nRanks = 1)");
-        return bail(DUGKS_ERR_UNSUPPORTED);
+    std::vector<int> xrow(h->nflat, -1), xmir((size_t)3 * h->nflat, -1), symface;
+    if (h->has_sym) {
+        bool axis_used[3] = {false, false, false};
+        for (int p = 0; p < nPatches; p++) {
+            const dugks_patch_t& P = patches[p];
+            if ((P.kind != DUGKS_PATCH_DVM_SYMMETRY && P.kind != DUGKS_PATCH_SYMMETRY_PLANE) || P.size <= 0) continue;
+            // mirror axis from the normal of the FIRST face of the patch (discreteVelocity.C:763,777-779)
+            const double* s0 = mesh->Sf + (size_t)(nif + P.start) * 3;
+            const double mag = std::sqrt(s0[0] * s0[0] + s0[1] * s0[1] + s0[2] * s0[2]);
+            int axis = 0;
+            double best = -1;
+            for (int d = 0; d < 3; d++)
+                if (std::fabs(s0[d] / mag) > best) { best = std::fabs(s0[d] / mag); axis = d; }
+            if (!(best >= 1.0 - 1e-9) || axis >= D) {
+                fail(h, DUGKS_ERR_UNSUPPORTED, "symmetry patch %d: normal is not along a solved axis (the reference's mirror-id rule, discreteVelocity.C:777-779, needs it)", p);
+                return bail(DUGKS_ERR_UNSUPPORTED);
+            }
+            axis_used[axis] = true;
+            SymPatch sp{P.start, P.size, axis, (int)symface.size(), s0[0], s0[1], s0[2]};
+            h->sym_patches.push_back(sp);
+            for (int j = 0; j < P.size; j++) symface.push_back(P.start + j);
+        }
+        h->nsym = (int)symface.size();
+        // every rank must take the same decision (the exchange is a collective): does ANY rank miss a partner
+        // along an axis some symmetry patch mirrors about?
+        h->sym_exchange = false;
+        for (int g = 0; g < h->nxi && !h->sym_exchange; g++) {
+            const int ix = g % n, iy = (g / n) % ny, iz = g / (n * ny);
+            const int mg[3] = {(iz * ny + iy) * n + (n - 1 - ix), (iz * ny + (ny - 1 - iy)) * n + ix,
+                               ((nz - 1 - iz) * ny + iy) * n + ix};
+            for (int d = 0; d < D; d++)
+                if (axis_used[d] && h->owner_rank_of_gid[mg[d]] != h->owner_rank_of_gid[g]) h->sym_exchange = true;
+        }
+        h->sym_rows = h->sym_exchange ? h->nxi : (int)h->nflat;
+        for (size_t flat = 0; flat < h->nflat; flat++) {
+            const int g = h->flat_gid[flat];
+            if (g < 0) continue;
+            xrow[flat] = h->sym_exchange ? g : (int)flat;
+            for (int d = 0; d < 3; d++) {
+                const int mg = mir_gid[(size_t)d * h->nflat + flat];
+                xmir[(size_t)d * h->nflat + flat] = h->sym_exchange ? mg : gid_flat[mg];
+            }
+        }
     }
 
     // ---- cell -> face CSR (internal faces first), geometry per entry
@@ -1293,7 +1376,9 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
     TRYB(dev_upload(h, &d_i, row_cb)); V.row_cbase = d_i;
     TRYB(dev_upload(h, &h->d_bc, b_bc));
     TRYB(dev_upload(h, &h->d_pres, b_pres));
-    TRYB(dev_upload(h, &h->d_mirror, mirror));
+    TRYB(dev_upload(h, &h->d_xrow, xrow));
+    TRYB(dev_upload(h, &h->d_xmir, xmir));
+    TRYB(dev_upload(h, &h->d_symface, symface));
 
     // ---- macros
     std::vector<double> cmac((size_t)nc * MAC_N, 0.0), bmac((size_t)nbf * 5, 0.0), fmac((size_t)nf * MAC_N, 0.0);
@@ -1337,7 +1422,7 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
     const size_t ncell_dv = (size_t)nc * h->nflat, nb_dv = (size_t)nbf * h->nflat;
     const int nfld = h->hasH ? 2 : 1;
     // gBarP: at least one slab block (face-storage slabs share a transient one), at most one per slab
-    size_t need = (ncell_dv + (size_t)nc * L * h->Rs + 3 * nb_dv + (h->has_sym ? nb_dv : 0) + (size_t)nif * L * h->Rs) * nfld * sizeof(double) +
+    size_t need = (ncell_dv + (size_t)nc * L * h->Rs + 3 * nb_dv + (size_t)h->sym_rows * h->nsym + (size_t)nif * L * h->Rs) * nfld * sizeof(double) +
                   ((size_t)(2 * nif + nbf) + nc) * h->nm * sizeof(double);
     if (need > free_b) {
         fail(h, DUGKS_ERR_NOMEM, "state needs %.2f GB of device memory, only %.2f GB free (nCells=%d, local DVs=%d, h %s)",
@@ -1360,11 +1445,13 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
     }
     TRYB(dev_alloc(h, &A.fcoef, (size_t)nf * FCOEF_N));
     if (h->has_sym) {
-        TRYB(dev_alloc(h, &h->snap_g, nb_dv));
-        if (h->hasH) TRYB(dev_alloc(h, &h->snap_h, nb_dv));
+        // g rows, then h rows: one buffer, one collective
+        TRYB(dev_alloc(h, &h->sym_Xg, (size_t)h->sym_rows * h->nsym * nfld));
+        if (h->hasH) h->sym_Xh = h->sym_Xg + (size_t)h->sym_rows * h->nsym;
     }
     TRYB(dev_alloc(h, &A.fslot, ((size_t)2 * nif + nbf) * h->nm));
     TRYB(dev_alloc(h, &A.cslot, (size_t)nc * h->nm));
+    if (nranks > 1) TRYB(dev_alloc(h, &h->fslot_fold, (size_t)nf * h->nm));
     TRYB(dev_alloc(h, &h->wall_cin, (size_t)nbf * h->nm));
     TRYB(dev_alloc(h, &h->wall_in, (size_t)nbf));
     TRYB(dev_alloc(h, &A.wall_diag, (size_t)nbf * 12));
@@ -1461,7 +1548,10 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
         const size_t reserve = nranks > 1 ? (size_t)3 << 30 : (size_t)3 << 29;
         const bool can_w = h->hsmem_half > 0 && getenv("DUGKS_NO_WMODE") == nullptr;   // test hook: persistent gBarP everywhere
         h->gb_in_fbuf = can_w && nif >= nc;
-        const long long avail = free2 > reserve ? (long long)(free2 - reserve) : 0;
+        long long avail = free2 > reserve ? (long long)(free2 - reserve) : 0;
+        // dugks_par_t.scratch_bytes: the caller's cap on what the kept face values (and the gBarP blocks that go
+        // with them) may take; the slabs that do not fit recompute their face values in phase 2
+        if (par->scratch_bytes > 0) avail = std::min<long long>(avail, (long long)std::min<size_t>(par->scratch_bytes, (size_t)1 << 62));
         long long fit = 0;
         for (long long k = h->nslab; k > 0; k--) {
             const long long blocks = can_w ? (h->nslab - k) + (h->gb_in_fbuf ? 0 : 1) : h->nslab;
@@ -1612,7 +1702,7 @@ extern "C" int dugks_set_boundary_macros(dugks_handle_t* h, const double* rho_b,
     if (rho_b) { d_rho = h->d_bstage; CUDA_TRY(h, cudaMemcpyAsync(d_rho, rho_b, nb * sizeof(double), cudaMemcpyHostToDevice, h->stream)); }
     if (U_b) { d_U = h->d_bstage + nb; CUDA_TRY(h, cudaMemcpyAsync(d_U, U_b, 3 * nb * sizeof(double), cudaMemcpyHostToDevice, h->stream)); }
     if (T_b) { d_T = h->d_bstage + 4 * nb; CUDA_TRY(h, cudaMemcpyAsync(d_T, T_b, nb * sizeof(double), cudaMemcpyHostToDevice, h->stream)); }
-    k_set_bmac<<<(h->nbf + 127) / 128, 128, 0, h->stream>>>(h->A, d_rho, d_U, d_T);
+    k_set_bmac<<<(h->nbf + 127) / 128, 128, 0, h->stream>>>(h->A, h->d_bc, d_rho, d_U, d_T);
     int rc = check_launch(h, "k_set_bmac");
     if (rc) return rc;
     rc = h->hasH ? compute_wall_constants<true>(h) : compute_wall_constants<false>(h);
@@ -1770,6 +1860,105 @@ extern "C" int dugks_get_df(dugks_handle_t* h, int32_t cell, double* g, double* 
         }
         memcpy(dst, glob.data(), sizeof(double) * h->nxi);
     }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------
+// Exact restart.  The reference's restart is lossy: every distribution-function field
+// is NO_READ/NO_WRITE (discreteVelocity.C:74-205), so a restarted run re-initialises gTilde/hTilde to an
+// equilibrium of the saved macros (:220-249) and rho_w to 1 (calculatedMaxwellFvPatchField.C:80).  The blob
+// carries everything the next evolution() reads: gTilde/hTilde, the boundary-face values (the incoming half of
+// "mixed" patches is never recomputed, :556-573), the lagged boundary gradient (:462-468), cell/face/boundary
+// macros (q and tau enter the next half step, :393-396; Usurf the next Courant number), the wall constants
+// and the convergence monitor's old fields.  Rank-local, in device layout: valid for the same case, rank
+// count and rank only (checked).
+struct CkHeader {
+    uint64_t magic;
+    int32_t abi, nc, nbf, nf, nm, hasH, nranks, rank, L, Rs, nslab, Lt;
+    uint64_t nflat, steps, total_bytes;
+};
+#define CK_MAGIC 0x44554732434b5054ull   // "DUG2CKPT"
+
+struct CkPiece { void* dev; size_t bytes; };
+static std::vector<CkPiece> ck_pieces(dugks_handle* h) {
+    const size_t ncell_dv = (size_t)h->nc * h->nflat, nb_dv = (size_t)h->nbf * h->nflat;
+    // the array the NEXT step reads as the lagged gradient (step_impl flips first)
+    const bool flip_next = !h->gam_flip;
+    double* gam_g = flip_next ? h->gam_b_g : h->gam_a_g;
+    double* gam_h = flip_next ? h->gam_b_h : h->gam_a_h;
+    std::vector<CkPiece> v;
+    auto add = [&](double* p, size_t n) { if (p && n) v.push_back({p, n * sizeof(double)}); };
+    add(h->A.gt, ncell_dv);
+    if (h->hasH) add(h->A.ht, ncell_dv);
+    add(h->A.gsb, nb_dv);
+    if (h->hasH) add(h->A.hsb, nb_dv);
+    add(gam_g, nb_dv);
+    if (h->hasH) add(gam_h, nb_dv);
+    add(h->A.cmac, (size_t)h->nc * MAC_N);
+    add(h->A.fmac, (size_t)h->nf * MAC_N);
+    add(h->A.bmac, (size_t)h->nbf * 5);
+    add(h->A.wall_diag, (size_t)h->nbf * 12);
+    add(h->wall_cin, (size_t)h->nbf * h->nm);
+    add(h->wall_in, (size_t)h->nbf);
+    add(h->d_conv_old, (size_t)5 * h->nc);
+    return v;
+}
+static CkHeader ck_header(dugks_handle* h) {
+    CkHeader k{};
+    k.magic = CK_MAGIC; k.abi = DUGKS_ABI_VERSION; k.nc = h->nc; k.nbf = h->nbf; k.nf = h->nf; k.nm = h->nm;
+    k.hasH = h->hasH; k.nranks = h->nranks; k.rank = h->rank; k.L = h->L; k.Rs = h->Rs; k.nslab = h->nslab; k.Lt = h->Lt;
+    k.nflat = h->nflat; k.steps = h->steps;
+    k.total_bytes = sizeof(CkHeader);
+    for (const CkPiece& p : ck_pieces(h)) k.total_bytes += p.bytes;
+    return k;
+}
+
+extern "C" int dugks_checkpoint_size(dugks_handle_t* h, uint64_t* bytes) {
+    if (!h || !bytes) return DUGKS_ERR_INVALID;
+    *bytes = ck_header(h).total_bytes;
+    return 0;
+}
+
+extern "C" int dugks_checkpoint_save(dugks_handle_t* h, void* buf, uint64_t bytes) {
+    if (!h || !buf) return DUGKS_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const CkHeader k = ck_header(h);
+    if (bytes < k.total_bytes) return fail(h, DUGKS_ERR_INVALID, "dugks_checkpoint_save: buffer of %llu bytes, %llu needed", (unsigned long long)bytes, (unsigned long long)k.total_bytes);
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    char* out = (char*)buf;
+    memcpy(out, &k, sizeof k);
+    out += sizeof k;
+    for (const CkPiece& p : ck_pieces(h)) {
+        CUDA_TRY(h, cudaMemcpy(out, p.dev, p.bytes, cudaMemcpyDeviceToHost));
+        out += p.bytes;
+    }
+    return 0;
+}
+
+extern "C" int dugks_checkpoint_load(dugks_handle_t* h, const void* buf, uint64_t bytes) {
+    if (!h || !buf) return DUGKS_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (bytes < sizeof(CkHeader)) return fail(h, DUGKS_ERR_INVALID, "dugks_checkpoint_load: truncated blob");
+    CkHeader got;
+    memcpy(&got, buf, sizeof got);
+    const CkHeader want = ck_header(h);
+    if (got.magic != CK_MAGIC || got.abi != want.abi) return fail(h, DUGKS_ERR_INVALID, "dugks_checkpoint_load: not a checkpoint of this library version");
+    if (got.nc != want.nc || got.nbf != want.nbf || got.nf != want.nf || got.nm != want.nm || got.hasH != want.hasH ||
+        got.nranks != want.nranks || got.rank != want.rank || got.L != want.L || got.Rs != want.Rs || got.nslab != want.nslab ||
+        got.Lt != want.Lt || got.nflat != want.nflat || got.total_bytes != want.total_bytes)
+        return fail(h, DUGKS_ERR_INVALID, "dugks_checkpoint_load: the blob belongs to another case, rank count or rank "
+                    "(cells %d/%d, boundary faces %d/%d, ranks %d/%d, rank %d/%d, local DV slots %llu/%llu)", got.nc, want.nc, got.nbf,
+                    want.nbf, got.nranks, want.nranks, got.rank, want.rank, (unsigned long long)got.nflat, (unsigned long long)want.nflat);
+    if (bytes < got.total_bytes) return fail(h, DUGKS_ERR_INVALID, "dugks_checkpoint_load: truncated blob");
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    const char* in = (const char*)buf + sizeof got;
+    for (const CkPiece& p : ck_pieces(h)) {
+        CUDA_TRY(h, cudaMemcpy(p.dev, in, p.bytes, cudaMemcpyHostToDevice));
+        in += p.bytes;
+    }
+    h->steps = got.steps;
+    // the caller's last boundary arrays are unknown now: the next dugks_set_boundary_macros always applies
+    h->last_rho_b.clear(); h->last_U_b.clear(); h->last_T_b.clear();
     return 0;
 }
 

@@ -547,31 +547,55 @@ k_bnd_outgoing(StepArgs a, int far_only) {
 
 // ---------------------------------------------------------------------------------
 // Symmetry patches: incoming DVs copy the patch values of their mirror DV
-// (discreteVelocity.C:733-817).  snap_* is a snapshot of gsb/hsb taken after
-// k_bnd_outgoing (the reference's dfContainer, fvDVM.C:423-431).
-// mirror[3][ndvpad]: flat local index (slab*L*Rs + i*Rs + r) of the x/y/z mirror DV or -1.
+// (discreteVelocity.C:733-817).  Two kernels around an optional collective, as in the reference
+// (fvDVM.C:375-454: every rank copies its DVs' patch values into dfContainer, MPI_Allgatherv, then every
+// incoming DV reads its mirror partner's entry):
+//   k_sym_pack   X[xrow[k]][j] = gSurf of local DV k on symmetry face j   (the dfContainer; rows the rank
+//                does not own stay zero, so a SUM all-reduce over the ranks is the all-gather)
+//   k_sym_apply  incoming DVs (xi.Sf0 <= 0, :775, Sf0 = first face of the patch) take X[xmir[axis][k]][j]
+// xrow / xmir index X by GLOBAL DV id when mirror partners may live on another rank, by the local flat index
+// (slab*L*Rs + i*Rs + r) when every partner is local (no collective then).  X: [nX][nsym] (+ the same for h).
+struct SymPatch {
+    int start, size, axis, xoff;     // boundary-face range, mirror axis (:777-779), first column in X
+    double s0x, s0y, s0z;            // Sf of the first face of the patch
+};
+
 template <bool HAS_H>
-__global__ void k_bnd_symmetry(StepArgs a, const double* snap_g, const double* snap_h, const int* mirror,
-                               int ndvpad, int p_start, int p_size, int axis, double s0x, double s0y, double s0z) {
+__global__ void k_sym_pack(StepArgs a, const int* symface, int nsym, const int* xrow, int ndvpad, double* Xg, double* Xh) {
     const DevDV& dv = a.dv;
-    long long total = (long long)p_size * ndvpad;
-    int slabsz = dv.L * dv.Rs;
+    const long long total = (long long)nsym * ndvpad;
+    const int slabsz = dv.L * dv.Rs;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
          t += (long long)gridDim.x * blockDim.x) {
-        int j = (int)(t / ndvpad), k = (int)(t % ndvpad);
-        int s = k / slabsz, rem = k % slabsz, i = rem / dv.Rs, r = rem % dv.Rs;
-        if (i >= dv_len(dv, s)) continue;
-        int grow = s * dv.Rs + r;
-        double x = dv.tx[dv.row_cbase[grow] + i], y = dv.row_y[grow], z = dv.row_z[grow];
-        if (dot_exact(x, y, z, s0x, s0y, s0z) <= 0) {     // :775 (first face of the patch)
-            int mk = mirror[(size_t)axis * ndvpad + k];
-            if (mk < 0) continue;
-            int ms = mk / slabsz, mrem = mk % slabsz;
-            int b = p_start + j;
-            size_t dst = ((size_t)s * a.m.nbf + b) * slabsz + rem;
-            size_t src = ((size_t)ms * a.m.nbf + b) * slabsz + mrem;
-            a.gsb[dst] = snap_g[src];
-            if (HAS_H) a.hsb[dst] = snap_h[src];
+        const int j = (int)(t / ndvpad), k = (int)(t % ndvpad);
+        const int row = xrow[k];
+        if (row < 0) continue;                                   // padding entry: owns no velocity
+        const int s = k / slabsz, rem = k % slabsz;
+        const size_t src = ((size_t)s * a.m.nbf + symface[j]) * slabsz + rem;
+        Xg[(size_t)row * nsym + j] = a.gsb[src];
+        if (HAS_H) Xh[(size_t)row * nsym + j] = a.hsb[src];
+    }
+}
+
+template <bool HAS_H>
+__global__ void k_sym_apply(StepArgs a, SymPatch P, int nsym, const int* xrow, const int* xmir, int ndvpad,
+                            const double* Xg, const double* Xh) {
+    const DevDV& dv = a.dv;
+    const long long total = (long long)P.size * ndvpad;
+    const int slabsz = dv.L * dv.Rs;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(t / ndvpad), k = (int)(t % ndvpad);
+        if (xrow[k] < 0) continue;
+        const int s = k / slabsz, rem = k % slabsz, i = rem / dv.Rs, r = rem % dv.Rs;
+        const int grow = s * dv.Rs + r;
+        const double x = dv.tx[dv.row_cbase[grow] + i], y = dv.row_y[grow], z = dv.row_z[grow];
+        if (dot_exact(x, y, z, P.s0x, P.s0y, P.s0z) <= 0) {      // :775 (first face of the patch)
+            const int mrow = xmir[(size_t)P.axis * ndvpad + k];
+            if (mrow < 0) continue;
+            const size_t dst = ((size_t)s * a.m.nbf + P.start + j) * slabsz + rem;
+            a.gsb[dst] = Xg[(size_t)mrow * nsym + P.xoff + j];
+            if (HAS_H) a.hsb[dst] = Xh[(size_t)mrow * nsym + P.xoff + j];
         }
     }
 }
@@ -701,20 +725,39 @@ k_wall_constants(StepArgs a, double* cin, double* win) {
 
 // ---------------------------------------------------------------------------------
 // face macros from the (all-reduced) moment slots; wall density; wall diagnostics.
-__global__ void k_face_macros(StepArgs a) {
+// Owner-side + neighbour-side slot of every internal face, boundary slots copied: [nf][nm].  Run before the
+// face all-reduce of a sharded step so that the collective carries nf instead of 2 nif + nbf slots.
+__global__ void k_fold_fslot(StepArgs a, double* out) {
+    const long long total = (long long)a.m.nf * a.nm;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int f = (int)(t / a.nm), k = (int)(t % a.nm);
+        out[t] = f < a.m.nif ? a.fslot[(size_t)(2 * f) * a.nm + k] + a.fslot[(size_t)(2 * f + 1) * a.nm + k]
+                             : a.fslot[((size_t)a.m.nif + f) * a.nm + k];
+    }
+}
+
+// fsum: folded (and all-reduced) slots [nf][nm] of a sharded step, or null: the two sides are added here
+__global__ void k_face_macros(StepArgs a, const double* fsum) {
     int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= a.m.nf) return;
     const int nm = a.nm;
     double M[NM_MAX];
     for (int k = 0; k < NM_MAX; k++) M[k] = 0.0;
+    if (fsum) {
+        for (int k = 0; k < nm; k++) M[k] = fsum[(size_t)f * nm + k];
+    }
     if (f < a.m.nif) {
+        if (!fsum) {
         const double* s0 = a.fslot + (size_t)(2 * f) * nm;
         const double* s1 = s0 + nm;
         for (int k = 0; k < nm; k++) M[k] = s0[k] + s1[k];
+        }
     } else {
         int b = f - a.m.nif;
-        const double* s0 = a.fslot + ((size_t)2 * a.m.nif + b) * nm;
-        for (int k = 0; k < nm; k++) M[k] = s0[k];
+        if (!fsum) {
+            const double* s0 = a.fslot + ((size_t)2 * a.m.nif + b) * nm;
+            for (int k = 0; k < nm; k++) M[k] = s0[k];
+        }
         if (a.m.b_kind[b] == K_MAXWELL_WALL) {
             const double* Sf = a.m.b_Sf + (size_t)b * 3;
             // outGoing = sum_{out} w (xi.Sf) gSurf (discreteVelocity.C:623-624);
@@ -1103,12 +1146,18 @@ __global__ void k_convergence_init(StepArgs a, double* old) {
     o[0] = mc[0]; o[1] = mc[1]; o[2] = mc[2]; o[3] = mc[3]; o[4] = mc[4];
 }
 
-// dugks_set_boundary_macros: scatter the caller's boundary fields (any may be null) into bmac
-__global__ void k_set_bmac(StepArgs a, const double* rho_b, const double* U_b, const double* T_b) {
+// dugks_set_boundary_macros: scatter the caller's boundary fields (any may be null) into bmac.  Only values
+// the caller owns are taken: components the library evolves itself keep their device values — U / T of
+// zeroGradient patch fields (bc bits, fvDVM.C:698-699), rho_w of Maxwell walls
+// (calculatedMaxwellFvPatchField.C:158), and on pressure patches U and rho (and T on outlets), which
+// updatePressureInOutBC recomputes every step (fvDVM.C:743-804).
+__global__ void k_set_bmac(StepArgs a, const int* bc, const double* rho_b, const double* U_b, const double* T_b) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= a.m.nbf) return;
     double* bm = a.bmac + (size_t)b * 5;
-    if (rho_b) bm[0] = rho_b[b];
-    if (U_b) { bm[1] = U_b[3 * b]; bm[2] = U_b[3 * b + 1]; bm[3] = U_b[3 * b + 2]; }
-    if (T_b) bm[4] = T_b[b];
+    const int kind = a.m.b_kind[b];
+    const bool pres = kind == K_PRESSURE_IN || kind == K_PRESSURE_OUT;
+    if (rho_b && !pres && kind != K_MAXWELL_WALL) bm[0] = rho_b[b];
+    if (U_b && !pres && !(bc[b] & 1)) { bm[1] = U_b[3 * b]; bm[2] = U_b[3 * b + 1]; bm[3] = U_b[3 * b + 2]; }
+    if (T_b && kind != K_PRESSURE_OUT && !(bc[b] & 2)) bm[4] = T_b[b];
 }

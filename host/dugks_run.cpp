@@ -1,9 +1,10 @@
 // host/dugks_run.cpp — stand-alone driver that plays the role of dugksFoam.C's time loop
 // (reference src/dugksFoam.C:63-109, setDeltaTvar.H:34-47) on a case dumped by
 // `python -m dugksfoam_b200.dump_case`.  Usage:
-//     dugks_run <case.bin> <nSteps> <maxCo or 0 for the case's fixed deltaT> <out.bin>
+//     dugks_run <case.bin> <nSteps> <maxCo or 0 for the case's fixed deltaT> <out.bin> [maxDeltaT]
 // Writes rho[nc], U[nc][3], T[nc], q[nc][3] as raw doubles to <out.bin>.
 // Exit code 2 + the library's message when no CUDA device is present (there is no CPU fallback).
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -67,6 +68,7 @@ int main(int argc, char** argv) {
         const int nSteps = std::atoi(argv[2]);
         const double maxCo = std::atof(argv[3]);
         double dt = sc[7];
+        const double maxDeltaT = argc > 5 ? std::atof(argv[5]) : 1e300;     // controlDict maxDeltaT (readTimeControlsExplicit.H:39-52)
 
         dugks::fvDVM dvm(c);
         std::printf("dugks_run: %d cells, %d faces, %d discrete velocities\n", c.nCells,
@@ -74,7 +76,11 @@ int main(int argc, char** argv) {
         for (int step = 0; step < nSteps; step++) {
             double maxCoNum = 0, meanCoNum = 0;
             dvm.getCoNum(dt, maxCoNum, meanCoNum);                          // CourantNo.H:35
-            if (maxCo > 0) dt = dt * maxCo / (maxCoNum > 0 ? maxCoNum : 1); // setDeltaTvar.H:39-46 (maxDeltaT not limiting)
+            if (maxCo > 0) {                                                // setDeltaTvar.H:34-47: cuts are immediate, growth is damped
+                const double maxDeltaTFact = maxCo / (maxCoNum + 1e-15);   // SMALL
+                const double deltaTFact = std::min(std::min(maxDeltaTFact, 1.0 + 0.1 * maxDeltaTFact), 1.2);
+                dt = std::min(deltaTFact * dt, maxDeltaT);
+            }
             dvm.evolution(dt);                                              // dugksFoam.C:78
             if (step == nSteps - 1 || step % 10 == 0)
                 std::printf("step %d  deltaT = %.9e  Courant max %.6f mean %.6f\n", step + 1, dt, maxCoNum, meanCoNum);

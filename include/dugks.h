@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define DUGKS_ABI_VERSION 1
+#define DUGKS_ABI_VERSION 2
 
 typedef enum dugks_status {
     DUGKS_OK = 0,
@@ -155,15 +155,17 @@ typedef struct dugks_par_t {
     int32_t rank;                /* fieldMPIreducer::rank()                     */
     int32_t nRanks;              /* fieldMPIreducer::nproc()                    */
     int32_t device;              /* CUDA device ordinal, -1 = current device    */
-    int32_t partition;           /* reserved (0): contiguous blocks of the slow DV indices,
+    int32_t partition;           /* reserved, must be 0: contiguous blocks of the slow DV indices,
                                     see dugks_partition */
     dugks_allreduce_fn reduce;
     void* reduce_user;
     const void* nccl_unique_id;  /* 128 bytes or NULL                           */
-    size_t scratch_bytes;        /* cap for per-slab face buffers, 0 = auto     */
+    size_t scratch_bytes;        /* cap (bytes) on the device memory taken for kept face values between the
+                                    two phases of a step; 0 = all free device memory but a reserve.  Slabs
+                                    that do not fit recompute their face values (slower, same results).   */
     int32_t store_h;             /* 1: always carry h; 0: elide h when K+3-D==0 (h==0 exactly,
                                     discreteVelocity.C:1043) */
-    int32_t dv_chunk;            /* reserved (0): a launch slab is 32 velocity rows */
+    int32_t dv_chunk;            /* reserved, must be 0: a launch slab is 32 velocity rows */
 } dugks_par_t;
 
 typedef struct dugks_handle dugks_handle_t;
@@ -259,14 +261,23 @@ int dugks_convergence(dugks_handle_t* h, double change[3]);
  * g,h: [nXi] each, h_ may be NULL. */
 int dugks_get_df(dugks_handle_t* h, int32_t cell, double* g, double* h_);
 
-/* The rank-local slice of the full state, DV-major like the reference's
+/* The rank-local slice of gTildeVol/hTildeVol, DV-major like the reference's
  * PtrList<discreteVelocity>: g[i*nCells + c] for local DV i.  For parity
- * tests and checkpoints that keep the distribution functions (the reference's
- * restart drops them, discreteVelocity.C:220-249).  A bit-exact resume would also
- * need the lagged boundary gradient, the wall densities and q/tau of the cells,
- * which these two calls do not carry yet.  Either pointer may be NULL. */
+ * tests and DF probes; they move the distribution functions only (use
+ * dugks_checkpoint_save/load for a restart).  Either pointer may be NULL. */
 int dugks_get_state(dugks_handle_t* h, double* g, double* h_);
 int dugks_set_state(dugks_handle_t* h, const double* g, const double* h_);
+
+/* Exact restart.  The reference's own restart is lossy: the distribution functions are NO_READ/NO_WRITE
+ * (discreteVelocity.C:74-205), a restarted run re-initialises them to an equilibrium of the saved macros
+ * (:220-249) and the wall density to 1 (calculatedMaxwellFvPatchField.C:80).  The blob holds everything the
+ * next evolution() reads — gTilde/hTilde, boundary-face values (incoming half of "mixed" patches, :556-573),
+ * the lagged boundary gradient (:462-468), cell / face / boundary macros with q and tau, wall constants, the
+ * convergence monitor's old fields — so that save -> load -> step reproduces step bit for bit.  Rank-local and
+ * layout-bound: load checks that case sizes, rank count and rank match.  buf is host memory. */
+int dugks_checkpoint_size(dugks_handle_t* h, uint64_t* bytes);
+int dugks_checkpoint_save(dugks_handle_t* h, void* buf, uint64_t bytes);
+int dugks_checkpoint_load(dugks_handle_t* h, const void* buf, uint64_t bytes);
 
 /* Host-only (no device needed): the global DV ids rank `rank` of `nRanks` owns under the
  * library's partition (contiguous blocks of the slow velocity indices; the reference's

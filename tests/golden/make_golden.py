@@ -7,6 +7,8 @@ demo_cavity_dvset.json : the reference's only golden vector on the hot path —
     demo/cavity/constant/{Xis,weights} (28-point half-range Gauss-Hermite set, also
     printed in doc/usage.tex:114-148) — plus the mesh / case facts of demo/cavity
     (polyMesh/owner header note, polyMesh/boundary, DVMProperties, 0/*).
+demo_cavity_case.npz : the shipped demo/cavity case as data (mesh with its 4-block numbering, quadrature,
+    gas, fields), loaded by tests/parity_util.demo_cavity_case() where the reference tree is not mounted.
 """
 import json
 import os
@@ -44,6 +46,19 @@ def main():
     with open(os.path.join(HERE, "demo_cavity.json"), "w") as f:
         json.dump(out, f, indent=1)
     print("wrote demo_cavity.json")
+    # The shipped case itself, as data (the GPU box has no /root/reference): polyMesh exactly as shipped (point
+    # coordinates, face vertex lists, owner / neighbour with the 4-block blockMesh numbering, patch table), the
+    # quadrature files, DVMProperties values and the initial / boundary fields as read_case() parses them.
+    m = c.mesh
+    np.savez_compressed(
+        os.path.join(HERE, "demo_cavity_case.npz"),
+        points=m.points, face_verts=m.face_verts.astype(np.int32), face_offsets=m.face_offsets.astype(np.int32),
+        owner=m.owner, neighbour=m.neighbour,
+        patch_table=json.dumps([[p.name, p.type, int(p.nFaces), int(p.startFace)] for p in m.patches]),
+        case_patches=json.dumps([[p.name, p.kind, p.start, p.size, p.U_bc, p.T_bc, p.pressure] for p in c.patches]),
+        Xis=c.Xis, weights=c.weights, xiMax=c.xiMax, xiMin=c.xiMin, gas=json.dumps(c.gas),
+        rho=c.rho, U=c.U, T=c.T, rho_b=c.rho_b, U_b=c.U_b, T_b=c.T_b, deltaT=c.deltaT, maxCo=c.maxCo)
+    print("wrote demo_cavity_case.npz", os.path.getsize(os.path.join(HERE, "demo_cavity_case.npz")), "bytes")
 
 
 if __name__ == "__main__":

@@ -53,3 +53,21 @@ def cases_small():
     out.append(("cavity3d_5_gh8_distort", cs.cavity3d_case(5, 8, distort=0.15, perturb=0.01), False))
     out.append(("tri_8_gh8", cs.tri_cavity_case(8, 8, perturb=0.01), False))
     return out
+
+
+def demo_cavity_case():
+    """The reference's shipped demo/cavity (BASELINE config 1) from tests/golden/demo_cavity_case.npz (made by
+    tests/golden/make_golden.py from /root/reference/demo/cavity): 60 x 60 cells in 4 blockMesh blocks, the
+    shipped 28-point Gauss-Hermite set, argon at Kn = 0.075, lid at 50 m/s."""
+    import json
+    import os
+    from dugksfoam_b200.polymesh import Patch, PolyMesh, compute_geometry
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "demo_cavity_case.npz"))
+    mesh = PolyMesh(points=z["points"], face_verts=z["face_verts"], face_offsets=z["face_offsets"], owner=z["owner"],
+                    neighbour=z["neighbour"], patches=[Patch(n, t, k, s) for n, t, k, s in json.loads(str(z["patch_table"]))])
+    geom = compute_geometry(mesh)
+    patches = [cs.PatchSpec(n, k, st, sz, ub, tb, pr) for n, k, st, sz, ub, tb, pr in json.loads(str(z["case_patches"]))]
+    return cs.Case(geom=geom, patches=patches, Xis=z["Xis"], weights=z["weights"], xiMax=float(z["xiMax"]),
+                   xiMin=float(z["xiMin"]), gas=json.loads(str(z["gas"])), rho=z["rho"], U=z["U"], T=z["T"],
+                   rho_b=z["rho_b"], U_b=z["U_b"], T_b=z["T_b"], deltaT=float(z["deltaT"]), maxCo=float(z["maxCo"]),
+                   name="demo/cavity (shipped)", mesh=mesh)

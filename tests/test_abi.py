@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"libdugks.so does not export {n}"
     assert sorted(capi.EXPORTS) == names
-    assert lib.dugks_abi_version() == 1
+    assert lib.dugks_abi_version() == 2
 
 
 def test_no_cpu_fallback():
@@ -69,28 +69,42 @@ def test_row_layout_covers_every_velocity_once():
                 if ny * nz < nranks:
                     continue
                 seen = np.zeros((nz, ny, n), dtype=np.int32)
-                if n > 32 and (ny * nz) // nranks < 32:
-                    # rows longer than 32 points are cut into ix-chunks, which needs >= 32 rows per rank
-                    # (a warp's equilibrium tables span at most two chunks): refused, loudly
-                    with pytest.raises(capi.DugksError):
-                        capi.row_layout(n, D, nranks, 0)
-                    continue
                 for rank in range(nranks):
                     lay = capi.row_layout(n, D, nranks, rank)
-                    L, Lt = lay["L"], lay["Lt"]
+                    L, Lt, nch = lay["L"], lay["Lt"], lay["nch"]
                     assert 1 <= L <= 32 and 0 <= Lt < max(L, 1) + (Lt == 0)
+                    assert nch * L >= n and (nch - 1) * L < n
                     nrows = len(lay["iy"])
                     nslab = (nrows + 31) // 32
                     for k in range(nrows):
                         ln, first = int(lay["len"][k]), int(lay["first"][k])
+                        if ln == 0:          # filler row: keeps a slab to two adjacent ix-chunks, owns no velocity
+                            assert nch > 1
+                            continue
                         in_last = k // 32 == nslab - 1
                         assert ln == (Lt if (Lt > 0 and in_last) else L), (D, n, nranks, rank, k)
                         hi = min(first + ln, n)
                         seen[lay["iz"][k], lay["iy"][k], first:hi] += 1
+                    # rows longer than 32 points are cut into ix-chunks; a slab (one warp's 32 rows) spans at most two
+                    # ADJACENT chunks, whatever the number of rows a rank owns (a warp's tables hold 64 entries)
+                    for s0 in range(0, nrows, 32):
+                        fl = [(int(f), int(l)) for f, l in zip(lay["first"][s0:s0 + 32], lay["len"][s0:s0 + 32]) if l > 0]
+                        firsts = {f for f, _ in fl}
+                        assert max(f + l for f, l in fl) - min(firsts) <= 64, (D, n, nranks, rank, s0, firsts)
+                        if nch > 1:
+                            assert len(firsts) <= 2 and max(firsts) - min(firsts) <= L, (D, n, nranks, rank, s0, firsts)
                     # the DVs of this rank are exactly its partition
                     ids = capi.partition(n, D, nranks, rank)
                     assert ids.size == sum(min(int(f) + int(l), n) - int(f) for f, l in zip(lay["first"], lay["len"]))
                 assert (seen == 1).all(), (D, n, nranks)
+    # BASELINE configs 2 and 5 over 8 GPUs: 101 (81) points per direction, 12-13 (10-11) rows per rank
+    for n in (101, 81):
+        lay = capi.row_layout(n, 2, 8, 3)
+        assert lay["nch"] == 4 and (np.asarray(lay["len"]) > 0).sum() == lay["nch"] * (len(capi.partition(n, 2, 8, 3)) // n)
+        assert len(lay["iy"]) <= 64          # two slabs: chunks (0, 1) and (2, 3)
+    # 1-D with more than 32 points: one row per chunk
+    lay = capi.row_layout(41, 1, 1, 0)
+    assert lay["nch"] == 2 and list(lay["len"]) == [21, 21]
     # the case that motivated the tail slab: 28^3 over 8 ranks = 98 rows = 3 slabs + 2 rows -> short rows of 2
     lay = capi.row_layout(28, 3, 8, 0)
     assert lay["L"] == 28 and lay["Lt"] == 2 and len(lay["iy"]) == 96 + 28

@@ -150,9 +150,10 @@ def test_every_kernel_path(oracle_lib, monkeypatch, path, env):
         dv.close(); orc.close()
 
 
-def test_thousand_steps(oracle_lib):
+@pytest.mark.parametrize("which", ["cavity2d", "cavity3d_perturbed"])
+def test_thousand_steps(oracle_lib, which):
     """1e-9 on rho/U/T/q after 1000 steps (north_star)."""
-    case = cs.cavity2d_case(10, 8)
+    case = cs.cavity2d_case(10, 8) if which == "cavity2d" else cs.cavity3d_case(5, 8, distort=0.1, perturb=0.01)
     dv = capi.fvDVM(case)
     orc = oracle_lib.Oracle(case)
     dt = case.courant_dt(0.8)
@@ -216,17 +217,171 @@ def test_fails_loudly_on_bad_input():
         capi.fvDVM(case)
 
 
-@pytest.mark.xfail(strict=False, reason="written after this round's GPU budget was spent: not yet run on a device "
-                                        "(XPASS = parity holds for chunked rows; remove the mark then)")
-@pytest.mark.parametrize("quad,nDV", [("NC", 37), ("GH", 36)])
-def test_chunked_rows_parity(oracle_lib, quad, nDV):
-    """More than 32 velocity points per direction (BASELINE config 2 has 101): rows are cut into ix-chunks."""
-    case = cs.cavity2d_case(10, nDV, quad=quad, perturb=0.01)
+_CHUNKED = [
+    # (label, case builder, environment): more than 32 velocity points per direction -> rows are cut into ix-chunks
+    ("nc37", lambda: cs.cavity2d_case(10, 37, quad="NC", perturb=0.01), {}),
+    ("nc101_cfg2_grid", lambda: cs.cavity2d_case(6, 101, quad="NC", perturb=0.01), {}),          # BASELINE config 2's velocity grid
+    ("nc41_ties", lambda: cs.cavity2d_case(7, 41, quad="NC", xiMax=1600.0, perturb=0.01), {}),    # xi = 0 abscissa: ties on every axis-aligned face
+    ("gh28_forced_2_chunks", lambda: cs.cavity2d_case(10, 28, perturb=0.01), {"DUGKS_NCH": "2"}),
+    ("gh40_stable_recurrence", lambda: cs.cavity2d_case(6, 40, quad="GHs", perturb=0.01), {}),
+    ("nc37_3d", lambda: _cavity3d_nc(4, 33), {}),
+    ("nc41_distorted", lambda: cs.cavity2d_case(6, 41, quad="NC", distort=0.2, perturb=0.01), {}),
+]
+
+
+def _cavity3d_nc(n, nDV):
+    from dugksfoam_b200 import dvset
+    from dugksfoam_b200.polymesh import hex_block
+    Xis, w = dvset.dvNC(4.0 * np.sqrt(2 * cs.ARGON["R"] * cs.T0), nDV)
+    return cs._uniform_case(hex_block(n, n, n, (1.0, 1.0, 1.0)), Xis, w, {}, name=f"cavity3d_{n}_NC{nDV}", perturb=0.01)
+
+
+@pytest.mark.parametrize("label,build,env", _CHUNKED, ids=[c[0] for c in _CHUNKED])
+def test_chunked_rows_parity(oracle_lib, monkeypatch, label, build, env):
+    """More than 32 velocity points per direction (BASELINE config 2 has 101, config 5 about 80)."""
+    monkeypatch.delenv("DUGKS_NCH", raising=False)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    case = build()
     dv = capi.fvDVM(case)
     orc = oracle_lib.Oracle(case)
     dt = case.courant_dt(0.5)
     for step in range(3):
         dv.evolution(dt)
         orc.step(dt)
-        _compare(dv, orc, case, util.TOL_STEP * (step + 1), f"chunked {quad}{nDV} step {step + 1}")
+        _compare(dv, orc, case, util.TOL_STEP * (step + 1), f"chunked {label} step {step + 1}")
     dv.close(); orc.close()
+
+
+def test_shipped_demo_cavity(oracle_lib):
+    """BASELINE config 1: the reference's own demo/cavity (shipped polyMesh with its 4-block numbering, shipped
+    Xis/weights, DVMProperties, 0/*; tests/golden/demo_cavity_case.npz), stepped as dugksFoam steps it: the first
+    step at the controlDict deltaT, then the Courant-limited one (setDeltaTvar.H:34-47)."""
+    case = util.demo_cavity_case()
+    assert (case.nCells, case.nXi) == (3600, 784)
+    dv = capi.fvDVM(case)
+    orc = oracle_lib.Oracle(case)
+    dt = case.courant_dt(case.maxCo)
+    assert abs(dt - 5.3e-6) < 1e-7                  # doc: about 5.3e-6 s from step 2 on (SURVEY.md section 6)
+    _compare(dv, orc, case, util.TOL_STEP, "demo/cavity init")
+    for step in range(5):
+        dv.evolution(dt)
+        orc.step(dt)
+        errs = _compare(dv, orc, case, util.TOL_STEP * (step + 1), f"demo/cavity step {step + 1}")
+    assert np.allclose(dv.getCoNum(dt), orc.courant(dt), rtol=1e-10)
+    # closed cavity, diffuse walls: total mass is conserved to round-off (SURVEY.md section 4)
+    m0 = float((case.rho * case.geom.V).sum())
+    m5 = float((dv.cell_macros()["rho"] * case.geom.V).sum())
+    assert abs(m5 - m0) <= 1e-12 * m0, (m0, m5)
+    dv.close(); orc.close()
+
+
+def _hypersonic_channel(nDV=29, nx=10, ny=6):
+    """Free stream at Ma = 5 (argon, 273 K: a = 307.8 m/s) through far-field in / zeroGradient out, fixedValue-rho
+    ("mixed") top, Maxwell wall bottom; Newton-Cotes grid wide enough for the shifted Maxwellian."""
+    from dugksfoam_b200 import dvset
+    from dugksfoam_b200.polymesh import hex_block
+    K = cs
+    Uinf = 5.0 * np.sqrt(5.0 / 3.0 * K.ARGON["R"] * K.T0)
+    names = {"xmin": "inlet", "xmax": "outlet", "ymin": "bottom", "ymax": "top"}
+    mesh = hex_block(nx, ny, 1, (1.0, 0.6, 0.1), two_d=True, patch_names=names, distort=0.1)
+    Xis, w = dvset.dvNC(3200.0, nDV)
+    return cs._uniform_case(
+        mesh, Xis, w, {"inlet": K.PATCH_FAR_FIELD, "outlet": K.PATCH_ZERO_GRADIENT, "top": K.PATCH_MIXED}, lid_patch="none",
+        U0=(Uinf, 0.0, 0.0), name="ma5_channel", perturb=0.01,
+        bc_overrides={"inlet": dict(U=(Uinf, 0, 0), U_bc=K.BC_ZERO_GRADIENT), "top": dict(U=(Uinf, 0, 0))}), Uinf
+
+
+def test_hypersonic_free_stream(oracle_lib):
+    """Ma = 5 (BASELINE config 5's regime): the CUDA path forms U, T and the centred heat flux from RAW moments
+    about zero and centres them algebraically; the oracle sums (xi - U) directly as fvDVM.C:503-516 does.
+    The raw third moment is (U / c)^3 ~ 100 times the heat-flux scale here: the 1e-12 budget must survive it."""
+    case, Uinf = _hypersonic_channel()
+    dv = capi.fvDVM(case)
+    orc = oracle_lib.Oracle(case)
+    dt = case.courant_dt(0.5)
+    for step in range(4):
+        dv.evolution(dt)
+        orc.step(dt)
+        errs = _compare(dv, orc, case, util.TOL_STEP * (step + 1), f"Ma 5 step {step + 1}")
+    m = dv.cell_macros()
+    assert np.abs(m["U"][:, 0] - Uinf).max() < 0.5 * Uinf and np.isfinite(m["q"]).all()
+    dv.close(); orc.close()
+
+
+def test_symmetry_patch_on_every_axis(oracle_lib):
+    """DVMsymmetry / symmetryPlane patches with x- and y-normals on one rank (the sharded variants are in
+    tests/test_multi_gpu.py)."""
+    K = cs
+    for kinds in ({"bottom": K.PATCH_DVM_SYMMETRY, "inlet": K.PATCH_DVM_SYMMETRY}, {"top": K.PATCH_SYMMETRY_PLANE},
+                  {"outlet": K.PATCH_DVM_SYMMETRY, "bottom": K.PATCH_SYMMETRY_PLANE}):
+        ov = {} if "top" in kinds else {"top": dict(U=(40.0, 0, 0))}
+        case = util.channel_case(8, 6, 8, kinds=kinds, bc_overrides=ov, perturb=0.01)
+        dv = capi.fvDVM(case)
+        orc = oracle_lib.Oracle(case)
+        dt = case.courant_dt(0.5)
+        for step in range(3):
+            dv.evolution(dt)
+            orc.step(dt)
+            _compare(dv, orc, case, util.TOL_STEP * (step + 1), f"symmetry {sorted(kinds)} step {step + 1}")
+        dv.close(); orc.close()
+
+
+def test_checkpoint_resume_is_bit_exact():
+    """dugks_checkpoint_save/load: a fresh handle restored from the blob continues with the same bits (the
+    reference's own restart re-initialises the distribution functions, discreteVelocity.C:220-249)."""
+    K = cs
+    zoo = [cs.cavity3d_case(6, 8, perturb=0.01),
+           util.channel_case(10, 6, 8, kinds={"inlet": K.PATCH_FAR_FIELD, "outlet": K.PATCH_ZERO_GRADIENT, "top": K.PATCH_MIXED},
+                             bc_overrides={"inlet": dict(U=(30.0, 0, 0), rho=1.2 * K.RHO0, T=290.0, U_bc=K.BC_ZERO_GRADIENT),
+                                           "top": dict(U=(20.0, 0, 0), T=280.0)}, perturb=0.01)]
+    for case in zoo:
+        dt = case.courant_dt(0.5)
+        a = capi.fvDVM(case)
+        for _ in range(3):
+            a.evolution(dt)
+        blob = a.checkpoint()
+        conv_a0 = a.convergence()
+        for _ in range(2):
+            a.evolution(dt * 1.1)
+        b = capi.fvDVM(case)                       # starts from the t = 0 fields, then takes the blob
+        b.restore(blob)
+        conv_b0 = b.convergence()
+        for _ in range(2):
+            b.evolution(dt * 1.1)
+        assert conv_a0 == conv_b0
+        ma, mb = a.cell_macros(), b.cell_macros()
+        for k in ma:
+            assert np.array_equal(ma[k], mb[k]), k
+        fa, fb = a.face_macros(), b.face_macros()
+        for k in fa:
+            assert np.array_equal(fa[k], fb[k]), k
+        (ga, ha), (gb, hb) = a.state(), b.state()
+        assert np.array_equal(ga, gb) and np.array_equal(ha, hb)
+        assert all(np.array_equal(x, y) for x, y in zip(a.boundary_surf(), b.boundary_surf()))
+        wa, wb = a.wall_diag(), b.wall_diag()
+        assert np.array_equal(wa["qWall"], wb["qWall"]) and np.array_equal(a.boundary_macros()["rho"], b.boundary_macros()["rho"])
+        assert a.getCoNum(dt) == b.getCoNum(dt)
+        # a blob of another case is refused
+        other = capi.fvDVM(cs.cavity2d_case(6, 8))
+        with pytest.raises(capi.DugksError, match="another case"):
+            other.restore(blob)
+        other.close(); a.close(); b.close()
+
+
+def test_scratch_bytes_caps_the_face_storage():
+    """dugks_par_t.scratch_bytes bounds the memory taken for kept face values; the result does not depend on it."""
+    case = cs.cavity3d_case(6, 28, perturb=0.01)          # 25 slabs of 216 cells
+    free = capi.fvDVM(case)
+    st = free.stats()
+    assert st["keep_slabs"] == st["n_slabs"]
+    per_slab = case.geom.nInternalFaces * st["slab_dvs"] * 8
+    capped = capi.fvDVM(case, scratch_bytes=int(3.5 * per_slab) + case.nCells * st["slab_dvs"] * 8 * st["n_slabs"])
+    sc = capped.stats()
+    assert 0 < sc["keep_slabs"] < st["n_slabs"] and sc["device_bytes"] < st["device_bytes"]
+    dt = case.courant_dt(0.5)
+    for _ in range(2):
+        free.evolution(dt); capped.evolution(dt)
+    a, b = free.cell_macros(), capped.cell_macros()
+    assert util.rel_err(a["rho"], b["rho"]) <= 1e-13 and util.rel_err(a["T"], b["T"]) <= 1e-13
+    free.close(); capped.close()

@@ -47,12 +47,13 @@ def test_host_driver_matches_oracle(runner, tmp_path, oracle_lib):
     raw = np.fromfile(outf, dtype=np.float64)
     nc = case.nCells
     rho, U, T, q = raw[:nc], raw[nc:4 * nc].reshape(nc, 3), raw[4 * nc:5 * nc], raw[5 * nc:8 * nc].reshape(nc, 3)
-    # the same adaptive-dt loop on the oracle (setDeltaTvar.H:39-46)
+    # the same adaptive-dt loop on the oracle (setDeltaTvar.H:34-47: cuts immediate, growth damped to x1.2)
     orc = oracle_lib.Oracle(case)
     dt = case.deltaT or case.courant_dt(0.5)
     for _ in range(nsteps):
         maxCo, _mean = orc.courant(dt)
-        dt = dt * 0.5 / maxCo
+        fact = 0.5 / (maxCo + 1e-15)
+        dt = min(min(fact, 1.0 + 0.1 * fact), 1.2) * dt
         orc.step(dt)
     m = orc.cell_macros()
     sc = util.macro_scales(case)
