@@ -30,6 +30,7 @@ WORKLOADS = {
     # name: (builder, args)
     "cavity3d_64_gh28": ("cavity3d", dict(n=64, nDV=28)),            # BASELINE configs[2] (headline)
     "cavity2d_256_nc101": ("cavity2d", dict(n=256, nDV=101, quad="NC")),  # BASELINE configs[1]
+    "cavity3d_48_gh28": ("cavity3d", dict(n=48, nDV=28)),            # profiling size: every slab keeps its face values, ncu can replay
     "cavity3d_32_gh28": ("cavity3d", dict(n=32, nDV=28)),
     "cavity3d_16_gh16": ("cavity3d", dict(n=16, nDV=16)),
     "cavity2d_60_gh28": ("cavity2d", dict(n=60, nDV=28)),            # demo/cavity shape

@@ -1277,7 +1277,7 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
     {
         unsigned char* d_c = nullptr;
         TRYB(dev_upload(h, &d_c, cell_cls)); A.cell_cls = d_c;
-        // traversal order of the cell kernels (build_cell_order): DUGKS_ORDER = tiled (default) | wave | morton | natural
+        // traversal order of the cell kernels (build_cell_order): DUGKS_ORDER = wave (default) | tiled | morton | natural
         h->want_split = 2 * (long long)h->n_axis > nc && getenv("DUGKS_NO_SPLIT_AXIS") == nullptr;
         const char* ord_env = getenv("DUGKS_ORDER");
         int dev_sms = 148;
@@ -1287,7 +1287,7 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
         int tile = 0;
         if (const char* e = getenv("DUGKS_TILE")) tile = std::max(1, atoi(e));
         std::vector<int> order;
-        build_cell_order(nc, D, mesh->C, h->want_split ? cell_cls.data() : nullptr, ord_env ? ord_env : "tiled", tile, nwarps, order);
+        build_cell_order(nc, D, mesh->C, h->want_split ? cell_cls.data() : nullptr, ord_env ? ord_env : "wave", tile, nwarps, order);
         // per-cell record (CMETA_N ints) in traversal order: everything a warp needs to start a cell in one load level
         std::vector<int> cmeta((size_t)nc * CMETA_N, 0);
         for (int item = 0; item < nc; item++) {

@@ -1262,24 +1262,30 @@ k_hot_update(StepArgs a) {
 // by the two cells that share the face; each relaxes it to g_f with the face equilibrium
 // (discreteVelocity.C:867-881) and adds its flux (:934-978).  Boundary-face values come relaxed from
 // k_bnd_relax.  Replaces k_hot_outgoing<2> + k_hot_update and their flux buffer round trip.
-// WMODE: the cell stream is w = -1/3 gTilde + 4/3 gBarP, left in place of gTilde by the half-step kernel
+// WMODE 1: the cell stream is w = -1/3 gTilde + 4/3 gBarP, left in place of gTilde by the half-step kernel
 // (one stream and 8 bytes per update less; gBarP of the slab need not outlive phase 1).
-template <bool HAS_H, int NE, int TW, int CI, bool WMODE = false>
+// WMODE 2: the cell stream is gTilde itself and w is formed here, gBarP = (1 - rf) gTilde + rf gS from the cell's
+// macros of the step start (discreteVelocity.C:393-406; they are only replaced after phase 2): slabs whose phase 1
+// applied the half step on the fly (dugks_pencil.cuh) never wrote gBarP or w.  Same operations as
+// k_hot_halfstep + hot_w_combine, so the bits are those of WMODE 1.
+template <bool HAS_H, int NE, int TW, int CI, int WMODE = 0>
 struct HotRelaxPlan {
     static constexpr int NFLD = HAS_H ? 2 : 1;
     static constexpr int NPRE = WMODE ? 1 : 2;
     static constexpr int NSLOT = NPRE + NE;
     static constexpr int STAGE_D = NFLD * NSLOT * CI * 32;
+    static constexpr int NTABS = WMODE == 2 ? NE + 1 : NE;   // one more equilibrium table: the cell's own
     // the moment reduction (32 x 17 doubles) runs through the face tables, which are dead by then
-    static constexpr int TAB_D = (NE * 4 * TW + NE * 2) > 32 * 17 ? (NE * 4 * TW + NE * 2) : 32 * 17;
-    static constexpr int REC_D = NE * (FCOEF_N + 4);     // face equilibrium records + outward area vectors of a cell
+    static constexpr int TAB_D = (NTABS * 4 * TW + NE * 2) > 32 * 17 ? (NTABS * 4 * TW + NE * 2) : 32 * 17;
+    // face equilibrium records + outward area vectors of a cell (+ the cell's macro record, WMODE 2)
+    static constexpr int REC_D = NE * (FCOEF_N + 4) + (WMODE == 2 ? 10 : 0);
     static constexpr int PER_WARP_D = 2 * HOT_PTRS + 2 * REC_D + HOT_STAGES * STAGE_D + TAB_D;
     static constexpr size_t PER_WARP = ((size_t)PER_WARP_D * 8 + 127) / 128 * 128;
     static __host__ __device__ size_t txs_bytes(int ntab) { return ((size_t)(ntab + HOT_CI_MAX) * 48 + 127) / 128 * 128; }
     static __host__ size_t total(int ntab) { return txs_bytes(ntab) + HOT_WARPS * PER_WARP; }
 };
 
-template <bool HAS_H, int NE, int TW, int CI, bool WMODE>
+template <bool HAS_H, int NE, int TW, int CI, int WMODE>
 __global__ void __launch_bounds__(HOT_WARPS * 32, HOT_MINB(CI))
 k_hot_relax_update(StepArgs a) {
     using P = HotRelaxPlan<HAS_H, NE, TW, CI, WMODE>;
@@ -1294,8 +1300,9 @@ k_hot_relax_update(StepArgs a) {
     unsigned long long* sptr = reinterpret_cast<unsigned long long*>(wbase);
     double* recs = reinterpret_cast<double*>(wbase) + 2 * HOT_PTRS;   // [2][NE][FCOEF_N] | [NE][4] per buffer
     double* stages = recs + 2 * P::REC_D;
-    double* xtab = stages + HOT_STAGES * P::STAGE_D;       // [NE][TW][4]
-    double* unic = xtab + NE * 4 * TW;                     // [NE][2] omrf, RT
+    double* xtab = stages + HOT_STAGES * P::STAGE_D;       // [NTABS][TW][4]
+    double* unic = xtab + P::NTABS * 4 * TW;               // [NE][2] omrf, RT
+    double* ctab = xtab + NE * 4 * TW;                     // WMODE 2: [TW][4] half-step table of the cell
     __syncthreads();
 
     const size_t slab_c = (size_t)a.slab * nc * blk, slab_b = (size_t)a.slab * a.m.nbf * blk;
@@ -1335,6 +1342,9 @@ k_hot_relax_update(StepArgs a) {
                     cp_async16(sd + NE * FCOEF_N * 8 + pe * 16, reinterpret_cast<const char*>(a.geoS + (size_t)M.e0 * 4) + pe * 16);
             }
         }
+        if (WMODE == 2 && lane < MAC_N)   // macro record of the cell (72 bytes, 8-byte aligned)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sd + (NE * (FCOEF_N + 4) + lane) * 8),
+                         "l"(a.cmac + (size_t)M.c * MAC_N + lane));
     };
     const unsigned long long pol_ef = l2_evict_first_policy();
     const unsigned long long pol_el = l2_evict_last_policy();
@@ -1388,7 +1398,7 @@ k_hot_relax_update(StepArgs a) {
 #pragma unroll
             for (int fld = 0; fld < P::NFLD; fld++) {
                 hot_stage_one_ef<CI>(sdst + (fld * NSLOT + 0) * (CI * 256), fld ? hts : gts, offc, coff, pol_ef);
-                if (!WMODE) hot_stage_one_ef<CI>(sdst + (fld * NSLOT + 1) * (CI * 256), fld ? hbs : gbs, offc, coff, pol_ef);
+                if (WMODE == 0) hot_stage_one_ef<CI>(sdst + (fld * NSLOT + 1) * (CI * 256), fld ? hbs : gbs, offc, coff, pol_ef);
 #pragma unroll
                 for (int j = 0; j < NE; j++)   // every face block is read by two cells: keep it in L2 for the second one
                     hot_stage_one_ef<CI>(sdst + (fld * NSLOT + NPRE + j) * (CI * 256), fld ? fk_h : fk_g, offf[j], coff, pol_el);
@@ -1426,6 +1436,26 @@ k_hot_relax_update(StepArgs a) {
                 QYZ[j] = cy * qy + cz * qz;
                 if (lane == 0) { unic[j * 2] = fc[8]; unic[j * 2 + 1] = fc[9]; }
             }
+        }
+        // WMODE 2: half-step table of the cell itself (the operations of k_hot_halfstep)
+        double cEYZ = 0.0, cYZ2 = 0.0, cQYZ = 0.0, comrf = 0.0, cRT = 0.0;
+        if (WMODE == 2) {
+            const double* mc = rec_s + NE * 4;
+            const double rf = 1.5 * a.dt / (2.0 * mc[5] + a.dt);         // discreteVelocity.C:393
+            const EqCoef e = make_eq(a.gas, mc, rf);
+            for (int tt = lane; tt < span; tt += 32) {
+                const double cx = txs[(tmin + tt) * 6 + 5] - e.Ux;
+                const double x2 = cx * cx * e.a;
+                double* xt = ctab + tt * 4;
+                xt[0] = exp(-0.5 * x2); xt[1] = x2; xt[2] = cx * e.qx; xt[3] = 0.0;
+            }
+            const double cy = y - e.Uy, cz = z - e.Uz;
+            const double yz2 = (cy * cy + cz * cz) * e.a;
+            cEYZ = e.pre * exp(-0.5 * yz2);
+            cYZ2 = yz2 - a.gas.D - 2.0;
+            cQYZ = cy * e.qy + cz * e.qz;
+            comrf = 1.0 - rf;
+            cRT = e.RT;
         }
         __syncwarp();
         const double dtv = a.dt / a.m.V[c];
@@ -1482,7 +1512,18 @@ k_hot_relax_update(StepArgs a) {
                 }
 #pragma unroll
                 for (int u = 0; u < CI; u++) {
-                    const double wcell = WMODE ? sf[u * 32] : hot_w_combine(sf[u * 32], sf[(CI + u) * 32]);
+                    double wcell;
+                    if (WMODE == 1) wcell = sf[u * 32];
+                    else if (WMODE == 0) wcell = hot_w_combine(sf[u * 32], sf[(CI + u) * 32]);
+                    else {
+                        const double* xt = ctab + (size_t)(tb + u - tmin) * 4;
+                        const double2 x01 = lds2(xt);
+                        const double cc = x01.y + cYZ2, cq = xt[2] + cQYZ, gM = x01.x * cEYZ;
+                        const double t_i = sf[u * 32];
+                        const double b_i = fld == 0 ? fma(comrf, t_i, fma(cq, cc, 1.0) * gM)                                      // :405,1042
+                                                    : fma(comrf, t_i, (kd + cq * ((cc + 2.0) * kd - 2.0 * a.gas.K)) * gM * cRT);   // :406,1043
+                        wcell = hot_w_combine(t_i, b_i);
+                    }
                     const double vnew = fma(-sum[u], dtv, wcell);                                      // :937,952
                     if (i0 + u >= Ln) continue;   // tail chunk (warp-uniform)
                     __stcs((fld == 0 ? gdst : hdst) + (i0 + u) * 32, vnew);
@@ -1533,7 +1574,8 @@ struct HotHalfPlan {
 
 template <bool HAS_H>
 __global__ void __launch_bounds__(HOT_WARPS * 32, 4)
-k_hot_halfstep(StepArgs a, int tw, int wmode /* also leave w = -1/3 gTilde + 4/3 gBarP in place of gTilde */) {
+k_hot_halfstep(StepArgs a, int tw, int wmode /* also leave w = -1/3 gTilde + 4/3 gBarP in place of gTilde */,
+               const int* list /* cells to convert, or null: all */, int nlist) {
     using P = HotHalfPlan<HAS_H>;
     extern __shared__ __align__(128) unsigned char dyn[];
     const DevDV& dv = a.dv;
@@ -1574,11 +1616,13 @@ k_hot_halfstep(StepArgs a, int tw, int wmode /* also leave w = -1/3 gTilde + 4/3
                          "l"(a.cmac + (size_t)c * MAC_N + lane));
     };
     const int nw = gridDim.x * HOT_WARPS;
-    int c = blockIdx.x * HOT_WARPS + wib, buf = 0;
-    if (c < nc) stage_cell(c, 0);
+    const int nitems = list ? nlist : nc;
+    int idx = blockIdx.x * HOT_WARPS + wib, buf = 0;
+    if (idx < nitems) stage_cell(list ? list[idx] : idx, 0);
     cp_async_commit();
-    for (; c < nc; c += nw, buf ^= 1) {
-        if (c + nw < nc) stage_cell(c + nw, buf ^ 1);
+    for (; idx < nitems; idx += nw, buf ^= 1) {
+        const int c = list ? list[idx] : idx;
+        if (idx + nw < nitems) stage_cell(list ? list[idx + nw] : idx + nw, buf ^ 1);
         cp_async_commit();
         cp_async_wait<1>();
         __syncwarp();

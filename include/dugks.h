@@ -296,8 +296,8 @@ int dugks_row_layout(int32_t nXiPerDim, int32_t nSolutionD, int32_t nRanks, int3
                      int32_t* row_iy, int32_t* row_iz, int32_t* row_first, int32_t* row_len);
 
 /* Host-only (no device needed): the order in which the cell kernels walk the mesh, a
- * permutation of the cells computed from the cell centres C [nCells][3].  kind: "tiled" (what dugks_create
- * uses unless DUGKS_ORDER says otherwise), "wave", "morton" or "natural"; nWarps: persistent warps in flight
+ * permutation of the cells computed from the cell centres C [nCells][3].  kind: "wave" (what dugks_create
+ * uses unless DUGKS_ORDER says otherwise), "tiled", "morton" or "natural"; nWarps: persistent warps in flight
  * (only "wave" uses it); first_class (may be NULL): cells with a non-zero entry come first, as the axis-only
  * launch of phase 1 needs them.  The reference walks cells in label order (discreteVelocity.C:346-410 and the
  * face loops :491-530, :948-956); any order gives the same result. */

@@ -107,7 +107,7 @@ _PATHS = [
     ("no_split", {"DUGKS_NO_SPLIT_AXIS": "1"}),         # axis-aligned cells inside the unified phase-1 launch
     ("no_wmode", {"DUGKS_NO_WMODE": "1"}),              # face-storage slabs with persistent gBarP (update reads gTilde, gBarP)
     ("no_wmode_keep_one", {"DUGKS_NO_WMODE": "1", "DUGKS_KEEP_SLABS": "1"}),
-    ("order_wave", {"DUGKS_ORDER": "wave"}),            # x-wavefront traversal (opt-in, dugks_cell_order)
+    ("order_tiled", {"DUGKS_ORDER": "tiled"}),          # strips of rows (the default is the x-wavefront order, dugks_cell_order)
     ("order_natural", {"DUGKS_ORDER": "natural"}),
     ("gen1_tma", {"DUGKS_NO_HOT": "1"}),                # first-generation bulk-copy kernels
     ("gen1_ldg", {"DUGKS_NO_HOT": "1", "DUGKS_NO_TMA": "1"}),
@@ -269,10 +269,13 @@ def test_shipped_demo_cavity(oracle_lib):
         orc.step(dt)
         errs = _compare(dv, orc, case, util.TOL_STEP * (step + 1), f"demo/cavity step {step + 1}")
     assert np.allclose(dv.getCoNum(dt), orc.courant(dt), rtol=1e-10)
-    # closed cavity, diffuse walls: total mass is conserved to round-off
+    # closed cavity, diffuse walls: internal fluxes cancel, the total mass only feels the (tiny) wall-flux
+    # imbalance of the scheme (tests/test_oracle.py::test_mass_change_equals_boundary_flux_only) - and it is the
+    # oracle's mass to round-off
     m0 = float((case.rho * case.geom.V).sum())
     m5 = float((dv.cell_macros()["rho"] * case.geom.V).sum())
-    assert abs(m5 - m0) <= 1e-12 * m0, (m0, m5)
+    m5o = float((orc.cell_macros()["rho"] * case.geom.V).sum())
+    assert abs(m5 - m0) <= 1e-6 * m0 and abs(m5 - m5o) <= 5e-12 * m0, (m0, m5, m5o)
     dv.close(); orc.close()
 
 
