@@ -51,7 +51,8 @@ class ParT(C.Structure):
 class StatsT(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("steps", C.c_uint64),
                 ("device_bytes", C.c_uint64), ("h_elided", C.c_int32), ("n_slabs", C.c_int32),
-                ("slab_dvs", C.c_int32), ("keep_slabs", C.c_int32)]
+                ("slab_dvs", C.c_int32), ("keep_slabs", C.c_int32), ("pencil_cells", C.c_int32),
+                ("pencil_mode", C.c_int32)]
 
 
 def dptr(a: Optional[np.ndarray]):

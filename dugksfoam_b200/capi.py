@@ -33,7 +33,7 @@ EXPORTS = ["dugks_abi_version", "dugks_nccl_unique_id", "dugks_create", "dugks_d
            "dugks_get_df", "dugks_get_state", "dugks_set_state", "dugks_local_dvs", "dugks_sizes",
            "dugks_get_stats", "dugks_stream", "dugks_kernel_timing", "dugks_partition",
            "dugks_get_boundary_df", "dugks_row_layout", "dugks_convergence", "dugks_cell_order",
-           "dugks_checkpoint_size", "dugks_checkpoint_save", "dugks_checkpoint_load"]
+           "dugks_checkpoint_size", "dugks_checkpoint_save", "dugks_checkpoint_load", "dugks_pencil_plan"]
 
 
 class DugksError(RuntimeError):
@@ -45,7 +45,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     src = os.path.join(_HERE, "csrc", "dugks_capi.cu")
     deps = [src, os.path.join(_HERE, "csrc", "dugks_kernels.cuh"), os.path.join(_HERE, "csrc", "dugks_device.cuh"),
             os.path.join(_HERE, "csrc", "dugks_fast.cuh"), os.path.join(_HERE, "csrc", "dugks_tma.cuh"),
-            os.path.join(_HERE, "csrc", "dugks_hot.cuh"),
+            os.path.join(_HERE, "csrc", "dugks_hot.cuh"), os.path.join(_HERE, "csrc", "dugks_pencil.cuh"),
             os.path.join(_HERE, "..", "include", "dugks.h")]
     if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(d) for d in deps):
         return LIB_PATH
@@ -93,6 +93,7 @@ def load_library():
     L.dugks_get_boundary_df.argtypes = [C.c_void_p, c_double_p, c_double_p]
     L.dugks_row_layout.argtypes = [C.c_int32] * 4 + [c_int32_p] * 8
     L.dugks_cell_order.argtypes = [C.c_int32, C.c_int32, c_double_p, C.POINTER(C.c_uint8), C.c_char_p, C.c_int32, c_int32_p]
+    L.dugks_pencil_plan.argtypes = [C.POINTER(MeshT), C.c_int32, c_int32_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p]
     L.dugks_checkpoint_size.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     L.dugks_checkpoint_save.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
     L.dugks_checkpoint_load.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
@@ -143,6 +144,21 @@ def cell_order(centres: np.ndarray, nSolutionD: int, kind: str = "tiled", nWarps
     if rc:
         raise DugksError(f"dugks_cell_order failed ({rc}): {L.dugks_last_error(None).decode()}")
     return out
+
+
+def pencil_plan(case: Case, nCtas: int = 296) -> dict:
+    """CTA-pencil plan of phase 1 (host-only, needs no device): see dugks_pencil_plan."""
+    L = load_library()
+    m = Marshalled(case)
+    ni, npc = C.c_int32(0), C.c_int32(0)
+    nax = C.c_int32(0)
+    rc = L.dugks_pencil_plan(C.byref(m.mesh), nCtas, C.byref(ni), C.byref(npc), None, None, None, C.byref(nax))
+    if rc:
+        raise DugksError(f"dugks_pencil_plan failed ({rc}): {L.dugks_last_error(None).decode()}")
+    cells = np.empty(npc.value, dtype=np.int32)
+    first, steps = np.empty(ni.value, dtype=np.int32), np.empty(ni.value, dtype=np.int32)
+    L.dugks_pencil_plan(C.byref(m.mesh), nCtas, C.byref(ni), C.byref(npc), iptr(cells), iptr(first), iptr(steps), None)
+    return dict(cells=cells, item_first=first, item_steps=steps, n_axis=nax.value)
 
 
 def nccl_unique_id() -> bytes:

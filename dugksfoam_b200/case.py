@@ -213,9 +213,11 @@ def cavity2d_case(n: int, nDV: int = 28, quad: str = "GH", *, distort: float = 0
 
 
 def cavity3d_case(n: int, nDV: int = 28, *, distort: float = 0.0, perturb: float = 0.0,
-                  name: Optional[str] = None) -> Case:
-    """3-D lid-driven cavity n^3 hexes on [0,1]^3, six Maxwell walls, lid = top (BASELINE config 3)."""
-    mesh = hex_block(n, n, n, (1.0, 1.0, 1.0), distort=distort)
+                  name: Optional[str] = None, length: float = 1.0) -> Case:
+    """3-D lid-driven cavity n^3 hexes on [0,length]^3, six Maxwell walls, lid = top (BASELINE config 3).
+    With n a power of two (or length = n / 2^k) the point coordinates are exact binary fractions, the
+    geometry formulas give exact zeros and the cells are recognised as axis-aligned."""
+    mesh = hex_block(n, n, n, (length, length, length), distort=distort)
     Xis, w = gh_set(nDV)
     return _uniform_case(mesh, Xis, w, {}, name=name or f"cavity3d_{n}^3_GH{nDV}", perturb=perturb)
 

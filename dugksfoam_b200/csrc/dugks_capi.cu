@@ -2,6 +2,7 @@
 // sm_100a kernels in dugks_kernels.cuh.  No CPU fallback: every entry point needs a
 // CUDA device and fails loudly (DUGKS_ERR_NO_DEVICE) without one.
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -13,6 +14,7 @@
 
 #include "../../include/dugks.h"
 #include "dugks_hot.cuh"
+#include "dugks_pencil.cuh"
 
 // ------------------------------------------------------------------------------
 // NCCL through dlopen (the library is present in every torch install and on the
@@ -138,6 +140,16 @@ struct dugks_handle {
     size_t hsmem_axis = 0;
     std::vector<char> slab_pair_ok;   // per slab: the axis-only launch of phase 1 is valid (hot_axis_item)
     int n_axis = 0, axis_ne = 0;
+    // CTA pencils of phase 1 (dugks_pencil.cuh): 2 x 2 bundles of x-lines of axis-aligned interior cells
+    int pen_mode = 0;                  // 0 off, 1 pencil reads gBarP, 2 fused: the pencil applies the half step itself
+    int n_pen = 0;                     // traversal items [0, n_pen) are pencil cells, [n_pen, n_axis) the other axis-aligned cells
+    PenArgs pen{};
+    int pen_grid = 0;
+    size_t pen_smem = 0;
+    int* d_halflist = nullptr;         // fused mode: cells whose gBarP the other kernels still read (non-pencil cells + their neighbours)
+    int n_halflist = 0;
+    size_t hsmem_rlx_g = 0;            // relax+update that forms w from gTilde (WMODE 2)
+    int hot_grid_rlx_g = 148;
     // face-storage slabs: phase 1 keeps the reconstructed face values of slabs [0, n_keep) so that
     // phase 2 is ONE fused relax+update pass for them (no second gradient, no flux-buffer round trip)
     int n_keep = 0;
@@ -250,6 +262,14 @@ constexpr int CI_OUT1 = DUGKS_CI_OUT1, CI_OUT2 = 2, CI_RLX = 2;
 constexpr int CI_AXIS = DUGKS_CI_AXIS;
 // update kernel of the flux-buffer path: 4 points per chunk, 2 when h doubles the streams (shared memory per CTA)
 #define CI_UPD (H ? 2 : 4)
+// How phase 1 of a slab treats the pencil cells: 0 = no pencil (warp-per-cell kernels), 1 = pencil over gBarP
+// written by the half-step kernel, 2 = fused: the pencil reads gTilde and applies the half step itself (face-
+// storage slabs only: the recompute path needs gBarP of every cell again in phase 2).
+static int pencil_mode(const dugks_handle* h, int slab) {
+    if (!h->pen_mode || !h->split_axis || slab >= (int)h->slab_pair_ok.size() || !h->slab_pair_ok[slab]) return 0;
+    return (h->pen_mode == 2 && slab < h->n_keep) ? 2 : 1;
+}
+
 template <int PHASE, bool H>
 static void launch_hot_outgoing(dugks_handle* h, const StepArgs& a) {
     const size_t sm = PHASE == 1 ? h->hsmem_out1 : h->hsmem_out2;
@@ -259,14 +279,22 @@ static void launch_hot_outgoing(dugks_handle* h, const StepArgs& a) {
         // mostly axis-aligned mesh: the light variant (hot_axis_item) alone runs 3 CTAs/SM, a second launch
         // takes the rest.  Slabs with a tie on a y/z face or rows that are not whole chunks take the unified launch.
         StepArgs a1 = a, a2 = a;
-        a1.item0 = 0; a1.item1 = h->n_axis;
+        const int pm = pencil_mode(h, a.slab);
+        a1.item0 = pm ? h->n_pen : 0; a1.item1 = h->n_axis;
         a2.item0 = h->n_axis; a2.item1 = h->nc;
         const int grid2 = std::max(1, std::min(grid, (h->nc - h->n_axis + HOT_WARPS - 1) / HOT_WARPS));
+        const int grid1 = std::max(1, std::min(h->hot_grid_axis, (a1.item1 - a1.item0 + HOT_WARPS - 1) / HOT_WARPS));
+        if (!H && pm) {
+            // CTA pencils (dugks_pencil.cuh) take the bundled x-lines; the axis-only launch what is left of the axis-aligned cells
+            if (pm == 2) k_pencil_phase1<true><<<h->pen_grid, PEN_WARPS * 32, h->pen_smem, h->stream>>>(a, h->pen);
+            else k_pencil_phase1<false><<<h->pen_grid, PEN_WARPS * 32, h->pen_smem, h->stream>>>(a, h->pen);
+            h->launches++;
+        }
         if (h->hot_ne == 4) {
-            k_hot_outgoing<1, H, 4, 32, CI_AXIS, 1><<<h->hot_grid_axis, HOT_WARPS * 32, h->hsmem_axis, h->stream>>>(a1);
+            if (a1.item0 < a1.item1) k_hot_outgoing<1, H, 4, 32, CI_AXIS, 1><<<grid1, HOT_WARPS * 32, h->hsmem_axis, h->stream>>>(a1);
             if (h->n_axis < h->nc) k_hot_outgoing<1, H, 4, 32, CI_OUT1, 2><<<grid2, HOT_WARPS * 32, sm, h->stream>>>(a2);
         } else {
-            k_hot_outgoing<1, H, 6, 32, CI_AXIS, 1><<<h->hot_grid_axis, HOT_WARPS * 32, h->hsmem_axis, h->stream>>>(a1);
+            if (a1.item0 < a1.item1) k_hot_outgoing<1, H, 6, 32, CI_AXIS, 1><<<grid1, HOT_WARPS * 32, h->hsmem_axis, h->stream>>>(a1);
             if (h->n_axis < h->nc) k_hot_outgoing<1, H, 6, 32, CI_OUT1, 2><<<grid2, HOT_WARPS * 32, sm, h->stream>>>(a2);
         }
         h->launches++;
@@ -289,8 +317,9 @@ static void launch_hot_relax(dugks_handle* h, const StepArgs& a) {
     const int tw = h->tma_tw;
 #define DUGKS_HOT_RLX(NE_, TW_)                                                                                            \
     do {                                                                                                                   \
-        if (h->wmode) k_hot_relax_update<H, NE_, TW_, CI_RLX, true><<<h->hot_grid_rlx_w, HOT_WARPS * 32, h->hsmem_rlx_w, h->stream>>>(a); \
-        else k_hot_relax_update<H, NE_, TW_, CI_RLX, false><<<h->hot_grid_rlx, HOT_WARPS * 32, h->hsmem_rlx, h->stream>>>(a);             \
+        if (pencil_mode(h, a.slab) == 2) k_hot_relax_update<H, NE_, TW_, CI_RLX, 2><<<h->hot_grid_rlx_g, HOT_WARPS * 32, h->hsmem_rlx_g, h->stream>>>(a); \
+        else if (h->wmode) k_hot_relax_update<H, NE_, TW_, CI_RLX, 1><<<h->hot_grid_rlx_w, HOT_WARPS * 32, h->hsmem_rlx_w, h->stream>>>(a); \
+        else k_hot_relax_update<H, NE_, TW_, CI_RLX, 0><<<h->hot_grid_rlx, HOT_WARPS * 32, h->hsmem_rlx, h->stream>>>(a);             \
     } while (0)
     if (h->hot_ne == 4) { if (tw == 32) DUGKS_HOT_RLX(4, 32); else DUGKS_HOT_RLX(4, 64); }
     else if (h->hot_ne == 6) { if (tw == 32) DUGKS_HOT_RLX(6, 32); else DUGKS_HOT_RLX(6, 64); }
@@ -299,12 +328,15 @@ static void launch_hot_relax(dugks_handle* h, const StepArgs& a) {
 }
 template <bool H, int NE, int TW>
 static cudaError_t hot_cfg_rlx(dugks_handle* h, int* occ) {
-    h->hsmem_rlx = HotRelaxPlan<H, NE, TW, CI_RLX, false>::total(h->ntab);
-    h->hsmem_rlx_w = HotRelaxPlan<H, NE, TW, CI_RLX, true>::total(h->ntab);
-    cudaError_t e = cudaFuncSetAttribute(k_hot_relax_update<H, NE, TW, CI_RLX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->hsmem_rlx);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_hot_relax_update<H, NE, TW, CI_RLX, false>, HOT_WARPS * 32, h->hsmem_rlx);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_hot_relax_update<H, NE, TW, CI_RLX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->hsmem_rlx_w);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ + 1, k_hot_relax_update<H, NE, TW, CI_RLX, true>, HOT_WARPS * 32, h->hsmem_rlx_w);
+    h->hsmem_rlx = HotRelaxPlan<H, NE, TW, CI_RLX, 0>::total(h->ntab);
+    h->hsmem_rlx_w = HotRelaxPlan<H, NE, TW, CI_RLX, 1>::total(h->ntab);
+    h->hsmem_rlx_g = HotRelaxPlan<H, NE, TW, CI_RLX, 2>::total(h->ntab);
+    cudaError_t e = cudaFuncSetAttribute(k_hot_relax_update<H, NE, TW, CI_RLX, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->hsmem_rlx);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_hot_relax_update<H, NE, TW, CI_RLX, 0>, HOT_WARPS * 32, h->hsmem_rlx);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_hot_relax_update<H, NE, TW, CI_RLX, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->hsmem_rlx_w);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ + 1, k_hot_relax_update<H, NE, TW, CI_RLX, 1>, HOT_WARPS * 32, h->hsmem_rlx_w);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_hot_relax_update<H, NE, TW, CI_RLX, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->hsmem_rlx_g);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ + 2, k_hot_relax_update<H, NE, TW, CI_RLX, 2>, HOT_WARPS * 32, h->hsmem_rlx_g);
     return e;
 }
 template <int PHASE, bool H, int NE, int TW>
@@ -315,7 +347,7 @@ template <bool H>
 static int hot_configure(dugks_handle* h) {
     const int ntab = h->ntab, tw = h->tma_tw;
     cudaError_t e = cudaSuccess;
-    int occ[5] = {1, 1, 1, 1, 1};
+    int occ[6] = {1, 1, 1, 1, 1, 1};
 #define DUGKS_HOT_CFG(NE_)                                                                                   \
     do {                                                                                                     \
         h->hsmem_out1 = HotPlan<1, H, NE_, 32, CI_OUT1>::total(ntab);                                                 \
@@ -373,6 +405,23 @@ static int hot_configure(dugks_handle* h) {
     h->hot_grid_upd = std::max(1, std::min(dev_sms * std::max(occ[2], 1), max_ctas));
     h->hot_grid_rlx = std::max(1, std::min(dev_sms * std::max(occ[3], 1), max_ctas));
     h->hot_grid_rlx_w = std::max(1, std::min(dev_sms * std::max(occ[4], 1), max_ctas));
+    h->hot_grid_rlx_g = std::max(1, std::min(dev_sms * std::max(occ[5], 1), max_ctas));
+    // CTA pencils: the shared-memory window has to fit twice per SM to be worth it
+    if (h->pen_mode) {
+        int occ_pen = 0;
+        h->pen_smem = PenPlan::total(h->L, ntab, h->tabw);
+        if (H || h->pen_smem > 113 * 1024 || !h->split_axis) h->pen_mode = 0;
+        else {
+            e = cudaFuncSetAttribute(k_pencil_phase1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->pen_smem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pencil_phase1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->pen_smem);
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_pen, k_pencil_phase1<true>, PEN_WARPS * 32, h->pen_smem);
+            if (e != cudaSuccess) return fail(h, DUGKS_ERR_CUDA, "pencil kernel configuration: %s", cudaGetErrorString(e));
+            if (occ_pen < 1) h->pen_mode = 0;
+        }
+        if (getenv("DUGKS_VERBOSE"))
+            fprintf(stderr, "dugks: pencils mode %d, %d of %d axis-aligned cells in %d work items, %zu B shared memory per CTA, %d CTAs/SM, %d cells in the half-step list\n",
+                    h->pen_mode, h->n_pen, h->n_axis, h->pen.nitems, h->pen_smem, occ_pen, h->n_halflist);
+    }
     h->hot_grid_half = std::max(1, std::min(dev_sms * std::max(occ_half, 1), max_ctas));
     h->hot_grid_axis = std::max(1, std::min(dev_sms * std::max(occ_axis, 1), max_ctas));
     if (getenv("DUGKS_VERBOSE"))
@@ -407,9 +456,13 @@ static int launch_slab_kernels_phase1(dugks_handle* h, StepArgs a) {
     map_gb(h, a);
     {
         Timed t(h, 2);
-        if (h->use_hot && h->hsmem_half > 0)
-            k_hot_halfstep<H><<<h->hot_grid_half, HOT_WARPS * 32, h->hsmem_half, h->stream>>>(a, h->tma_tw, (h->wmode && a.slab < h->n_keep) ? 1 : 0);
-        else
+        if (h->use_hot && h->hsmem_half > 0) {
+            if (pencil_mode(h, a.slab) == 2)   // only gBarP of the cells the warp-per-cell kernels still read; gTilde stays
+                k_hot_halfstep<H><<<std::max(1, std::min(h->hot_grid_half, (h->n_halflist + HOT_WARPS - 1) / HOT_WARPS)), HOT_WARPS * 32, h->hsmem_half, h->stream>>>(
+                    a, h->tma_tw, 0, h->d_halflist, h->n_halflist);
+            else
+                k_hot_halfstep<H><<<h->hot_grid_half, HOT_WARPS * 32, h->hsmem_half, h->stream>>>(a, h->tma_tw, (h->wmode && a.slab < h->n_keep) ? 1 : 0, nullptr, 0);
+        } else
             k_cell_halfstep<H><<<grid_for(items), WARPS_PER_CTA * 32, 0, h->stream>>>(a, 0);
     }
     if ((rc = check_launch(h, "k_cell_halfstep"))) return rc;
@@ -905,6 +958,268 @@ extern "C" int dugks_cell_order(int32_t nCells, int32_t nSolutionD, const double
     return 0;
 }
 
+// ------------------------------------------------------------------------------
+// Host-side mesh analysis shared by dugks_create and the host-only introspection entry points.
+// Cell -> face CSR (internal faces first) with one geometry record per (cell, face) entry: LS vector G(3),
+// r = Cf - C_cell (3), Sf (3).  Axis-aligned cells: every LS vector and face offset of the cell has exactly ONE
+// non-zero component (exact zeros, as orthogonal hexahedra give), two faces per axis, all internal; their
+// entries are put in the canonical order x-, x+, y-, y+[, z-, z+] so that the kernels can skip the products
+// with the exact zeros at compile time (bit-identical to the general path) and know a neighbour's direction
+// from its entry index.
+struct HostCsr {
+    std::vector<int> cnt, cnt_int, off, e_other, e_face, e_owner;
+    std::vector<double> e_geo;
+    std::vector<unsigned char> cell_cls;
+    int n_axis = 0, axis_ne = 0;     // axis_ne: 4 or 6 when all axis-aligned cells have that many faces, -1 if mixed
+};
+
+static int build_host_csr(const dugks_mesh_t* mesh, bool want_axis, HostCsr& out, std::string& err) {
+    const int nc = mesh->nCells, nif = mesh->nInternalFaces, nbf = mesh->nBoundaryFaces;
+    char buf[256];
+    std::vector<int>&cnt = out.cnt, &cnt_int = out.cnt_int, &off = out.off, &e_other = out.e_other, &e_face = out.e_face, &e_owner = out.e_owner;
+    std::vector<double>& e_geo = out.e_geo;
+    cnt.assign(nc, 0); cnt_int.assign(nc, 0);
+    for (int f = 0; f < nif; f++) {
+        int o = mesh->owner[f], nb = mesh->neighbour[f];
+        if (o < 0 || o >= nc || nb < 0 || nb >= nc) { snprintf(buf, sizeof buf, "face %d: owner/neighbour out of range", f); err = buf; return DUGKS_ERR_INVALID; }
+        cnt[o]++; cnt[nb]++; cnt_int[o]++; cnt_int[nb]++;
+    }
+    for (int b = 0; b < nbf; b++) {
+        int o = mesh->owner[nif + b];
+        if (o < 0 || o >= nc) { snprintf(buf, sizeof buf, "boundary face %d: owner out of range", b); err = buf; return DUGKS_ERR_INVALID; }
+        cnt[o]++;
+    }
+    off.assign(nc + 1, 0);
+    for (int c = 0; c < nc; c++) {
+        if (cnt[c] > MAX_CELL_FACES) { snprintf(buf, sizeof buf, "cell %d has %d faces (limit %d)", c, cnt[c], MAX_CELL_FACES); err = buf; return DUGKS_ERR_UNSUPPORTED; }
+        off[c + 1] = off[c] + cnt[c];
+    }
+    const int ne = off[nc];
+    e_other.assign(ne, 0); e_face.assign(ne, 0); e_owner.assign(ne, 0);
+    e_geo.assign((size_t)ne * 9, 0.0);
+    std::vector<int> fill_i(nc, 0), fill_b(nc, 0);
+    auto put = [&](int c, int pos, int other, int face, int isown, const double* G) {
+        int e = off[c] + pos;
+        e_other[e] = other; e_face[e] = face; e_owner[e] = isown;
+        for (int d = 0; d < 3; d++) {
+            e_geo[(size_t)e * 9 + d] = G[d];
+            e_geo[(size_t)e * 9 + 3 + d] = mesh->Cf[(size_t)face * 3 + d] - mesh->C[(size_t)c * 3 + d];
+            e_geo[(size_t)e * 9 + 6 + d] = mesh->Sf[(size_t)face * 3 + d];
+        }
+    };
+    for (int f = 0; f < nif; f++) {
+        int o = mesh->owner[f], nb = mesh->neighbour[f];
+        put(o, fill_i[o]++, nb, f, 1, mesh->ownLs + (size_t)f * 3);
+        // grad[nei] -= neiLs*(v_nei - v_own) == neiLs*(v_own - v_nei): the sign is inside neiLs
+        // (zeroBoundaryGrad.C:98, zeroBoundaryVectors.C:183-184)
+        put(nb, fill_i[nb]++, o, f, 0, mesh->neiLs + (size_t)f * 3);
+    }
+    for (int b = 0; b < nbf; b++) {
+        int f = nif + b, o = mesh->owner[f];
+        put(o, cnt_int[o] + fill_b[o]++, -1 - b, f, 1, mesh->patchLs + (size_t)b * 3);
+    }
+    // Rounding residue of the geometry formulas: on an orthogonal mesh whose coordinates are not exact binary
+    // fractions (60 x 60 cells on [0,1]^2, a plate of thickness 0.1) the components of Cf - C and of an LS vector
+    // that vanish in exact arithmetic come out as a few ulp of the COORDINATES they were differenced from, i.e.
+    // amplified by |C| / |Cf - C| relative to the vector itself.  Components below 16 ulp of that scale are set
+    // to zero HERE, for every kernel path alike.  What is dropped is rounding noise of the same size as the noise
+    // left in the other components (the reference computes with it; neither is "the" value), at worst a few
+    // 1e-13 of a face value, below the per-step tolerance; without it hardly any cell of such a mesh would be
+    // recognised as axis-aligned.  Components along a direction in which every LS vector of the cell vanishes
+    // (the empty direction of a 2-D case) multiply a gradient component that is exactly zero: zeroed as well.
+    if (want_axis) {
+        const double ulp16 = 16.0 * 2.220446049250313e-16;
+        for (int c = 0; c < nc; c++) {
+            bool gzero[3] = {true, true, true};
+            for (int e = off[c]; e < off[c + 1]; e++) {
+                double* g = &e_geo[(size_t)e * 9];
+                const int f = e_face[e];
+                double cmax = 0.0, rmax = 0.0, gmax = 0.0;
+                for (int d = 0; d < 3; d++) {
+                    cmax = std::max(cmax, std::max(std::fabs(mesh->Cf[(size_t)f * 3 + d]), std::fabs(mesh->C[(size_t)c * 3 + d])));
+                    rmax = std::max(rmax, std::fabs(g[3 + d]));
+                    gmax = std::max(gmax, std::fabs(g[d]));
+                }
+                const double amp = rmax > 0 ? std::max(1.0, cmax / rmax) : 1.0;
+                for (int d = 0; d < 3; d++) {
+                    if (std::fabs(g[3 + d]) <= ulp16 * std::max(cmax, rmax)) g[3 + d] = 0.0;
+                    if (std::fabs(g[d]) <= ulp16 * amp * gmax) g[d] = 0.0;
+                }
+                for (int d = 0; d < 3; d++) gzero[d] = gzero[d] && g[d] == 0.0;
+            }
+            for (int e = off[c]; e < off[c + 1]; e++)
+                for (int d = 0; d < 3; d++) if (gzero[d]) e_geo[(size_t)e * 9 + 3 + d] = 0.0;
+        }
+    }
+    out.cell_cls.assign(nc, 0);
+    out.n_axis = 0; out.axis_ne = 0;
+    std::vector<int> axis_of(MAX_CELL_FACES), order(MAX_CELL_FACES);
+    std::vector<double> tmp_geo(MAX_CELL_FACES * 9);
+    std::vector<int> tmp_i(MAX_CELL_FACES * 3);
+    for (int c = 0; c < nc && want_axis; c++) {
+        const int n_e = cnt[c];
+        if (n_e != cnt_int[c] || (n_e != 4 && n_e != 6)) continue;
+        int per_axis[3] = {0, 0, 0};
+        bool ok = true;
+        for (int j = 0; j < n_e && ok; j++) {
+            const double* g = &e_geo[(size_t)(off[c] + j) * 9];
+            int ax = -1;
+            for (int d = 0; d < 3; d++)
+                if (g[d] != 0.0 || g[3 + d] != 0.0) { if (ax >= 0 && ax != d) ok = false; ax = d; }
+            if (ax < 0) ok = false;
+            // the flux of the update kernels keeps the general form, so Sf is not constrained
+            if (ok) { axis_of[j] = ax; per_axis[ax]++; }
+        }
+        if (!ok) continue;
+        const int naxes = n_e / 2;
+        for (int d = 0; d < 3; d++) if (per_axis[d] != (d < naxes ? 2 : 0)) ok = false;
+        if (!ok) continue;
+        int k = 0;
+        for (int d = 0; d < 3; d++) {
+            const int k0 = k;
+            for (int j = 0; j < n_e; j++) if (axis_of[j] == d) order[k++] = j;
+            if (k - k0 == 2 && e_geo[(size_t)(off[c] + order[k0]) * 9 + 3 + d] > e_geo[(size_t)(off[c] + order[k0 + 1]) * 9 + 3 + d])
+                std::swap(order[k0], order[k0 + 1]);
+        }
+        for (int j = 0; j < n_e; j++) {
+            const int e = off[c] + order[j];
+            for (int d = 0; d < 9; d++) tmp_geo[j * 9 + d] = e_geo[(size_t)e * 9 + d];
+            tmp_i[j * 3] = e_other[e]; tmp_i[j * 3 + 1] = e_face[e]; tmp_i[j * 3 + 2] = e_owner[e];
+        }
+        for (int j = 0; j < n_e; j++) {
+            const int e = off[c] + j;
+            for (int d = 0; d < 9; d++) e_geo[(size_t)e * 9 + d] = tmp_geo[j * 9 + d];
+            e_other[e] = tmp_i[j * 3]; e_face[e] = tmp_i[j * 3 + 1]; e_owner[e] = tmp_i[j * 3 + 2];
+        }
+        out.cell_cls[c] = 1;
+        out.axis_ne = (out.n_axis == 0 || out.axis_ne == n_e) ? n_e : -1;   // -1: mixed face counts
+        out.n_axis++;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------
+// CTA pencils of phase 1 (dugks_pencil.cuh), host side: x-lines of axis-aligned interior cells (entries in the
+// canonical order x-, x+, y-, y+, z-, z+), 2 x 2 bundles of lines whose cells are mutual y / z neighbours position
+// by position, and the work items (runs of consecutive x positions of a bundle) in the order the CTAs take them.
+struct PenHost {
+    std::vector<PenItem> items;
+    std::vector<int> cells, halo;
+    std::vector<int> order;          // pencil cells in traversal order: item, step, line
+};
+
+static void build_pencils(int nc, const std::vector<int>& off, const std::vector<int>& e_other,
+                          const std::vector<unsigned char>& cls, int grid, PenHost& out) {
+    auto nbr = [&](int c, int j) { return e_other[off[c] + j]; };
+    auto axis = [&](int c) { return c >= 0 && cls[c] != 0; };
+    // ---- lines: maximal chains along x+ of axis-aligned cells
+    std::vector<int> line_of(nc, -1), pos_of(nc, -1);
+    std::vector<std::vector<int>> lines;
+    for (int c = 0; c < nc; c++) {
+        if (!axis(c) || axis(nbr(c, 0))) continue;            // not a line start
+        std::vector<int> ln;
+        for (int cur = c; axis(cur) && line_of[cur] < 0; cur = nbr(cur, 1)) {
+            line_of[cur] = (int)lines.size();
+            pos_of[cur] = (int)ln.size();
+            ln.push_back(cur);
+        }
+        lines.push_back(std::move(ln));
+    }
+    // ---- bundles: A, B = y+ of A, C = z+ of A, D = y+ of C, equal lengths, aligned position by position
+    std::vector<char> used(lines.size(), 0);
+    std::vector<std::array<int, 4>> bundles;
+    for (size_t la = 0; la < lines.size(); la++) {
+        if (used[la]) continue;
+        const std::vector<int>& A = lines[la];
+        const int b0 = nbr(A[0], 3), c0 = nbr(A[0], 5);
+        if (!axis(b0) || !axis(c0) || pos_of[b0] != 0 || pos_of[c0] != 0) continue;
+        const int lb = line_of[b0], lc = line_of[c0];
+        const int d0 = nbr(c0, 3);
+        if (!axis(d0) || pos_of[d0] != 0) continue;
+        const int ld = line_of[d0];
+        if (lb == (int)la || lc == (int)la || ld == (int)la || lb == lc || lb == ld || lc == ld) continue;
+        if (used[lb] || used[lc] || used[ld]) continue;
+        const std::vector<int>&B = lines[lb], &C = lines[lc], &Dl = lines[ld];
+        if (B.size() != A.size() || C.size() != A.size() || Dl.size() != A.size()) continue;
+        bool ok = true;
+        for (size_t k = 0; k < A.size() && ok; k++)
+            ok = nbr(A[k], 3) == B[k] && nbr(A[k], 5) == C[k] && nbr(C[k], 3) == Dl[k] && nbr(B[k], 5) == Dl[k] &&
+                 nbr(B[k], 2) == A[k] && nbr(C[k], 4) == A[k] && nbr(Dl[k], 2) == C[k] && nbr(Dl[k], 4) == B[k];
+        if (!ok) continue;
+        used[la] = used[lb] = used[lc] = used[ld] = 1;
+        bundles.push_back({(int)la, lb, lc, ld});
+    }
+    if (bundles.empty()) return;
+    // ---- work items.  CTA j of `grid` takes items j, j + grid, ...: whole lines for as many full rounds as there
+    // are, the remaining bundles cut into pieces so that the last rounds fill the grid too.
+    struct Piece { int b, s0, s1; };
+    std::vector<Piece> pieces;
+    const int nb = (int)bundles.size();
+    const int full = (nb / grid) * grid;
+    for (int b = 0; b < full; b++) pieces.push_back({b, 0, (int)lines[bundles[b][0]].size()});
+    if (nb > full) {
+        const int rem = nb - full;
+        int nmax = 0;
+        for (int b = full; b < nb; b++) nmax = std::max(nmax, (int)lines[bundles[b][0]].size());
+        int best_k = 1;
+        long long best = -1;
+        for (int k = 1; k <= 8; k++) {
+            const int len = (nmax + k - 1) / k;
+            if (k > 1 && len < 6) break;
+            const long long cost = (long long)(((long long)rem * k + grid - 1) / grid) * (len + 1);   // + 1: the prologue of a piece
+            if (best < 0 || cost < best) { best = cost; best_k = k; }
+        }
+        for (int pc = 0; pc < best_k; pc++)
+            for (int b = full; b < nb; b++) {
+                const int n = (int)lines[bundles[b][0]].size();
+                const int s0 = (int)((long long)n * pc / best_k), s1 = (int)((long long)n * (pc + 1) / best_k);
+                if (s1 > s0) pieces.push_back({b, s0, s1});
+            }
+    }
+    for (const Piece& pc : pieces) {
+        PenItem it;
+        it.cells = (int)out.cells.size();
+        it.halo = (int)out.halo.size();
+        it.item0 = (int)out.order.size();
+        it.nsteps = pc.s1 - pc.s0;
+        for (int p = pc.s0 - 1; p <= pc.s1; p++)
+            for (int l = 0; l < 4; l++) {
+                const std::vector<int>& ln = lines[bundles[pc.b][l]];
+                out.cells.push_back(p < 0 ? nbr(ln[0], 0) : (p >= (int)ln.size() ? nbr(ln.back(), 1) : ln[p]));
+            }
+        for (int p = pc.s0; p < pc.s1; p++)
+            for (int l = 0; l < 4; l++) {
+                const int c = lines[bundles[pc.b][l]][p];
+                out.halo.push_back(nbr(c, (l & 1) ? 3 : 2));   // by = 0: y- is outside the bundle, by = 1: y+
+                out.halo.push_back(nbr(c, (l & 2) ? 5 : 4));
+                out.order.push_back(c);
+            }
+        out.items.push_back(it);
+    }
+}
+
+// introspection (host only, no device needed): the pencil work items dugks_create would build for this mesh
+extern "C" int dugks_pencil_plan(const dugks_mesh_t* mesh, int32_t nCtas, int32_t* nItems, int32_t* nPencilCells,
+                                 int32_t* cells, int32_t* item_first, int32_t* item_steps, int32_t* nAxisCells) {
+    if (!mesh || nCtas < 1 || !nItems || !nPencilCells) return fail(nullptr, DUGKS_ERR_INVALID, "dugks_pencil_plan: bad argument");
+    HostCsr csr;
+    std::string err;
+    int rc = build_host_csr(mesh, true, csr, err);
+    if (rc) return fail(nullptr, rc, "%s", err.c_str());
+    PenHost ph;
+    if (mesh->nSolutionD == 3 && csr.axis_ne == PEN_NE) build_pencils(mesh->nCells, csr.off, csr.e_other, csr.cell_cls, nCtas, ph);
+    const int cap_items = *nItems, cap_cells = *nPencilCells;
+    *nItems = (int)ph.items.size();
+    *nPencilCells = (int)ph.order.size();
+    if (nAxisCells) *nAxisCells = csr.n_axis;
+    if (cells) for (int k = 0; k < (int)ph.order.size() && k < cap_cells; k++) cells[k] = ph.order[k];
+    for (int k = 0; k < (int)ph.items.size() && k < cap_items; k++) {
+        if (item_first) item_first[k] = ph.items[k].item0;
+        if (item_steps) item_steps[k] = ph.items[k].nsteps;
+    }
+    return 0;
+}
+
 extern "C" int dugks_abi_version(void) { return DUGKS_ABI_VERSION; }
 
 extern "C" int dugks_partition(int32_t nXiPerDim, int32_t nSolutionD, int32_t nRanks, int32_t rank, int32_t* ids,
@@ -1172,41 +1487,22 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
         }
     }
 
-    // ---- cell -> face CSR (internal faces first), geometry per entry
-    std::vector<int> cnt(nc, 0), cnt_int(nc, 0);
-    for (int f = 0; f < nif; f++) { cnt[mesh->owner[f]]++; cnt[mesh->neighbour[f]]++; cnt_int[mesh->owner[f]]++; cnt_int[mesh->neighbour[f]]++; }
-    for (int b = 0; b < nbf; b++) cnt[mesh->owner[nif + b]]++;
-    std::vector<int> off(nc + 1, 0);
-    for (int c = 0; c < nc; c++) {
-        if (cnt[c] > MAX_CELL_FACES) { fail(h, DUGKS_ERR_UNSUPPORTED, "cell %d has %d faces (limit %d)", c, cnt[c], MAX_CELL_FACES); return bail(DUGKS_ERR_UNSUPPORTED); }
-        off[c + 1] = off[c] + cnt[c];
+    // ---- cell -> face CSR (internal faces first), geometry per entry, axis-aligned cells (build_host_csr)
+    HostCsr csr;
+    {
+        std::string cerr;
+        const int crc = build_host_csr(mesh, getenv("DUGKS_NO_AXIS") == nullptr /* test hook: general path everywhere */, csr, cerr);
+        if (crc) { fail(h, crc, "%s", cerr.c_str()); return bail(crc); }
     }
+    std::vector<int>&cnt = csr.cnt, &cnt_int = csr.cnt_int, &off = csr.off, &e_other = csr.e_other, &e_face = csr.e_face, &e_owner = csr.e_owner;
+    std::vector<double>& e_geo = csr.e_geo;
+    std::vector<unsigned char>& cell_cls = csr.cell_cls;
+    h->n_axis = csr.n_axis; h->axis_ne = csr.axis_ne;
     const int ne = off[nc];
-    std::vector<int> e_other(ne), e_face(ne), e_owner(ne), fill_i(nc, 0), fill_b(nc, 0);
-    std::vector<double> e_geo((size_t)ne * 9);
-    auto put = [&](int c, int pos, int other, int face, int isown, const double* G) {
-        int e = off[c] + pos;
-        e_other[e] = other; e_face[e] = face; e_owner[e] = isown;
-        for (int d = 0; d < 3; d++) {
-            e_geo[(size_t)e * 9 + d] = G[d];
-            e_geo[(size_t)e * 9 + 3 + d] = mesh->Cf[(size_t)face * 3 + d] - mesh->C[(size_t)c * 3 + d];
-            e_geo[(size_t)e * 9 + 6 + d] = mesh->Sf[(size_t)face * 3 + d];
-        }
-    };
-    for (int f = 0; f < nif; f++) {
-        int o = mesh->owner[f], nb = mesh->neighbour[f];
-        if (o < 0 || o >= nc || nb < 0 || nb >= nc) { fail(h, DUGKS_ERR_INVALID, "face %d: owner/neighbour out of range", f); return bail(DUGKS_ERR_INVALID); }
-        put(o, fill_i[o]++, nb, f, 1, mesh->ownLs + (size_t)f * 3);
-        // grad[nei] -= neiLs*(v_nei - v_own) == neiLs*(v_own - v_nei): the sign is inside neiLs
-        // (zeroBoundaryGrad.C:98, zeroBoundaryVectors.C:183-184)
-        put(nb, fill_i[nb]++, o, f, 0, mesh->neiLs + (size_t)f * 3);
-    }
     std::vector<int> b_owner(nbf);
     std::vector<double> b_n((size_t)nbf * 3), b_invdc(nbf), b_Sf((size_t)nbf * 3), b_r((size_t)nbf * 3);
     for (int b = 0; b < nbf; b++) {
         int f = nif + b, o = mesh->owner[f];
-        if (o < 0 || o >= nc) { fail(h, DUGKS_ERR_INVALID, "boundary face %d: owner out of range", b); return bail(DUGKS_ERR_INVALID); }
-        put(o, cnt_int[o] + fill_b[o]++, -1 - b, f, 1, mesh->patchLs + (size_t)b * 3);
         b_owner[b] = o;
         const double* S = mesh->Sf + (size_t)f * 3;
         double mag = std::sqrt(S[0] * S[0] + S[1] * S[1] + S[2] * S[2]);
@@ -1216,53 +1512,6 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
             b_r[(size_t)b * 3 + d] = mesh->Cf[(size_t)f * 3 + d] - mesh->C[(size_t)o * 3 + d];
         }
         b_invdc[b] = 1.0 / mesh->deltaCoeffs[f];
-    }
-
-    // ---- axis-aligned cells: every LS vector and face offset of the cell has exactly ONE non-zero
-    // component (exact zeros, as orthogonal hexahedra give), two faces per axis, all internal.  Their
-    // entries are put in axis order (x, x, y, y[, z, z]) so that the kernels can skip the products with
-    // the exact zeros at compile time: the result is bit-identical to the general path.
-    std::vector<unsigned char> cell_cls(nc, 0);
-    {
-        const bool want = getenv("DUGKS_NO_AXIS") == nullptr;   // test hook: general path everywhere
-        std::vector<int> axis_of(MAX_CELL_FACES), order(MAX_CELL_FACES);
-        std::vector<double> tmp_geo(MAX_CELL_FACES * 9);
-        std::vector<int> tmp_i(MAX_CELL_FACES * 3);
-        for (int c = 0; c < nc && want; c++) {
-            const int n_e = cnt[c];
-            if (n_e != cnt_int[c] || (n_e != 4 && n_e != 6)) continue;
-            int per_axis[3] = {0, 0, 0};
-            bool ok = true;
-            for (int j = 0; j < n_e && ok; j++) {
-                const double* g = &e_geo[(size_t)(off[c] + j) * 9];
-                int ax = -1;
-                for (int d = 0; d < 3; d++)
-                    if (g[d] != 0.0 || g[3 + d] != 0.0) { if (ax >= 0 && ax != d) ok = false; ax = d; }
-                if (ax < 0) ok = false;
-                // the flux of the update kernels keeps the general form, so Sf is not constrained
-                if (ok) { axis_of[j] = ax; per_axis[ax]++; }
-            }
-            if (!ok) continue;
-            const int naxes = n_e / 2;
-            for (int d = 0; d < 3; d++) if (per_axis[d] != (d < naxes ? 2 : 0)) ok = false;
-            if (!ok) continue;
-            int k = 0;
-            for (int d = 0; d < 3; d++)
-                for (int j = 0; j < n_e; j++) if (axis_of[j] == d) order[k++] = j;
-            for (int j = 0; j < n_e; j++) {
-                const int e = off[c] + order[j];
-                for (int d = 0; d < 9; d++) tmp_geo[j * 9 + d] = e_geo[(size_t)e * 9 + d];
-                tmp_i[j * 3] = e_other[e]; tmp_i[j * 3 + 1] = e_face[e]; tmp_i[j * 3 + 2] = e_owner[e];
-            }
-            for (int j = 0; j < n_e; j++) {
-                const int e = off[c] + j;
-                for (int d = 0; d < 9; d++) e_geo[(size_t)e * 9 + d] = tmp_geo[j * 9 + d];
-                e_other[e] = tmp_i[j * 3]; e_face[e] = tmp_i[j * 3 + 1]; e_owner[e] = tmp_i[j * 3 + 2];
-            }
-            cell_cls[c] = 1;
-            h->axis_ne = (h->n_axis == 0 || h->axis_ne == n_e) ? n_e : -1;   // -1: mixed face counts
-            h->n_axis++;
-        }
     }
 
     // ---- upload static data
@@ -1288,6 +1537,48 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
         if (const char* e = getenv("DUGKS_TILE")) tile = std::max(1, atoi(e));
         std::vector<int> order;
         build_cell_order(nc, D, mesh->C, h->want_split ? cell_cls.data() : nullptr, ord_env ? ord_env : "wave", tile, nwarps, order);
+        // CTA pencils of phase 1 (3-D, h elided, every cell within the compile-time face count): DUGKS_PENCIL =
+        // 2 (default: the pencil applies the half step itself) | 1 (pencil reads gBarP) | 0 (off)
+        {
+            int want_pen = 2;
+            if (const char* e = getenv("DUGKS_PENCIL")) want_pen = std::max(0, std::min(2, atoi(e)));
+            bool big = false;
+            for (int c = 0; c < nc; c++) big = big || cnt[c] > FAST_NE;
+            if (want_pen && h->want_split && D == 3 && !h->hasH && h->axis_ne == PEN_NE && !big && nch == 1 && L % PEN_CI == 0 &&
+                getenv("DUGKS_NO_HOT") == nullptr) {
+                PenHost ph;
+                h->pen_grid = 2 * dev_sms;
+                build_pencils(nc, off, e_other, cell_cls, h->pen_grid, ph);
+                if (!ph.items.empty()) {
+                    h->pen_mode = want_pen;
+                    h->n_pen = (int)ph.order.size();
+                    std::vector<char> inpen(nc, 0);
+                    for (int c : ph.order) inpen[c] = 1;
+                    std::vector<int> rest;
+                    for (int c : order) if (!inpen[c]) rest.push_back(c);
+                    order = ph.order;
+                    order.insert(order.end(), rest.begin(), rest.end());
+                    PenItem* d_items = nullptr;
+                    int *d_pc = nullptr, *d_ph = nullptr;
+                    TRYB(dev_upload(h, &d_items, ph.items));
+                    TRYB(dev_upload(h, &d_pc, ph.cells));
+                    TRYB(dev_upload(h, &d_ph, ph.halo));
+                    h->pen = PenArgs{d_items, (int)ph.items.size(), d_pc, d_ph};
+                    h->pen_grid = std::min(h->pen_grid, (int)ph.items.size());
+                    // fused mode: the kernels of the other cells still read gBarP of those cells and of their neighbours
+                    std::vector<char> need(nc, 0);
+                    for (int c = 0; c < nc; c++) {
+                        if (inpen[c]) continue;
+                        need[c] = 1;
+                        for (int j = 0; j < cnt_int[c]; j++) need[e_other[off[c] + j]] = 1;
+                    }
+                    std::vector<int> hl;
+                    for (int c : order) if (need[c]) hl.push_back(c);
+                    h->n_halflist = (int)hl.size();
+                    TRYB(dev_upload(h, &h->d_halflist, hl));
+                }
+            }
+        }
         // per-cell record (CMETA_N ints) in traversal order: everything a warp needs to start a cell in one load level
         std::vector<int> cmeta((size_t)nc * CMETA_N, 0);
         for (int item = 0; item < nc; item++) {
@@ -1532,6 +1823,7 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
         if (bad) h->use_hot = false;
         A.upw = d_upw;
     }
+    if (!h->use_hot || h->hsmem_half == 0) h->pen_mode = 0;
 
     // ---- face-storage slabs: as many as device memory allows (all of them from 2 GPUs up at the
     // 64^3 x 28^3 size; about half on one GPU).  Cells with too many faces need the flux-buffer path.
@@ -1971,6 +2263,8 @@ extern "C" int dugks_get_stats(dugks_handle_t* h, dugks_stats_t* out) {
     out->n_slabs = h->nslab;
     out->slab_dvs = h->L * h->Rs;
     out->keep_slabs = h->n_keep;
+    out->pencil_mode = h->split_axis ? h->pen_mode : 0;
+    out->pencil_cells = out->pencil_mode ? h->n_pen : 0;
     return 0;
 }
 

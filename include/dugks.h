@@ -304,6 +304,16 @@ int dugks_row_layout(int32_t nXiPerDim, int32_t nSolutionD, int32_t nRanks, int3
 int dugks_cell_order(int32_t nCells, int32_t nSolutionD, const double* C, const uint8_t* first_class,
                      const char* kind, int32_t nWarps, int32_t* order);
 
+/* Host-only (no device needed): the CTA-pencil plan of phase 1 for a 3-D mesh: x-lines of
+ * axis-aligned interior cells in 2 x 2 bundles, cut into work items for nCtas persistent CTAs.  On entry *nItems /
+ * *nPencilCells are the capacities of item_first, item_steps / cells (any array may be NULL), on return the
+ * counts.  cells: the pencil cells in traversal order — item k covers cells[item_first[k] .. + 4 item_steps[k]),
+ * step-major, the four lines of the bundle within a step.  *nAxisCells (may be NULL): cells recognised as
+ * axis-aligned (any dimension; exact zeros in the LS vectors and face offsets).  The reference visits cells in label order
+ * (discreteVelocity.C:491-530); any order gives the same result. */
+int dugks_pencil_plan(const dugks_mesh_t* mesh, int32_t nCtas, int32_t* nItems, int32_t* nPencilCells,
+                      int32_t* cells, int32_t* item_first, int32_t* item_steps, int32_t* nAxisCells);
+
 /* Boundary-face values gSurf/hSurf of the local DVs on all boundary faces,
  * g[j*nBoundaryFaces + b] for local DV j (DVi(j).gSurf().boundaryField(),
  * discreteVelocity.H:230-239).  Either pointer may be NULL. */
@@ -328,6 +338,8 @@ typedef struct dugks_stats_t {
     int32_t  slab_dvs;          /* DVs per slab                             */
     int32_t  keep_slabs;        /* slabs whose face values are kept between the two phases
                                    (fused relax+update; limited by device memory) */
+    int32_t  pencil_cells;      /* cells phase 1 advances as CTA pencils (2 x 2 bundles of x-lines), 0 = none */
+    int32_t  pencil_mode;       /* 0 off, 1 pencils over gBarP, 2 pencils that apply the half step themselves */
 } dugks_stats_t;
 
 int dugks_get_stats(dugks_handle_t* h, dugks_stats_t* out);

@@ -52,7 +52,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(abi.GasT) == 48
     assert ctypes.sizeof(abi.DvsetT) == 40
     assert ctypes.sizeof(abi.MeshT) == 16 + 10 * 8
-    assert ctypes.sizeof(abi.StatsT) == 40
+    assert ctypes.sizeof(abi.StatsT) == 48
 
 
 def test_row_layout_covers_every_velocity_once():
@@ -138,3 +138,38 @@ def test_cell_order_is_a_permutation_with_the_promised_structure():
         assert (lines == lines[0]).all() and len(set(lines[0])) == 16
     # a warp (item w, w + 16, ...) walks ONE line along x
     assert len(set((Z * ny + Y)[3:16 * nx:16])) == 1
+
+
+def test_pencil_plan_structure():
+    """dugks_pencil_plan (host only): x-lines of axis-aligned interior cells in 2 x 2 bundles, cut into work items.
+    Every pencil cell appears once; the four cells of a step are the corners of a 2 x 2 square in (y, z) at one x;
+    consecutive steps of an item are x+ neighbours; lines that find no partner stay out (the axis-only launch
+    takes them); orthogonal meshes whose coordinates are not binary fractions are recognised as well."""
+    for n, length, nctas in ((10, 1.0, 296), (11, 1.0, 296), (13, 13 / 16, 7), (16, 1.0, 5)):
+        case = cs.cavity3d_case(n, 8, length=length)
+        plan = capi.pencil_plan(case, nctas)
+        m = n - 2                                    # interior cells per direction
+        assert plan["n_axis"] == m ** 3
+        nb = (m // 2) ** 2                           # complete 2 x 2 bundles of the m x m lines
+        assert len(plan["cells"]) == nb * 4 * m and len(set(plan["cells"].tolist())) == len(plan["cells"])
+        assert int(plan["item_steps"].sum()) * 4 == len(plan["cells"])
+        C = case.geom.C
+        h = length / n
+        for first, steps in zip(plan["item_first"], plan["item_steps"]):
+            blk = plan["cells"][first:first + 4 * steps].reshape(steps, 4)
+            xyz = np.rint(C[blk] / h - 0.5).astype(int)         # integer cell coordinates, [step, line, 3]
+            assert (xyz[:, :, 0] == xyz[:, :1, 0]).all() and (np.diff(xyz[:, 0, 0]) == 1).all()
+            assert (xyz[:, 1] - xyz[:, 0] == [0, 1, 0]).all() and (xyz[:, 2] - xyz[:, 0] == [0, 0, 1]).all()
+            assert (xyz[:, 3] - xyz[:, 0] == [0, 1, 1]).all()
+            assert xyz.min() >= 1 and xyz.max() <= n - 2        # interior cells only
+        # the schedule: whole lines while they fill the grid, the rest cut so that the last rounds fill it too
+        rounds = -(-len(plan["item_steps"]) // nctas)
+        work = [int(plan["item_steps"][j::nctas].sum()) for j in range(min(nctas, len(plan["item_steps"])))]
+        assert max(work) <= -(-nb * m // min(nctas, nb)) + m // 2 + rounds
+    # distorted and triangular meshes have no axis-aligned cells: no pencils, nothing breaks
+    for case in (cs.cavity3d_case(5, 8, distort=0.15), cs.tri_cavity_case(6, 8)):
+        plan = capi.pencil_plan(case)
+        assert plan["n_axis"] == 0 and len(plan["cells"]) == 0
+    # 2-D: axis-aligned cells are recognised (the plate thickness 0.1 is not a binary fraction), pencils are 3-D only
+    plan = capi.pencil_plan(cs.cavity2d_case(60, 8))
+    assert plan["n_axis"] == 58 * 58 and len(plan["cells"]) == 0

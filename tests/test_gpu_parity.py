@@ -109,6 +109,9 @@ _PATHS = [
     ("no_wmode_keep_one", {"DUGKS_NO_WMODE": "1", "DUGKS_KEEP_SLABS": "1"}),
     ("order_tiled", {"DUGKS_ORDER": "tiled"}),          # strips of rows (the default is the x-wavefront order, dugks_cell_order)
     ("order_natural", {"DUGKS_ORDER": "natural"}),
+    ("pencil_off", {"DUGKS_PENCIL": "0"}),              # phase 1 without CTA pencils (warp-per-cell kernels everywhere)
+    ("pencil_unfused", {"DUGKS_PENCIL": "1"}),          # CTA pencils over gBarP written by the half-step kernel
+    ("pencil_keep_one", {"DUGKS_KEEP_SLABS": "1"}),     # fused pencils on the face-storage slab, unfused on the others
     ("gen1_tma", {"DUGKS_NO_HOT": "1"}),                # first-generation bulk-copy kernels
     ("gen1_ldg", {"DUGKS_NO_HOT": "1", "DUGKS_NO_TMA": "1"}),
     ("generic", {"DUGKS_NO_HOT": "1", "DUGKS_FORCE_GENERIC": "1"}),   # cells with many faces
@@ -119,13 +122,14 @@ _PATHS = [
 def test_every_kernel_path(oracle_lib, monkeypatch, path, env):
     """Every device code path that can carry the step gives the oracle's answer."""
     for k in ("DUGKS_KEEP_SLABS", "DUGKS_NO_HOT", "DUGKS_NO_TMA", "DUGKS_FORCE_GENERIC", "DUGKS_NO_AXIS",
-              "DUGKS_NO_SPLIT_AXIS", "DUGKS_NO_WMODE", "DUGKS_ORDER"):
+              "DUGKS_NO_SPLIT_AXIS", "DUGKS_NO_WMODE", "DUGKS_ORDER", "DUGKS_PENCIL"):
         monkeypatch.delenv(k, raising=False)
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     zoo = [("cavity3d_5_gh8_distort", cs.cavity3d_case(5, 8, distort=0.15, perturb=0.01), False),
            ("cavity3d_6_gh28", cs.cavity3d_case(6, 28, perturb=0.01), False),      # two slabs
-           ("cavity3d_10_gh8", cs.cavity3d_case(10, 8, perturb=0.01), False),      # mostly interior cells: axis-only launch
+           ("cavity3d_10_gh8", cs.cavity3d_case(10, 8, perturb=0.01), False),      # mostly interior cells: axis-only launch, CTA pencils
+           ("cavity3d_11_gh28", cs.cavity3d_case(11, 28, perturb=0.01), False),    # 9 x 9 interior lines: 16 bundles + lines left to the axis-only launch; 25 slabs with a short-row tail
            ("cavity2d_12_gh28", cs.cavity2d_case(12, 28, perturb=0.01), False),    # same in 2-D, with h
            # more cells than resident warps (148 SMs x 12): persistent warps carry state from cell to cell
            ("cavity3d_20_gh8", cs.cavity3d_case(20, 8, perturb=0.01), False),
@@ -139,6 +143,11 @@ def test_every_kernel_path(oracle_lib, monkeypatch, path, env):
         st = dv.stats()
         if path == "keep_all":
             assert st["keep_slabs"] == st["n_slabs"]
+        if name in ("cavity3d_10_gh8", "cavity3d_20_gh8", "cavity3d_11_gh28") and "DUGKS_NO_HOT" not in env and "DUGKS_NO_AXIS" not in env \
+                and "DUGKS_NO_SPLIT_AXIS" not in env:
+            n_int = {"cavity3d_10_gh8": 8, "cavity3d_20_gh8": 18, "cavity3d_11_gh28": 8}[name]
+            want_mode = int(env.get("DUGKS_PENCIL", "2"))
+            assert st["pencil_mode"] == want_mode and st["pencil_cells"] == (n_int ** 2 * (n_int if name != "cavity3d_11_gh28" else 9) if want_mode else 0), st
         if path in ("keep_none", "gen1_tma", "gen1_ldg", "generic", "no_axis_keep_none"):
             assert st["keep_slabs"] == 0
         orc = oracle_lib.Oracle(case)
