@@ -39,7 +39,7 @@ WORKLOADS = {
 CHECK_STEPS = 3          # the checksum is taken after this many steps (W >= 3 always)
 CHECKSUMS = os.path.join(ROOT, "profiles", "bench_checksums.json")
 # bounded CPU sample of the same workload shape (3-D cavity, 28^3 GH velocities, same gas/BCs)
-CPU_SAMPLE = ("cavity3d", dict(n=8, nDV=28))
+CPU_SAMPLE = ("cavity3d", dict(n=16, nDV=28))
 
 
 def build_case(kind, kw):
@@ -111,13 +111,9 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def run_cpu_reference(steps, warmup, threads=None):
-    """Times the CPU restatement of the reference (oracle/, OpenMP over discrete velocities
-    like the reference's -dvParallel ranks) on a bounded sample of the workload."""
+def _cpu_worker(threads, steps, warmup):
+    """One timing of the CPU restatement in its own process (OpenMP reads OMP_NUM_THREADS once per process)."""
     from oracle import oracle as orc
-    orc.build()
-    threads = threads or os.cpu_count() or 1
-    os.environ["OMP_NUM_THREADS"] = str(threads)
     case = build_case(*CPU_SAMPLE)
     o = orc.Oracle(case)
     dt = case.courant_dt(0.8)
@@ -127,14 +123,37 @@ def run_cpu_reference(steps, warmup, threads=None):
     for _ in range(steps):
         o.step(dt)
     el = time.perf_counter() - t0
-    ups = case.nCells * o.nxi * steps / el
-    o.close()
+    print(json.dumps({"gups": case.nCells * o.nxi * steps / el / 1e9, "ms": el / steps * 1e3,
+                      "updates": case.nCells * case.nXi}))
+
+
+def run_cpu_reference(steps, warmup, threads=None, scaling_check=True):
+    """Times the CPU restatement of the reference (oracle/: the reference's own loop structure, one discrete
+    velocity after the other with OpenMP over the velocities like its -dvParallel ranks, DV sums streamed DV-outer)
+    on a bounded sample of the workload, with all host threads; a second, shorter run at half the threads shows
+    whether the baseline scales on this host."""
+    from oracle import oracle as orc
+    orc.build()
+    threads = threads or os.cpu_count() or 1
+
+    def timed(nthr, k, w):
+        env = dict(os.environ, OMP_NUM_THREADS=str(nthr), OMP_PROC_BIND="spread")
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-worker", str(nthr), str(k), str(w)],
+                             env=env, capture_output=True, text=True, timeout=900)
+        return json.loads(out.stdout.strip().splitlines()[-1])
+    r = timed(threads, steps, warmup)
+    scaling = {str(threads): round(r["gups"], 5)}
+    if scaling_check and threads >= 2:
+        scaling[str(threads // 2)] = round(timed(threads // 2, 1, 1)["gups"], 5)
     sample = (f"3-D cavity {CPU_SAMPLE[1]['n']}^3 cells x {CPU_SAMPLE[1]['nDV']}^3 GH velocities "
-              f"({case.nCells * case.nXi:.3g} updates/step), {steps} steps after {warmup} warm-up")
-    return ups / 1e9, el / steps * 1e3, threads, sample
+              f"({r['updates']:.3g} updates/step), {steps} steps after {warmup} warm-up, {threads} OpenMP threads; "
+              f"GUPS by thread count: {scaling}")
+    return r["gups"], r["ms"], threads, sample
 
 
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--cpu-worker":
+        return _cpu_worker(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]))
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -158,14 +177,16 @@ def main():
         # port stands in), rank 0 only
         if rank != 0:
             return
-        K = max(1, min(args.steps, 4))
+        K = max(1, min(args.steps, 3))
         W = max(1, min(args.warmup, 1))
         gups, ms, cores, sample = run_cpu_reference(K, W)
         line = {
             "impl": "reference", "metric": METRIC, "value": gups, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
             "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl_name, "timed_on": sample, "parallelism": f"openmp{cores}"},
+            "config": {"workload": wl_name, "timed_on": sample, "parallelism": f"openmp{cores}",
+                       "same_config": False,
+                       "note": "the reference needs OpenFOAM + MPI (absent): oracle/ restates its loops; a bounded sample of the workload"},
             "cpu_baseline": {"value": gups, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": gups, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
@@ -352,7 +373,7 @@ def main():
                      "dominant_kernel": dom, "kernels": fam},
     }
     if not args.no_cpu_baseline and world == 1:
-        cg, cms, cores, sample = run_cpu_reference(args.cpu_steps, 1)
+        cg, cms, cores, sample = run_cpu_reference(min(args.cpu_steps, 2), 1)
         line["cpu_baseline"] = {"value": cg, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                                 "ms_per_step": cms}
     print(json.dumps(line), flush=True)

@@ -134,7 +134,7 @@ struct dugks_handle {
     // gBarP storage: one block per slab, or (wmode) ONE transient block shared by the face-storage slabs
     // (their update reads w, left in place of gTilde by the half-step kernel) + one block per other slab
     double *gb_store = nullptr, *hb_store = nullptr;
-    bool wmode = false, gb_in_fbuf = false;
+    bool wmode = false;
     size_t hsmem_rlx_w = 0;
     int hot_grid_rlx_w = 148;
     size_t hsmem_axis = 0;
@@ -438,12 +438,11 @@ static void map_gb(const dugks_handle* h, StepArgs& a) {
     if (!h->wmode) return;
     const long long stride = (long long)h->nc * h->L * h->Rs;
     if (a.slab < h->n_keep) {
-        // transient block of the face-storage slabs: the flux buffer when it is large enough (it is only
-        // used in phase 2 of the OTHER slabs, never while a phase-1 kernel runs), else block 0 of the store
-        a.gb = (h->gb_in_fbuf ? h->A.fbuf_g : h->gb_store) - a.slab * stride;
-        if (h->hb_store) a.hb = (h->gb_in_fbuf ? h->A.fbuf_h : h->hb_store) - a.slab * stride;
+        // transient block of the face-storage slabs: block 0 of the store
+        a.gb = h->gb_store - a.slab * stride;
+        if (h->hb_store) a.hb = h->hb_store - a.slab * stride;
     } else {
-        const long long block = (h->gb_in_fbuf ? 0 : 1) + (a.slab - h->n_keep);
+        const long long block = 1 + (a.slab - h->n_keep);
         a.gb = h->gb_store + (block - a.slab) * stride;
         if (h->hb_store) a.hb = h->hb_store + (block - a.slab) * stride;
     }
@@ -660,6 +659,10 @@ static int step_impl(dugks_handle* h, double dt) {
     size_t nslots = (size_t)2 * h->nif + h->nbf;
     CUDA_TRY(h, cudaMemsetAsync(a.fslot, 0, nslots * h->nm * sizeof(double), h->stream));
     CUDA_TRY(h, cudaMemsetAsync(a.cslot, 0, (size_t)h->nc * h->nm * sizeof(double), h->stream));
+    if (h->pen_mode == 2) {
+        k_cell_coef<<<(h->nc + 127) / 128, 128, 0, h->stream>>>(a);
+        if ((rc = check_launch(h, "k_cell_coef"))) return rc;
+    }
     for (int s = 0; s < h->nslab; s++) {
         a.slab = s;
         if ((rc = launch_slab_kernels_phase1<H>(h, a))) return rc;
@@ -1726,15 +1729,15 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
     TRYB(dev_alloc(h, &A.gsb, nb_dv + HOT_PAD));
     TRYB(dev_alloc(h, &h->gam_a_g, nb_dv + HOT_PAD));
     TRYB(dev_alloc(h, &h->gam_b_g, nb_dv + HOT_PAD));
-    TRYB(dev_alloc(h, &A.fbuf_g, (size_t)nif * L * h->Rs + HOT_PAD));
+    // the flux buffer of the recompute path (A.fbuf_*) is placed with the face storage below
     if (h->hasH) {
         TRYB(dev_alloc(h, &A.ht, ncell_dv + HOT_PAD));
         TRYB(dev_alloc(h, &A.hsb, nb_dv + HOT_PAD));
         TRYB(dev_alloc(h, &h->gam_a_h, nb_dv + HOT_PAD));
         TRYB(dev_alloc(h, &h->gam_b_h, nb_dv + HOT_PAD));
-        TRYB(dev_alloc(h, &A.fbuf_h, (size_t)nif * L * h->Rs + HOT_PAD));
     }
     TRYB(dev_alloc(h, &A.fcoef, (size_t)nf * FCOEF_N));
+    TRYB(dev_alloc(h, &A.ccoef, (size_t)nc * FCOEF_N));
     if (h->has_sym) {
         // g rows, then h rows: one buffer, one collective
         TRYB(dev_alloc(h, &h->sym_Xg, (size_t)h->sym_rows * h->nsym * nfld));
@@ -1839,21 +1842,22 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
         // left free: CUDA context growth and the caller's own allocations; NCCL buffers when there are peers
         const size_t reserve = nranks > 1 ? (size_t)3 << 30 : (size_t)3 << 29;
         const bool can_w = h->hsmem_half > 0 && getenv("DUGKS_NO_WMODE") == nullptr;   // test hook: persistent gBarP everywhere
-        h->gb_in_fbuf = can_w && nif >= nc;
         long long avail = free2 > reserve ? (long long)(free2 - reserve) : 0;
         // dugks_par_t.scratch_bytes: the caller's cap on what the kept face values (and the gBarP blocks that go
         // with them) may take; the slabs that do not fit recompute their face values in phase 2
         if (par->scratch_bytes > 0) avail = std::min<long long>(avail, (long long)std::min<size_t>(par->scratch_bytes, (size_t)1 << 62));
+        // k face-storage slabs need their face values and ONE transient gBarP block; the other slabs a gBarP block
+        // each and a flux buffer - which is the face storage of slab 0: phase 2 runs the face-storage slabs first, and
+        // slab 0's values are consumed by then
         long long fit = 0;
         for (long long k = h->nslab; k > 0; k--) {
-            const long long blocks = can_w ? (h->nslab - k) + (h->gb_in_fbuf ? 0 : 1) : h->nslab;
+            const long long blocks = can_w ? (h->nslab - k) + 1 : h->nslab;
             if (blocks * (long long)per_gb + k * (long long)per_slab <= avail) { fit = k; break; }
         }
         if (const char* e = getenv("DUGKS_KEEP_SLABS")) fit = std::min<long long>(fit, atoll(e));   // test hook
         h->n_keep = (int)std::max<long long>(0, std::min<long long>(fit, h->nslab));
         h->wmode = can_w && h->n_keep > 0;
-        h->gb_in_fbuf = h->gb_in_fbuf && h->wmode;
-        if (h->wmode) gb_blocks = (size_t)(h->nslab - h->n_keep) + (h->gb_in_fbuf ? 0 : 1);
+        if (h->wmode) gb_blocks = (size_t)(h->nslab - h->n_keep) + 1;
     }
     TRYB(dev_alloc(h, &h->gb_store, gb_blocks * nc * L * h->Rs + HOT_PAD));
     if (h->hasH) TRYB(dev_alloc(h, &h->hb_store, gb_blocks * nc * L * h->Rs + HOT_PAD));
@@ -1864,6 +1868,10 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
         // tie points are written by one side only and padding rows by nobody: start from zeros
         CUDAB(cudaMemsetAsync(h->fkeep_g, 0, ((size_t)h->n_keep * nif * L * h->Rs + HOT_PAD) * sizeof(double), h->stream));
         if (h->hasH) CUDAB(cudaMemsetAsync(h->fkeep_h, 0, ((size_t)h->n_keep * nif * L * h->Rs + HOT_PAD) * sizeof(double), h->stream));
+        A.fbuf_g = h->fkeep_g; A.fbuf_h = h->fkeep_h;      // flux buffer of the recompute slabs = face storage of slab 0 (phase 2 only)
+    } else {
+        TRYB(dev_alloc(h, &A.fbuf_g, (size_t)nif * L * h->Rs + HOT_PAD));
+        if (h->hasH) TRYB(dev_alloc(h, &A.fbuf_h, (size_t)nif * L * h->Rs + HOT_PAD));
     }
 
     // ---- collective backend

@@ -1278,7 +1278,7 @@ struct HotRelaxPlan {
     // the moment reduction (32 x 17 doubles) runs through the face tables, which are dead by then
     static constexpr int TAB_D = (NTABS * 4 * TW + NE * 2) > 32 * 17 ? (NTABS * 4 * TW + NE * 2) : 32 * 17;
     // face equilibrium records + outward area vectors of a cell (+ the cell's macro record, WMODE 2)
-    static constexpr int REC_D = NE * (FCOEF_N + 4) + (WMODE == 2 ? 10 : 0);
+    static constexpr int REC_D = NE * (FCOEF_N + 4) + (WMODE == 2 ? FCOEF_N : 0);
     static constexpr int PER_WARP_D = 2 * HOT_PTRS + 2 * REC_D + HOT_STAGES * STAGE_D + TAB_D;
     static constexpr size_t PER_WARP = ((size_t)PER_WARP_D * 8 + 127) / 128 * 128;
     static __host__ __device__ size_t txs_bytes(int ntab) { return ((size_t)(ntab + HOT_CI_MAX) * 48 + 127) / 128 * 128; }
@@ -1342,9 +1342,8 @@ k_hot_relax_update(StepArgs a) {
                     cp_async16(sd + NE * FCOEF_N * 8 + pe * 16, reinterpret_cast<const char*>(a.geoS + (size_t)M.e0 * 4) + pe * 16);
             }
         }
-        if (WMODE == 2 && lane < MAC_N)   // macro record of the cell (72 bytes, 8-byte aligned)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sd + (NE * (FCOEF_N + 4) + lane) * 8),
-                         "l"(a.cmac + (size_t)M.c * MAC_N + lane));
+        if (WMODE == 2 && lane < FCOEF_N / 2)   // half-step coefficient record of the cell (k_cell_coef)
+            cp_async16(sd + (NE * (FCOEF_N + 4) + 2 * lane) * 8, a.ccoef + (size_t)M.c * FCOEF_N + 2 * lane);
     };
     const unsigned long long pol_ef = l2_evict_first_policy();
     const unsigned long long pol_el = l2_evict_last_policy();
@@ -1440,22 +1439,20 @@ k_hot_relax_update(StepArgs a) {
         // WMODE 2: half-step table of the cell itself (the operations of k_hot_halfstep)
         double cEYZ = 0.0, cYZ2 = 0.0, cQYZ = 0.0, comrf = 0.0, cRT = 0.0;
         if (WMODE == 2) {
-            const double* mc = rec_s + NE * 4;
-            const double rf = 1.5 * a.dt / (2.0 * mc[5] + a.dt);         // discreteVelocity.C:393
-            const EqCoef e = make_eq(a.gas, mc, rf);
+            const double* rc = rec_s + NE * 4;                            // Ux Uy Uz a pre qx qy qz omrf RT (k_cell_coef)
             for (int tt = lane; tt < span; tt += 32) {
-                const double cx = txs[(tmin + tt) * 6 + 5] - e.Ux;
-                const double x2 = cx * cx * e.a;
+                const double cx = txs[(tmin + tt) * 6 + 5] - rc[0];
+                const double x2 = cx * cx * rc[3];
                 double* xt = ctab + tt * 4;
-                xt[0] = exp(-0.5 * x2); xt[1] = x2; xt[2] = cx * e.qx; xt[3] = 0.0;
+                xt[0] = exp(-0.5 * x2); xt[1] = x2; xt[2] = cx * rc[5]; xt[3] = 0.0;
             }
-            const double cy = y - e.Uy, cz = z - e.Uz;
-            const double yz2 = (cy * cy + cz * cz) * e.a;
-            cEYZ = e.pre * exp(-0.5 * yz2);
+            const double cy = y - rc[1], cz = z - rc[2];
+            const double yz2 = (cy * cy + cz * cz) * rc[3];
+            cEYZ = rc[4] * exp(-0.5 * yz2);
             cYZ2 = yz2 - a.gas.D - 2.0;
-            cQYZ = cy * e.qy + cz * e.qz;
-            comrf = 1.0 - rf;
-            cRT = e.RT;
+            cQYZ = cy * rc[6] + cz * rc[7];
+            comrf = rc[8];
+            cRT = rc[9];
         }
         __syncwarp();
         const double dtv = a.dt / a.m.V[c];

@@ -50,6 +50,7 @@ struct StepArgs {
     const int *cmeta;                       // [nc][20] per-cell record of the second-generation kernels (dugks_hot.cuh)
     const unsigned char *cell_cls;          // [nc] 1: axis-aligned interior cell (entries in axis order), else 0
     double *fkeep_g, *fkeep_h;              // [n_keep_slabs][nif][L][32] reconstructed face values (face-storage slabs) or null
+    double *ccoef;                          // [nc][12] half-step equilibrium records of the cells (k_cell_coef)
 };
 
 __device__ __forceinline__ size_t dv_index(const DevDV& dv, int slab, int n_outer, int outer, int i, int r) {
@@ -997,6 +998,21 @@ k_cell_update(StepArgs a) {
         }
         __syncwarp();
     }
+}
+
+// Half-step coefficients of every cell for this step (discreteVelocity.C:393-404): relaxation factor
+// rf = 1.5 dt / (2 tau + dt) and the Shakhov coefficients scaled by it, in the layout of the face records:
+// Ux Uy Uz a pre qx qy qz omrf RT 0 0.  One evaluation per cell and step instead of one per warp that needs the
+// cell's equilibrium (CTA pencils and the update kernel of fused slabs).
+__global__ void k_cell_coef(StepArgs a) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.m.nc) return;
+    const double* mc = a.cmac + (size_t)c * MAC_N;
+    const double rf = 1.5 * a.dt / (2.0 * mc[5] + a.dt);
+    const EqCoef e = make_eq(a.gas, mc, rf);
+    double* o = a.ccoef + (size_t)c * 12;
+    o[0] = e.Ux; o[1] = e.Uy; o[2] = e.Uz; o[3] = e.a; o[4] = e.pre; o[5] = e.qx; o[6] = e.qy; o[7] = e.qz;
+    o[8] = 1.0 - rf; o[9] = e.RT; o[10] = 0.0; o[11] = 0.0;
 }
 
 // ---------------------------------------------------------------------------------

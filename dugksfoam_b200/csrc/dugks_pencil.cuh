@@ -44,10 +44,10 @@ struct PenArgs {
 struct PenPlan {
     static __host__ __device__ size_t txs_bytes(int ntab) { return ((size_t)(ntab + HOT_CI_MAX) * 48 + 127) / 128 * 128; }
     static __host__ __device__ size_t win_bytes(int L) { return (size_t)3 * PEN_WARPS * L * 32 * 8; }
-    // per warp: halo stages [2][2][CI][32], geometry records [2][7 * 6], macro records [2][3][10], tables [3][tw][2]
-    // (tw: table entries a warp spans, DevDV::tabw)
+    // per warp: halo stages [2][2][CI][32], geometry records [2][7 * 6], half-step coefficient records
+    // [2][3][FCOEF_N], tables [3][tw][2]  (tw: table entries a warp spans, DevDV::tabw)
     static __host__ __device__ size_t warp_bytes(int tw) {
-        return ((size_t)(2 * 2 * PEN_CI * 32 + 2 * (1 + PEN_NE) * 6 + 2 * 3 * 10 + 3 * tw * 2) * 8 + 127) / 128 * 128;
+        return ((size_t)(2 * 2 * PEN_CI * 32 + 2 * (1 + PEN_NE) * 6 + 2 * 3 * FCOEF_N + 3 * tw * 2) * 8 + 127) / 128 * 128;
     }
     static __host__ size_t total(int L, int ntab, int tw) { return txs_bytes(ntab) + win_bytes(L) + PEN_WARPS * warp_bytes(tw); }
 };
@@ -96,8 +96,8 @@ k_pencil_phase1(StepArgs a, PenArgs P) {
     double* wbase = reinterpret_cast<double*>(dyn + PenPlan::txs_bytes(dv.ntab) + PenPlan::win_bytes(L) + wl * PenPlan::warp_bytes(TW));
     double* halo = wbase;                                   // [2 stages][2 (y, z)][CI][32]
     double* geo = halo + 2 * 2 * PEN_CI * 32;               // [2][7 * 6]
-    double* mrec = geo + 2 * (1 + PEN_NE) * 6;              // [2][3][10]: own(k+1), halo y(k), halo z(k)
-    double* xtab = mrec + 2 * 3 * 10;                       // [3][TW][2]: EX, X2
+    double* mrec = geo + 2 * (1 + PEN_NE) * 6;              // [2][3][FCOEF_N]: records of own(k+1), halo y(k), halo z(k)
+    double* xtab = mrec + 2 * 3 * FCOEF_N;                  // [3][TW][2]: EX, X2
     __syncthreads();
 
     const size_t slab_c = (size_t)a.slab * nc * blk;
@@ -136,30 +136,28 @@ k_pencil_phase1(StepArgs a, PenArgs P) {
             cp_async16(s + PEN_CI * 256 + part * 512, gz + part * 512);
         }
     };
-    // macro record (9 doubles, 8-byte aligned) of cell c into dst
+    // half-step coefficient record of cell c (k_cell_coef: Ux Uy Uz a pre qx qy qz omrf RT, 96 bytes) into dst
     auto load_mrec = [&](int c, double* dst, int l0) {
-        if (lane >= l0 && lane < l0 + MAC_N)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst + (lane - l0))),
-                         "l"(a.cmac + (size_t)c * MAC_N + (lane - l0)));
+        if (lane >= l0 && lane < l0 + FCOEF_N / 2)
+            cp_async16(smem_u32(dst + 2 * (lane - l0)), a.ccoef + (size_t)c * FCOEF_N + 2 * (lane - l0));
     };
-    // half-step conversion table of the cell whose macro record is mc (discreteVelocity.C:393-406, :1033-1043)
-    auto build_table = [&](const double* mc, double* xt, PenEq& E) {
-        const double rf = 1.5 * a.dt / (2.0 * mc[5] + a.dt);
-        const EqCoef e = make_eq(a.gas, mc, rf);
+    // half-step conversion table of the cell whose record is rc (discreteVelocity.C:393-406, :1033-1043)
+    auto build_table = [&](const double* rc, double* xt, PenEq& E) {
+        const double Ux = rc[0], ia = rc[3];
         for (int tt = lane; tt < span; tt += 32) {
-            const double cx = txs[(tmin + tt) * 6 + 5] - e.Ux;
-            const double x2 = cx * cx * e.a;
+            const double cx = txs[(tmin + tt) * 6 + 5] - Ux;
+            const double x2 = cx * cx * ia;
             xt[tt * 2] = exp(-0.5 * x2);
             xt[tt * 2 + 1] = x2;
         }
-        const double cy = y - e.Uy, cz = z - e.Uz;
-        const double yz2 = (cy * cy + cz * cz) * e.a;
-        E.EYZ = e.pre * exp(-0.5 * yz2);
+        const double cy = y - rc[1], cz = z - rc[2];
+        const double yz2 = (cy * cy + cz * cz) * ia;
+        E.EYZ = rc[4] * exp(-0.5 * yz2);
         E.YZ2 = yz2 - a.gas.D - 2.0;
-        E.QYZ = cy * e.qy + cz * e.qz;
-        E.omrf = 1.0 - rf;
-        E.Ux = e.Ux;
-        E.qx = e.qx;
+        E.QYZ = cy * rc[6] + cz * rc[7];
+        E.omrf = rc[8];
+        E.Ux = Ux;
+        E.qx = rc[5];
     };
     // gBarP of one value (same operations as k_hot_halfstep): xt = table row of the point, x = its abscissa
     auto convert = [&](double raw, const double* xt, double x, const PenEq& E) {
@@ -188,7 +186,7 @@ k_pencil_phase1(StepArgs a, PenArgs P) {
             load_halo(htab[0], htab[1], 0, halo + (q & 1) * (2 * PEN_CI * 32));
             if (FUSE) {
                 load_mrec(cm1, mrec, 0);                       // buffer 0: own(-1), own(0) for the prologue conversion
-                load_mrec(c0, mrec + 10, 9);
+                load_mrec(c0, mrec + FCOEF_N, 6);
             }
         }
         HotMeta cur{}, nxt{};
@@ -201,7 +199,7 @@ k_pencil_phase1(StepArgs a, PenArgs P) {
             PenEq E;
 #pragma unroll 1
             for (int t = 0; t < 2; t++) {
-                build_table(mrec + t * 10, xtab, E);
+                build_table(mrec + t * FCOEF_N, xtab, E);
                 __syncwarp();
                 double* blkp = wslot(t - 1, wl) + lane;
                 const double* xt0 = xtab + (cb - tmin) * 2;
@@ -210,8 +208,8 @@ k_pencil_phase1(StepArgs a, PenArgs P) {
             }
             // macros of step 0: own(1), halo(0); geometry of step 0
             load_mrec(ctab[8], mrec, 0);
-            load_mrec(htab[0], mrec + 10, 9);
-            load_mrec(htab[1], mrec + 20, 18);
+            load_mrec(htab[0], mrec + FCOEF_N, 6);
+            load_mrec(htab[1], mrec + 2 * FCOEF_N, 12);
         }
         hot_stage_geo(a.geo6 + (size_t)(cur.e0 + cur.c) * 6, PEN_NE, geo, lane);
         cp_async_commit();
@@ -234,10 +232,10 @@ k_pencil_phase1(StepArgs a, PenArgs P) {
             // ---- half-step tables of the blocks converted in this step: own(k + 1), halo y(k), halo z(k)
             PenEq Exp{}, Ehy{}, Ehz{};
             if (FUSE) {
-                const double* mr = mrec + gsel * 30;
+                const double* mr = mrec + gsel * (3 * FCOEF_N);
                 build_table(mr, xtab, Exp);
-                build_table(mr + 10, xtab + TW * 2, Ehy);
-                build_table(mr + 20, xtab + 2 * TW * 2, Ehz);
+                build_table(mr + FCOEF_N, xtab + TW * 2, Ehy);
+                build_table(mr + 2 * FCOEF_N, xtab + 2 * TW * 2, Ehz);
                 __syncwarp();
             }
             // ---- upwind sets (static codes), store pointers, accumulators: as hot_axis_item
@@ -303,10 +301,10 @@ k_pencil_phase1(StepArgs a, PenArgs P) {
                     if (ch > 0 && own_k2m >= 0) load_chunk(own_k2m, ch - 1, wnew);
                     if (FUSE && ch == 0 && k + 1 < ns) {
                         // macros of the blocks converted in step k + 1: own(k + 2), halo(k + 1)
-                        double* mr = mrec + (gsel ^ 1) * 30;
+                        double* mr = mrec + (gsel ^ 1) * (3 * FCOEF_N);
                         if (own_k2m >= 0) load_mrec(own_k2m, mr, 0);
-                        load_mrec(hy_n, mr + 10, 9);
-                        load_mrec(hz_n, mr + 20, 18);
+                        load_mrec(hy_n, mr + FCOEF_N, 6);
+                        load_mrec(hz_n, mr + 2 * FCOEF_N, 12);
                     }
                 }
                 cp_async_commit();
@@ -314,27 +312,38 @@ k_pencil_phase1(StepArgs a, PenArgs P) {
                 __syncwarp();
                 const double* sg = halo + (q & 1) * (2 * PEN_CI * 32) + lane;
                 const int nsub = min(PEN_CI / PEN_CU, (Ln - ch * PEN_CI) / PEN_CU);
-#pragma unroll 1
-                for (int sub = 0; sub < nsub; sub++) {
-                    const int i0 = ch * PEN_CI + sub * PEN_CU;
-                    const int tb = cb + i0;
-                    const int ti = tb - tmin;
+                // one base per stream and chunk; everything inside the (unrolled) chunk is a compile-time offset from it
+                const int c0 = ch * PEN_CI;
+                const double* const ck = wk + c0 * 32;
+                const double* const cm = wm + c0 * 32;
+                double* const cp = wp + c0 * 32;
+                const double* const cy_ = wy + c0 * 32;
+                const double* const cz_ = wz + c0 * 32;
+                const double* const ctx = txs + (cb + c0) * 6;
+                const double* const cxt = xtab + (cb + c0 - tmin) * 2;
+                double* const kxc[2] = {kx[0] + c0 * 32, kx[1] + c0 * 32};
+                double* const kpc[2] = {kp[0] + c0 * 32, kp[1] + c0 * 32};
+#pragma unroll
+                for (int sub = 0; sub < PEN_CI / PEN_CU; sub++) {
+                    if (sub >= nsub) break;                                        // warp-uniform (short last chunk)
+                    const int i0 = c0 + sub * PEN_CU;
+                    const int so = sub * PEN_CU;                                    // compile-time after unrolling
                     double v[PEN_CU], g0[PEN_CU], g1[PEN_CU], g2[PEN_CU], base[PEN_CU], W[PEN_CU][4];
 #pragma unroll
                     for (int u = 0; u < PEN_CU; u++) {
-                        const double2 t0 = lds2(txs + (tb + u) * 6), t1 = lds2(txs + (tb + u) * 6 + 2), t2 = lds2(txs + (tb + u) * 6 + 4);
+                        const double2 t0 = lds2(ctx + (so + u) * 6), t1 = lds2(ctx + (so + u) * 6 + 2), t2 = lds2(ctx + (so + u) * 6 + 4);
                         W[u][0] = t0.y; W[u][1] = t1.x; W[u][2] = t1.y; W[u][3] = t2.x;
                         const double xq = t2.y;
-                        v[u] = wk[(i0 + u) * 32];
-                        const double vxm = wm[(i0 + u) * 32];
-                        double vxp = wp[(i0 + u) * 32];
-                        const double vyi = wy[(i0 + u) * 32], vzi = wz[(i0 + u) * 32];
-                        double vyh = sg[(sub * PEN_CU + u) * 32], vzh = sg[(PEN_CI + sub * PEN_CU + u) * 32];
+                        v[u] = ck[(so + u) * 32];
+                        const double vxm = cm[(so + u) * 32];
+                        double vxp = cp[(so + u) * 32];
+                        const double vyi = cy_[(so + u) * 32], vzi = cz_[(so + u) * 32];
+                        double vyh = sg[(so + u) * 32], vzh = sg[(PEN_CI + so + u) * 32];
                         if (FUSE) {
-                            vxp = convert(vxp, xtab + (ti + u) * 2, xq, Exp);
-                            wp[(i0 + u) * 32] = vxp;                      // from now on the block holds gBarP
-                            vyh = convert(vyh, xtab + (TW + ti + u) * 2, xq, Ehy);
-                            vzh = convert(vzh, xtab + (2 * TW + ti + u) * 2, xq, Ehz);
+                            vxp = convert(vxp, cxt + (so + u) * 2, xq, Exp);
+                            cp[(so + u) * 32] = vxp;                      // from now on the block holds gBarP
+                            vyh = convert(vyh, cxt + (TW + so + u) * 2, xq, Ehy);
+                            vzh = convert(vzh, cxt + (2 * TW + so + u) * 2, xq, Ehz);
                         }
                         // gradient (stock leastSquaresGrad, zeroBoundaryGrad.C:90-99): one component per face
                         g0[u] = fma(Gxp, vxp, fma(Gxm, vxm, G0x * v[u]));
@@ -348,7 +357,7 @@ k_pencil_phase1(StepArgs a, PenArgs P) {
                     for (int j = 0; j < 2; j++) {
                         if (!((anyx[j] >> i0) & 1u)) continue;                      // warp-uniform
                         const double r = j ? rxp : rxm;
-                        double* const keep = kx[j];
+                        double* const keep = kxc[j] + so * 32;
                         if ((allx[j] >> i0) & 1u) {                                  // warp-uniform
 #pragma unroll
                             for (int u = 0; u < PEN_CU; u++) {
@@ -379,13 +388,11 @@ k_pencil_phase1(StepArgs a, PenArgs P) {
 #pragma unroll
                         for (int u = 0; u < PEN_CU; u++) {
                             const double val = fma(rsel[p], p ? g2[u] : g1[u], base[u]);
-                            if (st) __stcs(kp[p] + u * 32, val);
+                            if (st) __stcs(kpc[p] + (so + u) * 32, val);
                             ap[p][0] = fma(W[u][0], val, ap[p][0]); ap[p][1] = fma(W[u][1], val, ap[p][1]);
                             ap[p][2] = fma(W[u][2], val, ap[p][2]); ap[p][3] = fma(W[u][3], val, ap[p][3]);
                         }
                     }
-#pragma unroll
-                    for (int j = 0; j < 2; j++) { kx[j] += PEN_CU * 32; kp[j] += PEN_CU * 32; }
                 }
                 __syncwarp();   // every lane is done with this halo stage (and this chunk of the window) before the refill
                 q++;

@@ -21,6 +21,7 @@
  * Build: see oracle/Makefile  (gcc -O2 -fopenmp -ffp-contract=off -shared).
  */
 #include <math.h>
+#include <omp.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -583,62 +584,127 @@ static void stage_symmetryIn(oracle_t *o) {
         (result) = tot__;                                        \
     } while (0)
 
+/* The DV sums of fvDVM::updateMacroSurf / updateMacroVol (fvDVM.C:473-483,503-516 and :612-622,712-721), for the
+ * n <= MBLK consecutive entries [e0, e0 + n) of a DV-major field pair g, h (leading dimension ld).  The reference
+ * streams one whole field per discrete velocity (DV outermost); this is that loop restricted to a block of entries
+ * that stays in cache, so every memory access is contiguous.  Per entry the terms are added in the order of the
+ * reference (k ascending inside a rank, ranks in order: forAll(DV_) + MPI_Allreduce): same bits as the
+ * entry-by-entry RANK_SUM form. */
+#define MBLK 512
+static void dv_moments(const oracle_t *o, const double *g, const double *h, size_t ld, int e0, int n,
+                       double *rho, double *rU, double *rE) {
+    double a0[MBLK], a1[MBLK], a2[MBLK], a3[MBLK], aE[MBLK];
+    for (int j = 0; j < n; j++) { rho[j] = 0.0; rU[3 * j] = rU[3 * j + 1] = rU[3 * j + 2] = 0.0; rE[j] = 0.0; }
+    for (int r = 0; r < o->P; r++) {
+        for (int j = 0; j < n; j++) a0[j] = a1[j] = a2[j] = a3[j] = aE[j] = 0.0;
+        for (int k = 0; k < o->nxi; k++) {
+            if (o->rank_of[k] != r) continue;
+            const double w = o->w[k], x = o->xi[3 * k], y = o->xi[3 * k + 1], z = o->xi[3 * k + 2];
+            const double x2 = dot3(o->xi + 3 * k, o->xi + 3 * k);
+            const double *gk = g + (size_t)k * ld + e0, *hk = h + (size_t)k * ld + e0;
+            for (int j = 0; j < n; j++) {
+                a0[j] += w * gk[j];
+                a1[j] += w * gk[j] * x;
+                a2[j] += w * gk[j] * y;
+                a3[j] += w * gk[j] * z;
+                aE[j] += 0.5 * w * (gk[j] * x2 + hk[j]);
+            }
+        }
+        for (int j = 0; j < n; j++) {
+            rho[j] += a0[j]; rU[3 * j] += a1[j]; rU[3 * j + 1] += a2[j]; rU[3 * j + 2] += a3[j]; rE[j] += aE[j];
+        }
+    }
+}
+
+/* second pass: 1/2 sum w c (|c|^2 g + h), c = xi - U[entry] */
+static void dv_heat_flux(const oracle_t *o, const double *g, const double *h, size_t ld, int e0, int n,
+                         const double *U /* [n][3] */, double *q /* [n][3] */) {
+    double a[3][MBLK];
+    for (int j = 0; j < 3 * n; j++) q[j] = 0.0;
+    for (int r = 0; r < o->P; r++) {
+        for (int d = 0; d < 3; d++) for (int j = 0; j < n; j++) a[d][j] = 0.0;
+        for (int k = 0; k < o->nxi; k++) {
+            if (o->rank_of[k] != r) continue;
+            const double w = o->w[k], x = o->xi[3 * k], y = o->xi[3 * k + 1], z = o->xi[3 * k + 2];
+            const double *gk = g + (size_t)k * ld + e0, *hk = h + (size_t)k * ld + e0;
+            for (int j = 0; j < n; j++) {
+                const double cx = x - U[3 * j], cy = y - U[3 * j + 1], cz = z - U[3 * j + 2];
+                const double m = (cx * cx + cy * cy + cz * cz) * gk[j] + hk[j];
+                a[0][j] += 0.5 * w * cx * m;
+                a[1][j] += 0.5 * w * cy * m;
+                a[2][j] += 0.5 * w * cz * m;
+            }
+        }
+        for (int d = 0; d < 3; d++) for (int j = 0; j < n; j++) q[3 * j + d] += a[d][j];
+    }
+}
+
 /* stage 3: fvDVM::updateMacroSurf fvDVM.C:456-582 */
 static void stage_macroSurf(oracle_t *o, double dt) {
     int nf = o->nf, nif = o->nif;
     const double R = o->R;
     const int K = o->K;
-#pragma omp parallel for schedule(static)
-    for (int f = 0; f < nf; f++) {
-        double rho, rU[3], rE;
-        RANK_SUM(rho, o->w[k] * o->gSurf[(size_t)k * nf + f]); /* :476 */
-        for (int d = 0; d < 3; d++)
-            RANK_SUM(rU[d], o->w[k] * o->gSurf[(size_t)k * nf + f] * o->xi[3 * k + d]); /* :477 */
-        RANK_SUM(rE, 0.5 * o->w[k] * (o->gSurf[(size_t)k * nf + f] * dot3(o->xi + 3 * k, o->xi + 3 * k) +
-                                      o->hSurf[(size_t)k * nf + f])); /* :478-482 */
-        double Us[3] = {rU[0] / rho, rU[1] / rho, rU[2] / rho}; /* :493 */
-        double Ts = (rE - 0.5 * rho * dot3(Us, Us)) / ((K + 3) / 2.0 * R * rho); /* :495 */
-        double taus = tau_of(o, Ts, rho); /* :497 */
-        double qs[3];
-        for (int d = 0; d < 3; d++) { /* :503-519 */
-            RANK_SUM(qs[d], 0.5 * o->w[k] * (o->xi[3 * k + d] - Us[d]) *
-                                ((  (o->xi[3 * k] - Us[0]) * (o->xi[3 * k] - Us[0])
-                                  + (o->xi[3 * k + 1] - Us[1]) * (o->xi[3 * k + 1] - Us[1])
-                                  + (o->xi[3 * k + 2] - Us[2]) * (o->xi[3 * k + 2] - Us[2])) *
-                                     o->gSurf[(size_t)k * nf + f] +
-                                 o->hSurf[(size_t)k * nf + f]));
+#pragma omp parallel for schedule(dynamic)
+    for (int f0 = 0; f0 < nf; f0 += MBLK) {
+        const int n = nf - f0 < MBLK ? nf - f0 : MBLK;
+        double rho[MBLK], rU[3 * MBLK], rE[MBLK], qs[3 * MBLK];
+        dv_moments(o, o->gSurf, o->hSurf, (size_t)nf, f0, n, rho, rU, rE); /* :473-490 */
+        for (int j = 0; j < n; j++) {
+            const int f = f0 + j;
+            double *Us = o->US + 3 * f;
+            for (int d = 0; d < 3; d++) Us[d] = rU[3 * j + d] / rho[j]; /* :493 */
+            o->rhoS[f] = rho[j];
+            o->TS[f] = (rE[j] - 0.5 * rho[j] * dot3(Us, Us)) / ((K + 3) / 2.0 * R * rho[j]); /* :495 */
+            o->tauS[f] = tau_of(o, o->TS[f], rho[j]); /* :497 */
         }
-        double fac = 2.0 * taus / (2.0 * taus + 0.5 * dt * o->Pr); /* :522 */
-        o->rhoS[f] = rho; o->TS[f] = Ts; o->tauS[f] = taus;
-        for (int d = 0; d < 3; d++) { o->US[3 * f + d] = Us[d]; o->qS[3 * f + d] = fac * qs[d]; }
+        dv_heat_flux(o, o->gSurf, o->hSurf, (size_t)nf, f0, n, o->US + 3 * (size_t)f0, qs); /* :503-519 */
+        for (int j = 0; j < n; j++) {
+            const int f = f0 + j;
+            double fac = 2.0 * o->tauS[f] / (2.0 * o->tauS[f] + 0.5 * dt * o->Pr); /* :522 */
+            for (int d = 0; d < 3; d++) o->qS[3 * f + d] = fac * qs[3 * j + d];
+        }
     }
-    /* :539-581 wall diagnostics */
+    /* :539-581 wall diagnostics: per wall face 1/2 sum w c (|c|^2 g + h) with c = xi - U_wall, and sum w g xi xi;
+     * blocks of boundary faces, DV outermost inside a block (contiguous reads), terms added per face in the
+     * reference's order (k ascending inside a rank, ranks in order) */
     memset(o->qWall, 0, sizeof(double) * 3 * o->nbf);
     memset(o->stressWall, 0, sizeof(double) * 9 * o->nbf);
     for (int p = 0; p < o->npatch; p++) {
         if (o->patch[p].kind != DUGKS_PATCH_MAXWELL_WALL) continue;
-        for (int j = 0; j < o->patch[p].size; j++) {
-            int b = o->patch[p].start + j, f = nif + b;
-            const double *Up = o->U_b + 3 * b;
-            double taup = o->tauS[f];
-            double fq = 2.0 * taup / (2.0 * taup + 0.5 * dt * o->Pr); /* :571 */
-            double fs = 2.0 * taup / (2.0 * taup + 0.5 * dt);         /* :573 */
-            for (int d = 0; d < 3; d++) {
-                double v;
-                RANK_SUM(v, 0.5 * o->w[k] * (o->xi[3 * k + d] - Up[d]) *
-                                ((  (o->xi[3 * k] - Up[0]) * (o->xi[3 * k] - Up[0])
-                                  + (o->xi[3 * k + 1] - Up[1]) * (o->xi[3 * k + 1] - Up[1])
-                                  + (o->xi[3 * k + 2] - Up[2]) * (o->xi[3 * k + 2] - Up[2])) *
-                                     o->gSurf[(size_t)k * nf + f] +
-                                 o->hSurf[(size_t)k * nf + f])); /* :563-567 */
-                o->qWall[3 * b + d] = fq * v;
-            }
-            for (int a = 0; a < 3; a++)
-                for (int c = 0; c < 3; c++) {
-                    double v;
-                    RANK_SUM(v, o->w[k] * o->gSurf[(size_t)k * nf + f] * o->xi[3 * k + a] * o->xi[3 * k + c]); /* :568-569 */
-                    o->stressWall[9 * b + 3 * a + c] = fs * v;
+        const int pb0 = o->patch[p].start, pn = o->patch[p].size;
+#pragma omp parallel for schedule(dynamic)
+        for (int j0 = 0; j0 < pn; j0 += MBLK) {
+            const int n = pn - j0 < MBLK ? pn - j0 : MBLK;
+            const int b0 = pb0 + j0;
+            double acc[12][MBLK], tot[12][MBLK];
+            for (int m = 0; m < 12; m++) for (int j = 0; j < n; j++) tot[m][j] = 0.0;
+            for (int r = 0; r < o->P; r++) {
+                for (int m = 0; m < 12; m++) for (int j = 0; j < n; j++) acc[m][j] = 0.0;
+                for (int k = 0; k < o->nxi; k++) {
+                    if (o->rank_of[k] != r) continue;
+                    const double w = o->w[k], *xi = o->xi + 3 * k;
+                    const double *gk = o->gSurf + (size_t)k * nf + nif + b0, *hk = o->hSurf + (size_t)k * nf + nif + b0;
+                    for (int j = 0; j < n; j++) {
+                        const double *Up = o->U_b + 3 * (b0 + j);
+                        const double cx = xi[0] - Up[0], cy = xi[1] - Up[1], cz = xi[2] - Up[2];
+                        const double m = (cx * cx + cy * cy + cz * cz) * gk[j] + hk[j]; /* :563-567 */
+                        acc[0][j] += 0.5 * w * cx * m;
+                        acc[1][j] += 0.5 * w * cy * m;
+                        acc[2][j] += 0.5 * w * cz * m;
+                        for (int a = 0; a < 3; a++)
+                            for (int c = 0; c < 3; c++) acc[3 + 3 * a + c][j] += w * gk[j] * xi[a] * xi[c]; /* :568-569 */
+                    }
                 }
+                for (int m = 0; m < 12; m++) for (int j = 0; j < n; j++) tot[m][j] += acc[m][j];
+            }
+            for (int j = 0; j < n; j++) {
+                const int b = b0 + j, f = nif + b;
+                double taup = o->tauS[f];
+                double fq = 2.0 * taup / (2.0 * taup + 0.5 * dt * o->Pr); /* :571 */
+                double fs = 2.0 * taup / (2.0 * taup + 0.5 * dt);         /* :573 */
+                for (int d = 0; d < 3; d++) o->qWall[3 * b + d] = fq * tot[d][j];
+                for (int m = 0; m < 9; m++) o->stressWall[9 * b + m] = fs * tot[3 + m][j];
+            }
         }
     }
 }
@@ -720,49 +786,57 @@ static void stage_macroVol(oracle_t *o, double dt) {
     int nc = o->nc;
     const double R = o->R;
     const int K = o->K;
-#pragma omp parallel for schedule(static)
-    for (int c = 0; c < nc; c++) {
-        double rho, rU[3], rE;
-        RANK_SUM(rho, o->w[k] * o->gTilde[(size_t)k * nc + c]); /* :615 */
-        for (int d = 0; d < 3; d++)
-            RANK_SUM(rU[d], o->w[k] * o->gTilde[(size_t)k * nc + c] * o->xi[3 * k + d]); /* :616 */
-        RANK_SUM(rE, 0.5 * o->w[k] * (dot3(o->xi + 3 * k, o->xi + 3 * k) * o->gTilde[(size_t)k * nc + c] +
-                                      o->hTilde[(size_t)k * nc + c])); /* :617-621 */
-        o->rho[c] = rho;
-        for (int d = 0; d < 3; d++) o->U[3 * c + d] = rU[d] / rho; /* :694 */
-        o->T[c] = (rE - 0.5 * rho * dot3(o->U + 3 * c, o->U + 3 * c)) / ((K + 3) / 2.0 * R * rho); /* :695 */
-        o->tau[c] = tau_of(o, o->T[c], rho); /* :707 */
+#pragma omp parallel for schedule(dynamic)
+    for (int c0 = 0; c0 < nc; c0 += MBLK) {
+        const int n = nc - c0 < MBLK ? nc - c0 : MBLK;
+        double rho[MBLK], rU[3 * MBLK], rE[MBLK];
+        dv_moments(o, o->gTilde, o->hTilde, (size_t)nc, c0, n, rho, rU, rE); /* :612-628 */
+        for (int j = 0; j < n; j++) {
+            const int c = c0 + j;
+            o->rho[c] = rho[j];
+            for (int d = 0; d < 3; d++) o->U[3 * c + d] = rU[3 * j + d] / rho[j]; /* :694 */
+            o->T[c] = (rE[j] - 0.5 * rho[j] * dot3(o->U + 3 * c, o->U + 3 * c)) / ((K + 3) / 2.0 * R * rho[j]); /* :695 */
+            o->tau[c] = tau_of(o, o->T[c], rho[j]); /* :707 */
+        }
     }
     correct_macro_bcs(o); /* :698-699 */
-#pragma omp parallel for schedule(static)
-    for (int c = 0; c < nc; c++) {
-        const double *Uc = o->U + 3 * c;
-        double fac = 2.0 * o->tau[c] / (2.0 * o->tau[c] + dt * o->Pr); /* :727 */
-        for (int d = 0; d < 3; d++) {
-            double v;
-            RANK_SUM(v, 0.5 * o->w[k] * (o->xi[3 * k + d] - Uc[d]) *
-                            ((  (o->xi[3 * k] - Uc[0]) * (o->xi[3 * k] - Uc[0])
-                              + (o->xi[3 * k + 1] - Uc[1]) * (o->xi[3 * k + 1] - Uc[1])
-                              + (o->xi[3 * k + 2] - Uc[2]) * (o->xi[3 * k + 2] - Uc[2])) *
-                                 o->gTilde[(size_t)k * nc + c] +
-                             o->hTilde[(size_t)k * nc + c])); /* :712-721 */
-            o->q[3 * c + d] = fac * v;
+#pragma omp parallel for schedule(dynamic)
+    for (int c0 = 0; c0 < nc; c0 += MBLK) {
+        const int n = nc - c0 < MBLK ? nc - c0 : MBLK;
+        double qs[3 * MBLK];
+        dv_heat_flux(o, o->gTilde, o->hTilde, (size_t)nc, c0, n, o->U + 3 * (size_t)c0, qs); /* :712-725 */
+        for (int j = 0; j < n; j++) {
+            const int c = c0 + j;
+            double fac = 2.0 * o->tau[c] / (2.0 * o->tau[c] + dt * o->Pr); /* :727 */
+            for (int d = 0; d < 3; d++) o->q[3 * c + d] = fac * qs[3 * j + d];
         }
     }
 }
 
 /* fvDVM::evolution fvDVM.C:1086-1108 */
 void oracle_step(oracle_t *o, double dt) {
-    stage_barPvol(o, dt);     /* :1089 */
-    stage_barSurf(o, dt);     /* :1091 */
-    stage_wallRho(o);         /* :1093 */
-    stage_wallIn(o);          /* :1095 */
-    stage_symmetryIn(o);      /* :1097 */
-    stage_macroSurf(o, dt);   /* :1099 */
-    stage_surf(o, dt);        /* :1101 */
-    stage_tildeVol(o, dt);    /* :1103 */
-    stage_macroVol(o, dt);    /* :1105 */
-    update_pressure_bc(o);    /* :1107 */
+    /* ORACLE_TIMING=1: wall time per stage on stderr (where the CPU baseline of bench.py spends its time) */
+    const int timing = getenv("ORACLE_TIMING") != NULL;
+    double t[11];
+#define STAGE(i, call) do { call; if (timing) t[i] = omp_get_wtime(); } while (0)
+    if (timing) t[0] = omp_get_wtime();
+    STAGE(1, stage_barPvol(o, dt));     /* :1089 */
+    STAGE(2, stage_barSurf(o, dt));     /* :1091 */
+    STAGE(3, stage_wallRho(o));         /* :1093 */
+    STAGE(4, stage_wallIn(o));          /* :1095 */
+    STAGE(5, stage_symmetryIn(o));      /* :1097 */
+    STAGE(6, stage_macroSurf(o, dt));   /* :1099 */
+    STAGE(7, stage_surf(o, dt));        /* :1101 */
+    STAGE(8, stage_tildeVol(o, dt));    /* :1103 */
+    STAGE(9, stage_macroVol(o, dt));    /* :1105 */
+    STAGE(10, update_pressure_bc(o));   /* :1107 */
+#undef STAGE
+    if (timing) {
+        static const char *nm[] = {"", "barPvol", "barSurf", "wallRho", "wallIn", "symmetryIn", "macroSurf", "surf", "tildeVol", "macroVol", "pressureBC"};
+        fprintf(stderr, "oracle_step:");
+        for (int i = 1; i <= 10; i++) fprintf(stderr, " %s %.3f", nm[i], t[i] - t[i - 1]);
+        fprintf(stderr, " s\n");
+    }
     o->steps++;
 }
 

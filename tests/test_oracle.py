@@ -222,3 +222,138 @@ def test_convergence_monitor(oracle_lib):
     assert all(v > 0 for v in got)
     assert orc.convergence() == (0.0, 0.0, 0.0)      # the snapshot was replaced by the current fields
     orc.close()
+
+
+# ---- a second, independent restatement (oracle/dugks_numpy.py) ---------------------------------------------
+def _xcheck_zoo():
+    K = cs
+    p0 = K.RHO0 * K.ARGON["R"] * K.T0
+    return [
+        ("cavity2d_6_gh8_distort", cs.cavity2d_case(6, 8, distort=0.2, perturb=0.02)),
+        ("cavity3d_4_gh8_distort", cs.cavity3d_case(4, 8, distort=0.1, perturb=0.02)),
+        ("tri_5_gh8", cs.tri_cavity_case(5, 8, perturb=0.02)),
+        ("cavity2d_5_nc9_ties", cs.cavity2d_case(5, 9, quad="NC", perturb=0.02)),
+        ("farfield_zg_mixed", util.channel_case(
+            6, 4, 8, kinds={"inlet": K.PATCH_FAR_FIELD, "outlet": K.PATCH_ZERO_GRADIENT, "top": K.PATCH_MIXED},
+            bc_overrides={"inlet": dict(U=(30.0, 0, 0), rho=1.2 * K.RHO0, T=290.0, U_bc=K.BC_ZERO_GRADIENT),
+                          "top": dict(U=(20.0, 0, 0), T=280.0)}, perturb=0.01, distort=0.1)),
+        ("pressure_in_out", util.channel_case(
+            6, 4, 8, kinds={"inlet": K.PATCH_PRESSURE_IN, "outlet": K.PATCH_PRESSURE_OUT},
+            bc_overrides={"inlet": dict(pressure=1.1 * p0), "outlet": dict(pressure=0.9 * p0)}, perturb=0.01)),
+        ("dvm_symmetry_xy", util.channel_case(
+            6, 4, 8, kinds={"inlet": K.PATCH_DVM_SYMMETRY, "bottom": K.PATCH_DVM_SYMMETRY},
+            bc_overrides={"top": dict(U=(40.0, 0, 0))}, perturb=0.01)),
+    ]
+
+
+@pytest.mark.parametrize("name,case", _xcheck_zoo(), ids=[c[0] for c in _xcheck_zoo()])
+def test_two_independent_restatements_agree(oracle_lib, name, case):
+    """The C oracle (stage by stage, scalar loops) and oracle/dugks_numpy.py (field at a time, written separately
+    from the reference text, no shared code) give the same step to round-off on every boundary kind: a misreading
+    of the reference would have to be made twice, independently, to go unnoticed."""
+    from oracle.dugks_numpy import NumpyDVM
+    o, p = oracle_lib.Oracle(case), NumpyDVM(case)
+    dt = case.courant_dt(0.5)
+    sc = util.macro_scales(case)
+    assert np.allclose(o.courant(dt), p.courant(dt), rtol=1e-13)
+    for s in range(3):
+        o.step(dt * (1 + 0.1 * s)); p.step(dt * (1 + 0.1 * s))
+    m, f, b, wd = o.cell_macros(), o.face_macros(), o.boundary_macros(), o.wall_diag()
+    g, h = o.state()
+    errs = dict(rho=util.rel_err(p.rho, m["rho"]), T=util.rel_err(p.T, m["T"]), U=util.rel_err(p.U, m["U"], sc["U"]),
+                q=util.rel_err(p.q, m["q"], sc["q"]), tau=util.rel_err(p.tau, m["tau"]),
+                face_rho=util.rel_err(p.rhoSurf, f["rho"]), face_q=util.rel_err(p.qSurf, f["q"], sc["q"]),
+                face_U=util.rel_err(p.Usurf, f["U"], sc["U"]), bnd_rho=util.rel_err(p.rho_b, b["rho"], sc["rho"]),
+                bnd_U=util.rel_err(p.U_b, b["U"], sc["U"]), bnd_T=util.rel_err(p.T_b, b["T"]),
+                g=util.rel_err(p.gT, g), h=util.rel_err(p.hT, h, max(np.abs(h).max(), 1e-300)),
+                qWall=util.rel_err(p.qWall, wd["qWall"], sc["q"]),
+                stressWall=util.rel_err(p.stressWall.reshape(-1, 9), wd["stressWall"], sc["rho"] * sc["U"] ** 2))
+    assert max(errs.values()) <= 1e-13, errs
+    assert np.allclose(o.courant(dt), p.courant(dt), rtol=1e-12)
+    o.close()
+
+
+def test_geometry_against_independent_formulas():
+    """[OF-lib] geometry checked WITHOUT polymesh.py's code path: areas and
+    centroids by the shoelace / divergence-theorem formulas from a different apex, interpolation weights, patch
+    deltas and the least-squares vectors rebuilt cell by cell with plain loops from their definition."""
+    sheared = hex_block(3, 2, 2, (1.0, 0.8, 0.6))
+    # an affine map keeps faces planar (a random distortion in 3-D warps them, and the fan about the vertex average
+    # that OpenFOAM uses then differs from any other triangulation at second order in the warp)
+    sheared.points = np.ascontiguousarray(sheared.points @ np.array([[1.0, 0.3, 0.1], [0.2, 1.0, -0.25], [-0.15, 0.1, 1.0]]).T)
+    for mesh in (hex_block(3, 3, 1, (1.0, 0.9, 0.1), two_d=True, distort=0.25), sheared):
+        g = compute_geometry(mesh)
+        P = mesh.points
+        nF = mesh.nFaces
+        # faces: area vector = 1/2 sum p_i x p_{i+1}; centroid = area-weighted centroid of the fan about vertex 0
+        Sf = np.zeros((nF, 3)); Cf = np.zeros((nF, 3))
+        for f in range(nF):
+            v = P[mesh.face_verts[mesh.face_offsets[f]:mesh.face_offsets[f + 1]]]
+            S = sum(np.cross(v[i], v[(i + 1) % len(v)]) for i in range(len(v))) / 2.0
+            num, den = np.zeros(3), 0.0
+            for i in range(1, len(v) - 1):
+                a = np.cross(v[i] - v[0], v[i + 1] - v[0]) / 2.0
+                wgt = a @ S / np.linalg.norm(S)
+                num += wgt * (v[0] + v[i] + v[i + 1]) / 3.0; den += wgt
+            Sf[f], Cf[f] = S, num / den
+        # cells: V = 1/3 sum Cf.Sf (outward); centroid from tetrahedra (apex = a vertex of the cell)
+        own_all, nei = mesh.owner, mesh.neighbour
+        V = np.zeros(mesh.nCells); Cc = np.zeros((mesh.nCells, 3)); apex = {}
+        faces_of = [[] for _ in range(mesh.nCells)]
+        for f in range(nF):
+            faces_of[own_all[f]].append((f, 1.0))
+            if f < len(nei):
+                faces_of[nei[f]].append((f, -1.0))
+        for c in range(mesh.nCells):
+            a0 = P[mesh.face_verts[mesh.face_offsets[faces_of[c][0][0]]]]
+            vol, mom = 0.0, np.zeros(3)
+            for f, sgn in faces_of[c]:
+                v = P[mesh.face_verts[mesh.face_offsets[f]:mesh.face_offsets[f + 1]]]
+                for i in range(1, len(v) - 1):
+                    t = sgn * np.dot(np.cross(v[i] - v[0], v[i + 1] - v[0]), v[0] - a0) / 6.0   # signed tetrahedron volume
+                    vol += t; mom += t * (a0 + v[0] + v[i] + v[i + 1]) / 4.0
+            V[c], Cc[c] = vol, mom / vol
+        # the solver's face list = internal faces + faces of non-empty patches, in that order
+        bfaces = []
+        for p in mesh.patches:
+            if p.type != "empty":
+                bfaces += list(range(p.startFace, p.startFace + p.nFaces))
+        sel = np.r_[np.arange(g.nInternalFaces), np.array(bfaces, dtype=int)]
+        tolg = 1e-12
+        assert np.allclose(g.Sf, Sf[sel], rtol=0, atol=1e-14) and np.allclose(g.Cf, Cf[sel], rtol=0, atol=tolg)
+        assert np.allclose(g.V, V, rtol=tolg) and np.allclose(g.C, Cc, rtol=0, atol=tolg)
+        # least-squares vectors from their definition, with polymesh's own C, Cf, Sf as input (Appendix C 3-6)
+        nif = g.nInternalFaces
+        dd = np.zeros((g.nCells, 3, 3))
+        wf = np.zeros(nif)
+        for f in range(nif):
+            o_, n_ = g.owner[f], g.neighbour[f]
+            sn, sp = abs(g.Sf[f] @ (g.C[n_] - g.Cf[f])), abs(g.Sf[f] @ (g.Cf[f] - g.C[o_]))
+            wf[f] = sn / (sp + sn)
+            d = g.C[n_] - g.C[o_]
+            wdd = np.linalg.norm(g.Sf[f]) / (d @ d) * np.outer(d, d)
+            dd[o_] += (1 - wf[f]) * wdd; dd[n_] += wf[f] * wdd
+            assert abs(g.deltaCoeffs[f] - 1 / np.linalg.norm(d)) < 1e-12 / np.linalg.norm(d)
+        deltas = []
+        for b in range(g.nBoundaryFaces):
+            f = nif + b; o_ = g.owner[f]
+            nh = g.Sf[f] / np.linalg.norm(g.Sf[f])
+            d = nh * (nh @ (g.Cf[f] - g.C[o_]))
+            deltas.append(d)
+            dd[o_] += np.linalg.norm(g.Sf[f]) / (d @ d) * np.outer(d, d)
+            assert abs(g.deltaCoeffs[f] - 1 / np.linalg.norm(d)) < 1e-12 / np.linalg.norm(d)
+        solved = ~g.empty_dirs
+        inv = np.zeros_like(dd)
+        for c in range(g.nCells):
+            sub = dd[c][np.ix_(solved, solved)]
+            inv[c][np.ix_(solved, solved)] = np.linalg.inv(sub)
+        for f in range(nif):
+            o_, n_ = g.owner[f], g.neighbour[f]
+            d = g.C[n_] - g.C[o_]
+            k = np.linalg.norm(g.Sf[f]) / (d @ d)
+            assert np.allclose(g.ownLs[f], (1 - wf[f]) * k * (inv[o_] @ d), rtol=1e-10, atol=1e-12 * np.abs(g.ownLs).max())
+            assert np.allclose(g.neiLs[f], -wf[f] * k * (inv[n_] @ d), rtol=1e-10, atol=1e-12 * np.abs(g.neiLs).max())
+        for b in range(g.nBoundaryFaces):
+            f = nif + b; o_ = g.owner[f]; d = deltas[b]
+            assert np.allclose(g.patchLs[b], np.linalg.norm(g.Sf[f]) / (d @ d) * (inv[o_] @ d), rtol=1e-10,
+                               atol=1e-12 * np.abs(g.patchLs).max())
