@@ -14,7 +14,7 @@ import numpy as np
 
 from . import dvset as _dvset
 from . import foam
-from .polymesh import Geometry, PolyMesh, compute_geometry, hex_block, tri_prism_2d
+from .polymesh import Geometry, PolyMesh, compute_geometry, hex_block, ogrid_cylinder, tri_prism_2d
 
 # dugks_patch_kind (include/dugks.h)
 PATCH_ZERO_GRADIENT, PATCH_MIXED, PATCH_MAXWELL_WALL, PATCH_FAR_FIELD = 0, 1, 2, 3
@@ -229,3 +229,32 @@ def tri_cavity_case(n: int, nDV: int = 28, *, distort: float = 0.15, wall_T=None
     Xis, w = gh_set(nDV)
     return _uniform_case(mesh, Xis, w, {}, wall_T=wall_T or {"movingWall": 300.0}, name=f"tri_{n}x{n}_GH{nDV}",
                          perturb=perturb)
+
+
+def cylinder_case(ntheta: int, nr: int, nDV: int = 81, *, mach: float = 5.0, quad: str = "NC", xiMax: Optional[float] = None,
+                  r_in: float = 0.5, r_out: float = 15.0, T_wall: float = T0, perturb: float = 0.0,
+                  blend: float = 3.0) -> Case:
+    """2-D hypersonic flow past a circular cylinder (BASELINE config 5): O-type quadrilateral mesh, free stream at
+    `mach` along +x (argon, Pr = 2/3, T = 273 K), outer boundary with fixedValue rho / U / T - the reference's way
+    of imposing a free stream: DF boundary type "mixed" (doc/usage.tex:85-89, discreteVelocity.C:556-573: the
+    incoming half keeps the free-stream Maxwellian of t = 0) - and a diffuse (calculatedMaxwell) cylinder.
+    Velocity set: compound Newton-Cotes on [-xiMax, xiMax] wide enough for the shifted Maxwellian (4Z + 1 points,
+    setDV.py:153; the config's "80 x 80" is taken as 81 x 81), or stable Gauss-Hermite with quad = "GHs".
+    Initial field: the free stream, slowed linearly to rest over `blend` cylinder radii from the surface (0 = the
+    uniform free stream; at Ma = 5 that leaves a vacuum on the lee side after one step - wall density 1e-17 of
+    the free stream - and the face temperature there is a quotient of round-off, in the reference as here)."""
+    mesh = ogrid_cylinder(ntheta, nr, r_in, r_out)
+    a = float(np.sqrt(5.0 / 3.0 * ARGON["R"] * T0))
+    Uinf = mach * a
+    c = float(np.sqrt(2.0 * ARGON["R"] * T0))
+    if quad == "NC":
+        Xis, w = _dvset.dvNC(xiMax if xiMax is not None else Uinf + 5.0 * c, nDV)
+    else:
+        Xis, w = gh_set(nDV, stable=True)
+    c_ = _uniform_case(mesh, Xis, w, {"farField": PATCH_MIXED, "cylinder": PATCH_MAXWELL_WALL}, lid_patch="none",
+                       U0=(Uinf, 0.0, 0.0), wall_T={"cylinder": T_wall}, name=f"cylinder_{ntheta}x{nr}_{quad}{nDV}_Ma{mach:g}",
+                       perturb=perturb, bc_overrides={"farField": dict(U=(Uinf, 0.0, 0.0))})
+    if blend > 0:
+        r = np.hypot(c_.geom.C[:, 0], c_.geom.C[:, 1])
+        c_.U *= np.clip((r - r_in) / (blend * r_in), 0.0, 1.0)[:, None]
+    return c_

@@ -435,6 +435,83 @@ def hex_block(nx: int, ny: int, nz: int, lengths=(1.0, 1.0, 1.0), *, two_d: bool
                     owner=owner, neighbour=fn, patches=patches, nCells=nx * ny * nz)
 
 
+def ogrid_cylinder(ntheta: int, nr: int, r_in: float = 0.5, r_out: float = 15.0, *, growth: Optional[float] = None,
+                   thickness: float = 0.1) -> PolyMesh:
+    """2-D O-type quadrilateral mesh around a circular cylinder (BASELINE config 5), extruded one cell in z:
+    ntheta cells around, nr cells from the cylinder (radius r_in, patch ``cylinder``) to the far boundary (radius
+    r_out, patch ``farField``), radial spacing in geometric progression (``growth`` = ratio of successive cell
+    heights; default: the ratio that makes the first cell square).  The ring is closed: the faces between the last
+    and the first sector are ordinary internal faces.  Cell id = i + ntheta * j with i running CLOCKWISE (so that
+    (i, j, z) is right-handed like hex_block's (x, y, z)) and j outwards; internal faces in OpenFOAM's
+    upper-triangular order; front and back are one ``empty`` patch."""
+    if ntheta < 3 or nr < 1:
+        raise ValueError("ogrid_cylinder: need ntheta >= 3 and nr >= 1")
+    if growth is None:
+        # first cell about square: h0 = r_in * 2 pi / ntheta; solve h0 (g^nr - 1) / (g - 1) = r_out - r_in for g
+        h0 = r_in * 2.0 * np.pi / ntheta
+        lo, hi = 1.0 + 1e-12, 4.0
+        for _ in range(200):
+            g = 0.5 * (lo + hi)
+            if h0 * (g ** nr - 1.0) / (g - 1.0) > r_out - r_in:
+                hi = g
+            else:
+                lo = g
+        growth = 0.5 * (lo + hi) if h0 * nr < r_out - r_in else 1.0
+    if abs(growth - 1.0) < 1e-12:
+        radii = np.linspace(r_in, r_out, nr + 1)
+    else:
+        hs = growth ** np.arange(nr)
+        radii = r_in + (r_out - r_in) * np.concatenate([[0.0], np.cumsum(hs)]) / hs.sum()
+    theta = -2.0 * np.pi * np.arange(ntheta) / ntheta
+    pr = nr + 1
+    J, I = np.meshgrid(np.arange(pr), np.arange(ntheta), indexing="ij")
+    xy = np.stack([radii[J] * np.cos(theta[I]), radii[J] * np.sin(theta[I])], axis=-1).reshape(-1, 2)
+    points = np.concatenate([np.c_[xy, np.zeros(len(xy))], np.c_[xy, np.full(len(xy), thickness)]])
+
+    def pid(i, j, k):
+        return (i % ntheta) + ntheta * (j + pr * k)
+
+    jj, ii = np.meshgrid(np.arange(nr), np.arange(ntheta), indexing="ij")
+    ii, jj = ii.ravel(), jj.ravel()
+    cells = ii + ntheta * jj
+
+    def iface(i, j):   # between sectors i - 1 and i, normal along +i
+        return np.stack([pid(i, j, 0), pid(i, j + 1, 0), pid(i, j + 1, 1), pid(i, j, 1)], axis=1)
+
+    def jface(i, j):   # radius index j, normal outwards
+        return np.stack([pid(i, j, 0), pid(i, j, 1), pid(i + 1, j, 1), pid(i + 1, j, 0)], axis=1)
+
+    def kface(i, j, k):  # normal +z
+        return np.stack([pid(i, j, k), pid(i + 1, j, k), pid(i + 1, j + 1, k), pid(i, j + 1, k)], axis=1)
+
+    # internal faces: i+ face of every cell (the last sector's closes the ring: its neighbour has the smaller id, so
+    # that cell owns the face and the vertex order is reversed), j+ face below the outer ring
+    nxt = ((ii + 1) % ntheta) + ntheta * jj
+    wrap = nxt < cells
+    fv_i = iface(ii + 1, jj)
+    fv_i[wrap] = fv_i[wrap][:, ::-1]
+    fo_i = np.where(wrap, nxt, cells)
+    fn_i = np.where(wrap, cells, nxt)
+    m = jj < nr - 1
+    fv = np.concatenate([fv_i, jface(ii[m], jj[m] + 1)])
+    fo = np.concatenate([fo_i, cells[m]])
+    fn = np.concatenate([fn_i, cells[m] + ntheta])
+    perm = np.lexsort((fn, fo))
+    fv, fo, fn = fv[perm], fo[perm], fn[perm]
+    inner, outer = jj == 0, jj == nr - 1
+    bnd = [("cylinder", "wall", jface(ii[inner], jj[inner])[:, ::-1], cells[inner]),
+           ("farField", "patch", jface(ii[outer], jj[outer] + 1), cells[outer]),
+           ("frontAndBack", "empty", np.concatenate([kface(ii, jj, 0)[:, ::-1], kface(ii, jj, 1)]), np.concatenate([cells, cells]))]
+    patches, all_fv, all_fo, start = [], [fv], [fo], len(fo)
+    for name, ptype, v, o in bnd:
+        patches.append(Patch(name, ptype, len(o), start))
+        all_fv.append(v); all_fo.append(o); start += len(o)
+    owner = np.concatenate(all_fo)
+    return PolyMesh(points=points, face_verts=np.concatenate(all_fv).ravel(),
+                    face_offsets=np.arange(len(owner) + 1, dtype=np.int64) * 4, owner=owner, neighbour=fn,
+                    patches=patches, nCells=ntheta * nr)
+
+
 def tri_prism_2d(nx: int, ny: int, lengths=(1.0, 1.0, 0.1), *, distort: float = 0.0,
                  seed: int = 20260101, patch_names: Optional[Dict[str, str]] = None) -> PolyMesh:
     """2-D unstructured triangular mesh (each quad of an nx*ny grid split along

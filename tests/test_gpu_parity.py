@@ -321,6 +321,23 @@ def test_hypersonic_free_stream(oracle_lib):
     dv.close(); orc.close()
 
 
+@pytest.mark.parametrize("ntheta,nr,nDV", [(24, 8, 29), (16, 6, 41)], ids=["24x8_nc29", "16x6_nc41_chunked"])
+def test_hypersonic_cylinder_ogrid(oracle_lib, ntheta, nr, nDV):
+    """BASELINE config 5 in small: Ma = 5 past a cylinder on an O-type mesh (curved, non-orthogonal quadrilaterals, the ring
+    closed through ordinary internal faces), free-stream "mixed" outer boundary, Maxwell-wall cylinder."""
+    case = cs.cylinder_case(ntheta, nr, nDV, perturb=0.01)
+    dv = capi.fvDVM(case)
+    orc = oracle_lib.Oracle(case)
+    dt = case.courant_dt(0.5)
+    for step in range(5):
+        dv.evolution(dt)
+        orc.step(dt)
+        _compare(dv, orc, case, util.TOL_STEP * (step + 1), f"cylinder {ntheta}x{nr} NC{nDV} step {step + 1}")
+    m = dv.cell_macros()
+    assert np.isfinite(m["q"]).all() and m["T"].max() > 1.2 * cs.T0       # the bow shock heats the gas
+    dv.close(); orc.close()
+
+
 def test_symmetry_patch_on_every_axis(oracle_lib):
     """DVMsymmetry / symmetryPlane patches with x- and y-normals on one rank (the sharded variants are in
     tests/test_multi_gpu.py)."""

@@ -98,6 +98,39 @@ def test_geometry_identities(mesh):
     assert np.abs(grad - a[None, :]).max() < 1e-10
 
 
+def test_ogrid_cylinder_mesh():
+    """The O-type mesh of BASELINE config 5: closed cells, volume of the polygonal annulus, outward boundary normals,
+    owner -> neighbour face normals, upper-triangular face order, least-squares gradient exact for linear fields."""
+    from dugksfoam_b200.polymesh import ogrid_cylinder
+    nt, nr, r0, r1, th = 20, 7, 0.5, 6.0, 0.1
+    mesh = ogrid_cylinder(nt, nr, r0, r1, thickness=th)
+    g = compute_geometry(mesh)
+    nif = g.nInternalFaces
+    assert (g.nCells, nif, g.nBoundaryFaces, g.nSolutionD) == (nt * nr, nt * nr + nt * (nr - 1), 2 * nt, 2)
+    assert g.patch_names == ["cylinder", "farField"] and (g.owner[:nif] < g.neighbour).all()
+    key = g.owner[:nif].astype(np.int64) * g.nCells + g.neighbour
+    assert (np.diff(key) > 0).all()                                        # sorted by owner, then neighbour
+    closure = np.zeros((g.nCells, 3))
+    np.add.at(closure, g.owner[:nif], g.Sf[:nif]); np.add.at(closure, g.neighbour, -g.Sf[:nif])
+    np.add.at(closure, g.owner[nif:], g.Sf[nif:])
+    assert np.abs(closure[:, :2]).max() < 1e-14
+    assert abs(g.V.sum() - th * 0.5 * nt * np.sin(2 * np.pi / nt) * (r1 ** 2 - r0 ** 2)) < 1e-12 and (g.V > 0).all()
+    assert (np.einsum("ij,ij->i", g.Sf[nif:], g.Cf[nif:] - g.C[g.owner[nif:]]) > 0).all()
+    assert (np.einsum("ij,ij->i", g.Sf[:nif], g.C[g.neighbour] - g.C[g.owner[:nif]]) > 0).all()
+    rin = np.hypot(g.Cf[nif:nif + nt, 0], g.Cf[nif:nif + nt, 1])
+    assert np.allclose(rin, r0 * np.cos(np.pi / nt))                      # chord mid-points of the cylinder polygon
+    a = np.array([0.3, -1.1, 0.0])
+    phi = g.C @ a + 2.0
+    grad = np.zeros((g.nCells, 3))
+    d = phi[g.neighbour] - phi[g.owner[:nif]]
+    np.add.at(grad, g.owner[:nif], g.ownLs * d[:, None]); np.add.at(grad, g.neighbour, -g.neiLs * d[:, None])
+    ob = g.owner[nif:]
+    nh = g.Sf[nif:] / np.linalg.norm(g.Sf[nif:], axis=1)[:, None]
+    delta = nh * np.einsum("ij,ij->i", nh, g.Cf[nif:] - g.C[ob])[:, None]
+    np.add.at(grad, ob, g.patchLs * (delta @ a)[:, None])
+    assert np.abs(grad - a[None, :]).max() < 1e-10
+
+
 # ---- oracle identities -------------------------------------------------------------------
 def _run(oracle_lib, case, nsteps, co=0.5, **kw):
     o = oracle_lib.Oracle(case, **kw)
