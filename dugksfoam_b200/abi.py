@@ -45,7 +45,7 @@ class ParT(C.Structure):
     _fields_ = [("rank", C.c_int32), ("nRanks", C.c_int32), ("device", C.c_int32),
                 ("partition", C.c_int32), ("reduce", ALLREDUCE_FN), ("reduce_user", C.c_void_p),
                 ("nccl_unique_id", C.c_void_p), ("scratch_bytes", C.c_size_t),
-                ("store_h", C.c_int32), ("dv_chunk", C.c_int32)]
+                ("store_h", C.c_int32), ("dv_chunk", C.c_int32), ("limiter_k", C.c_double)]
 
 
 class StatsT(C.Structure):

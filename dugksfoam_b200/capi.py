@@ -182,7 +182,7 @@ class fvDVM:
 
     def __init__(self, case: Case, *, rank: int = 0, nranks: int = 1, device: int = -1,
                  nccl_id: Optional[bytes] = None, reduce: Optional[Callable[[int, int, int], int]] = None,
-                 store_h: bool = False, scratch_bytes: int = 0):
+                 store_h: bool = False, scratch_bytes: int = 0, limiter_k: float = 0.0):
         self.L = load_library()
         self.case = case
         self._m = Marshalled(case)
@@ -192,6 +192,7 @@ class fvDVM:
         par.scratch_bytes = int(scratch_bytes)
         par.store_h = 1 if store_h else 0
         par.dv_chunk = 0
+        par.limiter_k = float(limiter_k)
         if reduce is not None:
             def _cb(user, ptr, n, stream):
                 try:

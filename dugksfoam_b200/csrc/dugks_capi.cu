@@ -1316,6 +1316,8 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
     if (par->rank < 0 || par->rank >= nranks) return fail(nullptr, DUGKS_ERR_INVALID, "dugks_create: bad rank");
     if (par->partition != 0 || par->dv_chunk != 0)
         return fail(nullptr, DUGKS_ERR_INVALID, "dugks_create: dugks_par_t.partition and .dv_chunk are reserved and must be 0");
+    if (!(par->limiter_k >= 0.0))
+        return fail(nullptr, DUGKS_ERR_INVALID, "dugks_create: dugks_par_t.limiter_k must be >= 0 (VenkatakrishnanSlopeMulti.C:70-76)");
 
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);
@@ -1521,6 +1523,7 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
     StepArgs& A = h->A;
     memset(&A, 0, sizeof A);
     A.gas = h->gas; A.nm = h->nm;
+    A.limiter_k = par->limiter_k;
     DevMesh& M = A.m;
     M.nc = nc; M.nif = nif; M.nbf = nbf; M.nf = nf;
     int *d_i; double* d_d;
@@ -1647,11 +1650,11 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
     }
     for (int b = 0; b < nbf; b++)
         if (b_kind[b] == K_FAR_FIELD || b_kind[b] == K_PRESSURE_IN || b_kind[b] == K_PRESSURE_OUT) h->has_far = true;
-    h->use_hot = getenv("DUGKS_NO_HOT") == nullptr;           // test hook: first-generation kernels
+    h->use_hot = getenv("DUGKS_NO_HOT") == nullptr && !(par->limiter_k > 0.0);   // test hook: first-generation kernels; limited gradient: generic kernels
     h->hot_ne = h->max_ne_fast <= 4 ? 4 : (h->max_ne_fast <= 6 ? 6 : 8);
     h->use_tma = getenv("DUGKS_NO_TMA") == nullptr;            // test hook: per-element LDG kernels instead
     h->ci = TMA_CI;
-    h->use_fast = getenv("DUGKS_FORCE_GENERIC") == nullptr;   // test hook: run every cell through the generic kernels
+    h->use_fast = getenv("DUGKS_FORCE_GENERIC") == nullptr && !(par->limiter_k > 0.0);   // test hook: run every cell through the generic kernels
     if (h->Lt > 0) h->use_fast = false;                        // only the generic and second-generation kernels know short rows
     TRYB(dev_upload(h, &d_d, std::vector<double>(mesh->V, mesh->V + nc))); M.V = d_d;
     TRYB(dev_upload(h, &d_i, b_owner)); M.b_owner = d_i;

@@ -51,6 +51,7 @@ struct StepArgs {
     const unsigned char *cell_cls;          // [nc] 1: axis-aligned interior cell (entries in axis order), else 0
     double *fkeep_g, *fkeep_h;              // [n_keep_slabs][nif][L][32] reconstructed face values (face-storage slabs) or null
     double *ccoef;                          // [nc][12] half-step equilibrium records of the cells (k_cell_coef)
+    double limiter_k;                       // > 0: Venkatakrishnan-limited least-squares gradient (generic kernels only)
 };
 
 __device__ __forceinline__ size_t dv_index(const DevDV& dv, int slab, int n_outer, int outer, int i, int r) {
@@ -111,11 +112,32 @@ __device__ __forceinline__ int stage_cell(const StepArgs& a, int c, int lane, Ce
 // stock leastSquaresGrad [OF-lib]; in-tree twin zeroBoundaryGrad.C:90-99 plus the
 // boundary contribution kept in comments at :126-133; boundary value of a
 // fixedGradient patch = cell + gradient/deltaCoeffs (lagged gradient, discreteVelocity.C:408-409)
+// VenkatakrishnanSlopeMultiLimiter::limitFace (VenkatakrishnanSlopeMulti.C:83-128): sqrEps = k^3 V
+__device__ __forceinline__ double venkat_limit_face(double sqrEps, double dMax, double dMin, double d2) {
+    const double two = 2.0 * d2 * d2;
+    if (d2 > 0.0) {
+        double den = dMax * dMax + two + dMax * d2 + sqrEps;
+        if (fabs(den) < DUGKS_VSMALL) den = den < 0 ? -DUGKS_VSMALL : DUGKS_VSMALL;   // stabilise() [OF-lib]
+        return ((dMax * dMax + sqrEps) + 2.0 * d2 * dMax) / den;
+    } else if (d2 < 0.0) {
+        double den = dMin * dMin + two + dMin * d2 + sqrEps;
+        if (fabs(den) < DUGKS_VSMALL) den = den < 0 ? -DUGKS_VSMALL : DUGKS_VSMALL;
+        return ((dMin * dMin + sqrEps) + 2.0 * d2 * dMin) / den;
+    }
+    return 1.0;
+}
+
+// a.limiter_k > 0: gradSchemes "VenkatakrishnanLimited leastSquares k" AS IT IS MEANT TO WORK
+// (VenkatakrishnanLimitedGrads.C:59-226: limiter = min over the faces of the cell of limitFace(V, max - phi,
+// min - phi, (Cf - C).grad) with max / min over the face neighbours and patch values, grad *= limiter; the
+// reference itself limits a copy and returns the unlimited gradient, :76,:225, i.e. behaves like limiter_k = 0).
+// V: volume of the staged cell.
 template <bool HAS_H>
 __device__ __forceinline__ void cell_gradient(const StepArgs& a, const CellStage& s, int ne, size_t ir,
-                                              double v0, double w0, double g[3], double h[3]) {
+                                              double v0, double w0, double g[3], double h[3], double V = 0.0) {
     g[0] = g[1] = g[2] = 0.0;
     h[0] = h[1] = h[2] = 0.0;
+    double gmax = 0.0, gmin = 0.0, hmax = 0.0, hmin = 0.0;   // max / min of (neighbour - cell), the cell itself included
     for (int j = 0; j < ne; j++) {
         int kind = s.kind[j];
         size_t off = (size_t)s.obase[j] + ir;
@@ -133,6 +155,19 @@ __device__ __forceinline__ void cell_gradient(const StepArgs& a, const CellStage
         const double* G = s.geo + j * 9;
         g[0] += G[0] * dg; g[1] += G[1] * dg; g[2] += G[2] * dg;
         if (HAS_H) { h[0] += G[0] * dh; h[1] += G[1] * dh; h[2] += G[2] * dh; }
+        gmax = fmax(gmax, dg); gmin = fmin(gmin, dg);
+        hmax = fmax(hmax, dh); hmin = fmin(hmin, dh);
+    }
+    if (a.limiter_k > 0.0) {
+        const double sqrEps = a.limiter_k * a.limiter_k * a.limiter_k * V;
+        double lg = 1.0, lh = 1.0;
+        for (int j = 0; j < ne; j++) {
+            const double* G = s.geo + j * 9;
+            lg = fmin(lg, venkat_limit_face(sqrEps, gmax, gmin, G[3] * g[0] + G[4] * g[1] + G[5] * g[2]));
+            if (HAS_H) lh = fmin(lh, venkat_limit_face(sqrEps, hmax, hmin, G[3] * h[0] + G[4] * h[1] + G[5] * h[2]));
+        }
+        g[0] *= lg; g[1] *= lg; g[2] *= lg;
+        if (HAS_H) { h[0] *= lh; h[1] *= lh; h[2] *= lh; }
     }
 }
 
@@ -409,7 +444,7 @@ k_cell_outgoing(StepArgs a) {
                     }
                 }
             };
-            const bool fast = ne <= FAST_NE;
+            const bool fast = ne <= FAST_NE && !(a.limiter_k > 0.0);   // the limited gradient lives in cell_gradient only
             const size_t cellbase = base - r;   // base offset of the cell's row block (without r)
             if (fast) {
                 NbrVals<HAS_H> A, B;
@@ -432,7 +467,7 @@ k_cell_outgoing(StepArgs a) {
                     double v0 = a.gb[base + (size_t)i * dv.Rs];
                     double w0 = HAS_H ? a.hb[base + (size_t)i * dv.Rs] : 0.0;
                     double gg[3], gh[3];
-                    cell_gradient<HAS_H>(a, st, ne, ir, v0, w0, gg, gh);
+                    cell_gradient<HAS_H>(a, st, ne, ir, v0, w0, gg, gh, a.m.V[c]);
                     body(i, v0, w0, gg, gh);
                 }
             }
@@ -506,7 +541,7 @@ k_bnd_outgoing(StepArgs a, int far_only) {
             double v0 = a.gb[cbase + (size_t)i * dv.Rs];
             double w0 = HAS_H ? a.hb[cbase + (size_t)i * dv.Rs] : 0.0;
             double gg[3], gh[3];
-            cell_gradient<HAS_H>(a, st, ne, ir, v0, w0, gg, gh);
+            cell_gradient<HAS_H>(a, st, ne, ir, v0, w0, gg, gh, a.m.V[c]);
             size_t bo = bbase + (size_t)i * dv.Rs;
             if (kind != K_SYMMETRY_PLANE) {   // discreteVelocity.C:444-468
                 a.gam_new_g[bo] = gg[0] * nn[0] + gg[1] * nn[1] + gg[2] * nn[2];

@@ -99,6 +99,19 @@ class fvDVM {
         g.assign(nXi_, 0.0); h.assign(nXi_, 0.0);
         check(dugks_get_df(h_, cell, g.data(), h.data()), "fvDVM::writeDFonCell");
     }
+    // exact restart (the reference's own restart drops the distribution functions, discreteVelocity.C:220-249):
+    // everything the next evolution() reads, as one rank-local blob
+    std::vector<char> checkpoint() {
+        uint64_t n = 0;
+        check(dugks_checkpoint_size(h_, &n), "fvDVM::checkpoint");
+        std::vector<char> blob(n);
+        check(dugks_checkpoint_save(h_, blob.data(), n), "fvDVM::checkpoint");
+        return blob;
+    }
+    void restore(const std::vector<char>& blob) {
+        check(dugks_checkpoint_load(h_, blob.data(), blob.size()), "fvDVM::restore");
+        dirty_ = surfDirty_ = true;
+    }
     dugks_handle_t* handle() { return h_; }
 
   private:

@@ -166,6 +166,13 @@ typedef struct dugks_par_t {
     int32_t store_h;             /* 1: always carry h; 0: elide h when K+3-D==0 (h==0 exactly,
                                     discreteVelocity.C:1043) */
     int32_t dv_chunk;            /* reserved, must be 0: a launch slab is 32 velocity rows */
+    /* system/fvSchemes gradSchemes (doc/usage.tex:169-192).  0: "leastSquares", the scheme of every shipped case.
+     * > 0: "VenkatakrishnanLimited leastSquares k" AS IT IS MEANT TO WORK (VenkatakrishnanLimitedGrads.C:59-226,
+     * VenkatakrishnanSlopeMulti.C:83-128: grad *= min over the cell's faces of limitFace, eps^2 = k^3 V).  The
+     * reference's own implementation limits a copy of the gradient and returns the unlimited one (:76, :225) and
+     * starts the limiter from 0 instead of 1 (:140-151), so IN THE REFERENCE the scheme is inert: pass 0 to
+     * reproduce a reference run that names it.  The limited gradient runs through the generic kernels (slower). */
+    double limiter_k;
 } dugks_par_t;
 
 typedef struct dugks_handle dugks_handle_t;

@@ -15,6 +15,16 @@ from __future__ import annotations
 import numpy as np
 
 VSMALL = 1.0e-300
+
+
+def xi_dot_sf(xi, Sf):
+    """xi & Sf evaluated like OpenFOAM's vector inner product, x*Sx + y*Sy + z*Sz, term by term without fused
+    multiply-adds (a BLAS matrix-vector product may sum in another order): the SIGN of this number picks the upwind
+    cell, and on a face whose normal is at 45 degrees a velocity with xi_x = xi_y gives exactly 0 one way and 1e-18 the
+    other - a tie averaged from both sides (discreteVelocity.C:513-529) or a one-sided value."""
+    return xi[0] * Sf[:, 0] + xi[1] * Sf[:, 1] + xi[2] * Sf[:, 2]
+
+
 ZERO_GRADIENT, MIXED, MAXWELL_WALL, FAR_FIELD, DVM_SYMMETRY, SYMMETRY_PLANE, PRESSURE_IN, PRESSURE_OUT = range(8)
 
 
@@ -93,7 +103,7 @@ class NumpyDVM:
         wall = np.where(self.kind == MAXWELL_WALL)[0]
         Sfb = self.Sf[self.nif:]
         for k in range(self.nxi):
-            phi = Sfb[wall] @ self.xi[k]
+            phi = xi_dot_sf(self.xi[k], Sfb[wall])
             inc = phi < 0
             b = wall[inc]
             self.inByRho[b] += -self.w[k] * phi[inc] * self._maxwell_by_rho(self.xi[k], self.U_b[b], self.T_b[b])
@@ -156,7 +166,7 @@ class NumpyDVM:
             # boundary value of the gradient = cell value (zeroGradient); its normal part is next step's gradient()
             self.gam_g[k] = (gG[self.bown] * nb).sum(axis=1)                      # :462-468
             self.gam_h[k] = (hG[self.bown] * nb).sum(axis=1)
-            phi = Sfi @ xi
+            phi = xi_dot_sf(xi, Sfi)
             ro = self.Cf[:nif] - self.C[self.own] - 0.5 * xi * dt
             rn = self.Cf[:nif] - self.C[self.nei] - 0.5 * xi * dt
             go = gB[k][self.own] + (gG[self.own] * ro).sum(axis=1); gn = gB[k][self.nei] + (gG[self.nei] * rn).sum(axis=1)
@@ -164,7 +174,7 @@ class NumpyDVM:
             up_o, up_n = phi >= VSMALL, phi < -VSMALL                             # :495, :506, else :513-529
             self.gS[k, :nif] = np.where(up_o, go, np.where(up_n, gn, 0.5 * (gn + go)))
             self.hS[k, :nif] = np.where(up_o, ho, np.where(up_n, hn, 0.5 * (hn + ho)))
-            phib = Sfb @ xi
+            phib = xi_dot_sf(xi, Sfb)
             rb = self.Cf[nif:] - self.C[self.bown] - 0.5 * xi * dt
             gout = gB[k][self.bown] + (gG[self.bown] * rb).sum(axis=1)
             hout = hB[k][self.bown] + (hG[self.bown] * rb).sum(axis=1)
@@ -183,7 +193,7 @@ class NumpyDVM:
         self.rho_b[is_wall] = outGoing[is_wall] / np.abs(self.inByRho[is_wall])
         # 2.3  updateGHbarSurfMaxwellWallIn  discreteVelocity.C:693-731
         for k in range(self.nxi):
-            m = is_wall & ((Sfb @ self.xi[k]) <= 0)
+            m = is_wall & (xi_dot_sf(self.xi[k], Sfb) <= 0)
             geq = self.rho_b[m] * self._maxwell_by_rho(self.xi[k], self.U_b[m], self.T_b[m])
             self.gS[k, nif:][m] = geq
             self.hS[k, nif:][m] = geq * (self.R * self.T_b[m]) * (self.K + 3 - self.D)
@@ -196,7 +206,7 @@ class NumpyDVM:
             Sf0 = Sfb[p.start]
             n0 = Sf0 / np.linalg.norm(Sf0)
             for k in range(self.nxi):
-                if self.xi[k] @ Sf0 <= 0:                                         # :775
+                if xi_dot_sf(self.xi[k], Sf0[None, :])[0] <= 0:                   # :775
                     tgt = int(round(abs(n0 @ self.mirror[k])))                    # :777-779
                     self.gS[k, sl] = snapG[tgt]; self.hS[k, sl] = snapH[tgt]
         # 3  updateMacroSurf  fvDVM.C:456-582
@@ -231,7 +241,7 @@ class NumpyDVM:
             gI = (1.0 - rfS[:nif]) * self.gS[k, :nif] + rfS[:nif] * gEq[:nif]      # :880-881 (internal faces)
             hI = (1.0 - rfS[:nif]) * self.hS[k, :nif] + rfS[:nif] * hEq[:nif]
             self.gS[k, :nif] = gI; self.hS[k, :nif] = hI
-            phib = Sfb @ xi[k]
+            phib = xi_dot_sf(xi[k], Sfb)
             gb, hb = self.gS[k, nif:], self.hS[k, nif:]
             rb_, geb, heb = rfS[nif:], gEq[nif:], hEq[nif:]
             m = phib > 0                                                           # :905-920 outgoing only
@@ -242,7 +252,7 @@ class NumpyDVM:
             hb[m] = (1.0 - rb_[m]) * hb[m] + rb_[m] * heb[m]
             gt = -1.0 / 3 * self.gT[k] + 4.0 / 3 * gB[k]                           # :937-938
             ht = -1.0 / 3 * self.hT[k] + 4.0 / 3 * hB[k]
-            phi = Sfi @ xi[k]
+            phi = xi_dot_sf(xi[k], Sfi)
             np.subtract.at(gt, self.own, phi * gI * dt / self.V[self.own])         # :948-956
             np.add.at(gt, self.nei, phi * gI * dt / self.V[self.nei])
             np.subtract.at(ht, self.own, phi * hI * dt / self.V[self.own])

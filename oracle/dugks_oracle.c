@@ -64,6 +64,8 @@ typedef struct oracle {
     double *qWall, *stressWall;              /* [nbf][3], [nbf][9] */
     double *part;                            /* scratch for rank partials */
     double *Told, *rhoOld, *Uold;            /* convergence monitor snapshot, createFields.H:40-82 */
+    int grad_limiter;                        /* 0: gradSchemes leastSquares; 1: VenkatakrishnanLimited leastSquares k, as meant */
+    double limiter_k;
     long steps;
 } oracle_t;
 
@@ -371,6 +373,62 @@ static inline double bvalue(const oracle_t *o, int kind, double cellv, double ga
     return cellv + gamma / dcoef;
 }
 
+/* VenkatakrishnanSlopeMultiLimiter::limitFace, VenkatakrishnanSlopeMulti.C:83-128 (Blazek chap. 5) */
+static inline double venkat_limit_face(double k, double V, double dMax, double dMin, double d2) {
+    double sqrEps = k * k * k * V;
+    double two = 2.0 * d2 * d2;
+    if (d2 > 0.0) {
+        double den = dMax * dMax + two + dMax * d2 + sqrEps;
+        if (fabs(den) < VSMALL) den = den < 0 ? -VSMALL : VSMALL; /* stabilise() [OF-lib] */
+        return ((dMax * dMax + sqrEps) + 2.0 * d2 * dMax) / den;
+    } else if (d2 < 0.0) {
+        double den = dMin * dMin + two + dMin * d2 + sqrEps;
+        if (fabs(den) < VSMALL) den = den < 0 ? -VSMALL : VSMALL;
+        return ((dMin * dMin + sqrEps) + 2.0 * d2 * dMin) / den;
+    }
+    return 1.0;
+}
+
+/* VenkatakrishnanLimitedGrad<scalar>::calcGrad, VenkatakrishnanLimitedGrads.C:59-226, AS IT IS MEANT TO WORK:
+ * the reference limits a COPY of the gradient and returns the unlimited one (:76 `volVectorField g = tGrad()`,
+ * :225 `return tGrad`), and starts the per-cell limiter from 0 instead of 1 (:140-151; the commented line :152
+ * shows the intent), so in the reference the scheme has no effect at all (= grad_limiter 0).  Here: limiter = 1,
+ * min over the faces of the cell of limitFace(V, max - phi, min - phi, (Cf - C).grad), grad *= limiter.
+ * vb: boundary value of the field on every boundary face. */
+static void venkat_limit(const oracle_t *o, const double *v, const double *vb, double *grad,
+                         double *maxV, double *minV, double *lim) {
+    int nc = o->nc, nif = o->nif, nbf = o->nbf;
+    for (int c = 0; c < nc; c++) { maxV[c] = v[c]; minV[c] = v[c]; lim[c] = 1.0; }
+    for (int f = 0; f < nif; f++) { /* :88-101 */
+        int own = o->owner[f], nei = o->neigh[f];
+        if (v[nei] > maxV[own]) maxV[own] = v[nei];
+        if (v[nei] < minV[own]) minV[own] = v[nei];
+        if (v[own] > maxV[nei]) maxV[nei] = v[own];
+        if (v[own] < minV[nei]) minV[nei] = v[own];
+    }
+    for (int b = 0; b < nbf; b++) { /* :126-134 non-coupled patches: the patch value */
+        int own = o->owner[nif + b];
+        if (vb[b] > maxV[own]) maxV[own] = vb[b];
+        if (vb[b] < minV[own]) minV[own] = vb[b];
+    }
+    for (int c = 0; c < nc; c++) { maxV[c] -= v[c]; minV[c] -= v[c]; } /* :137-138 */
+    for (int f = 0; f < nif + nbf; f++) { /* :156-207 */
+        const double *Cf = o->Cf + 3 * (size_t)f;
+        int own = o->owner[f];
+        double r[3] = {Cf[0] - o->C[3 * own], Cf[1] - o->C[3 * own + 1], Cf[2] - o->C[3 * own + 2]};
+        double l = venkat_limit_face(o->limiter_k, o->V[own], maxV[own], minV[own], dot3(r, grad + 3 * own));
+        if (l < lim[own]) lim[own] = l;
+        if (f < nif) {
+            int nei = o->neigh[f];
+            double rn[3] = {Cf[0] - o->C[3 * nei], Cf[1] - o->C[3 * nei + 1], Cf[2] - o->C[3 * nei + 2]};
+            l = venkat_limit_face(o->limiter_k, o->V[nei], maxV[nei], minV[nei], dot3(rn, grad + 3 * nei));
+            if (l < lim[nei]) lim[nei] = l;
+        }
+    }
+    for (int c = 0; c < nc; c++)
+        for (int d = 0; d < 3; d++) grad[3 * c + d] *= lim[c]; /* :219 */
+}
+
 /* stage 2.1: discreteVelocity::updateGHbarSurf, discreteVelocity.C:412-691 */
 static void stage_barSurf(oracle_t *o, double dt) {
     int nc = o->nc, nif = o->nif, nf = o->nf, nbf = o->nbf;
@@ -411,6 +469,19 @@ static void stage_barSurf(oracle_t *o, double dt) {
                     hG[3 * own + d] += o->patchLs[3 * b + d] * dh;
                 }
             }
+        }
+        if (o->grad_limiter == 1 && o->limiter_k >= 1e-15) { /* gradSchemes: VenkatakrishnanLimited leastSquares k (:70 k < SMALL: off) */
+            double *vbg = xcalloc((size_t)(nbf ? nbf : 1) * 2 + 3 * (size_t)nc, sizeof(double));
+            double *vbh = vbg + (nbf ? nbf : 1), *wrk = vbh + (nbf ? nbf : 1);
+            for (int p = 0; p < o->npatch; p++)
+                for (int j = 0; j < o->patch[p].size; j++) {
+                    int b = o->patch[p].start + j, own = o->owner[nif + b];
+                    vbg[b] = bvalue(o, o->patch[p].kind, gB[own], gamG[b], o->dcoef[nif + b]);
+                    vbh[b] = bvalue(o, o->patch[p].kind, hB[own], gamH[b], o->dcoef[nif + b]);
+                }
+            venkat_limit(o, gB, vbg, gG, wrk, wrk + nc, wrk + 2 * nc);
+            venkat_limit(o, hB, vbh, hG, wrk, wrk + nc, wrk + 2 * nc);
+            free(vbg);
         }
         /* :427-470 boundary grad = cell grad (zeroGradient); its normal component becomes
          * the fixedGradient gradient() used NEXT step; skipped for constraint patches */
@@ -811,6 +882,14 @@ static void stage_macroVol(oracle_t *o, double dt) {
             for (int d = 0; d < 3; d++) o->q[3 * c + d] = fac * qs[3 * j + d];
         }
     }
+}
+
+/* gradSchemes of system/fvSchemes (doc/usage.tex:169-192): 0 = leastSquares (what the demos use, and what the
+ * reference's VenkatakrishnanLimited amounts to because of its copy bug), 1 = VenkatakrishnanLimited leastSquares k
+ * as it is meant to work */
+void oracle_set_grad_scheme(oracle_t *o, int limiter, double k) {
+    o->grad_limiter = limiter;
+    o->limiter_k = k;
 }
 
 /* fvDVM::evolution fvDVM.C:1086-1108 */

@@ -51,6 +51,7 @@ def lib():
         L.oracle_get_surf.argtypes = [C.c_void_p, C.c_int, c_double_p, c_double_p]
         L.oracle_get_dvs.argtypes = [C.c_void_p, c_double_p, c_double_p, c_int32_p, c_int32_p, c_int32_p]
         L.oracle_get_wall_incoming.argtypes = [C.c_void_p, c_double_p]
+        L.oracle_set_grad_scheme.argtypes = [C.c_void_p, C.c_int, C.c_double]
         _LIB = L
     return _LIB
 
@@ -79,6 +80,11 @@ class Oracle:
             self.close()
         except Exception:
             pass
+
+    def set_grad_scheme(self, limiter: int, k: float = 0.0):
+        """0: leastSquares; 1: VenkatakrishnanLimited leastSquares k as it is meant to work (the reference's own
+        implementation is inert, VenkatakrishnanLimitedGrads.C:76,225)."""
+        lib().oracle_set_grad_scheme(self.h, int(limiter), float(k))
 
     def step(self, dt: float):
         lib().oracle_step(self.h, dt)

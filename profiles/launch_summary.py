@@ -17,7 +17,11 @@ if one_step:
 rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 14 and r[0].isdigit()]
 if one_step:
     ends = sorted({int(r[0]) for r in rows if r[4].startswith("k_bnd_macros")})
-    if len(ends) >= 2:
+    # the first k_bnd_macros belongs to dugks_create (the launches up to the second one include the initialisation
+    # kernels): take the window between the last two
+    if len(ends) >= 3:
+        rows = [r for r in rows if ends[-2] < int(r[0]) <= ends[-1]]
+    elif len(ends) == 2:
         rows = [r for r in rows if ends[0] < int(r[0]) <= ends[1]]
 per = collections.defaultdict(dict)
 name = {}
