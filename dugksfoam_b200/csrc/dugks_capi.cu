@@ -253,7 +253,10 @@ static int do_allreduce(dugks_handle* h, double* buf, size_t n) {
 #ifndef DUGKS_CI_OUT1
 #define DUGKS_CI_OUT1 4
 #endif
-constexpr int CI_OUT1 = DUGKS_CI_OUT1, CI_OUT2 = 2, CI_RLX = 2;
+#ifndef DUGKS_CI_RLX
+#define DUGKS_CI_RLX 2
+#endif
+constexpr int CI_OUT1 = DUGKS_CI_OUT1, CI_OUT2 = 2, CI_RLX = DUGKS_CI_RLX;
 // axis-only launch of phase 1 (hot_axis_item): chunks of 4 points are staged, HOT_AXIS_CU = 2 points are advanced
 // together, which keeps it at 3 CTAs/SM without spills
 #ifndef DUGKS_CI_AXIS
@@ -262,6 +265,13 @@ constexpr int CI_OUT1 = DUGKS_CI_OUT1, CI_OUT2 = 2, CI_RLX = 2;
 constexpr int CI_AXIS = DUGKS_CI_AXIS;
 // update kernel of the flux-buffer path: 4 points per chunk, 2 when h doubles the streams (shared memory per CTA)
 #define CI_UPD (H ? 2 : 4)
+// DUGKS_DEV_BUILD (experiment builds, profiles/ab_bench.py): only the instantiations of the 3-D, h-elided case with
+// unchunked rows are compiled (a tenth of the build time); every other case fails with DUGKS_ERR_UNSUPPORTED.
+#ifdef DUGKS_DEV_BUILD
+#define DUGKS_BY_H(h, fn, ...) ((h)->hasH ? fail((h), DUGKS_ERR_UNSUPPORTED, "DUGKS_DEV_BUILD holds the h-elided kernels only") : fn<false>(__VA_ARGS__))
+#else
+#define DUGKS_BY_H(h, fn, ...) ((h)->hasH ? fn<true>(__VA_ARGS__) : fn<false>(__VA_ARGS__))
+#endif
 // How phase 1 of a slab treats the pencil cells: 0 = no pencil (warp-per-cell kernels), 1 = pencil over gBarP
 // written by the half-step kernel, 2 = fused: the pencil reads gTilde and applies the half step itself (face-
 // storage slabs only: the recompute path needs gBarP of every cell again in phase 2).
@@ -290,10 +300,13 @@ static void launch_hot_outgoing(dugks_handle* h, const StepArgs& a) {
             else k_pencil_phase1<false><<<h->pen_grid, PEN_WARPS * 32, h->pen_smem, h->stream>>>(a, h->pen);
             h->launches++;
         }
+#ifndef DUGKS_DEV_BUILD
         if (h->hot_ne == 4) {
             if (a1.item0 < a1.item1) k_hot_outgoing<1, H, 4, 32, CI_AXIS, 1><<<grid1, HOT_WARPS * 32, h->hsmem_axis, h->stream>>>(a1);
             if (h->n_axis < h->nc) k_hot_outgoing<1, H, 4, 32, CI_OUT1, 2><<<grid2, HOT_WARPS * 32, sm, h->stream>>>(a2);
-        } else {
+        } else
+#endif
+        {
             if (a1.item0 < a1.item1) k_hot_outgoing<1, H, 6, 32, CI_AXIS, 1><<<grid1, HOT_WARPS * 32, h->hsmem_axis, h->stream>>>(a1);
             if (h->n_axis < h->nc) k_hot_outgoing<1, H, 6, 32, CI_OUT1, 2><<<grid2, HOT_WARPS * 32, sm, h->stream>>>(a2);
         }
@@ -301,16 +314,25 @@ static void launch_hot_outgoing(dugks_handle* h, const StepArgs& a) {
         return;
     }
 #define DUGKS_HOT_OUT(NE_, TW_) k_hot_outgoing<PHASE, H, NE_, TW_, (PHASE == 1 ? CI_OUT1 : CI_OUT2), 0><<<grid, HOT_WARPS * 32, sm, h->stream>>>(a)
+#ifdef DUGKS_DEV_BUILD
+    DUGKS_HOT_OUT(6, 32);
+#else
     if (h->hot_ne == 4) { if (tw == 32) DUGKS_HOT_OUT(4, 32); else DUGKS_HOT_OUT(4, 64); }
     else if (h->hot_ne == 6) { if (tw == 32) DUGKS_HOT_OUT(6, 32); else DUGKS_HOT_OUT(6, 64); }
     else { if (tw == 32) DUGKS_HOT_OUT(8, 32); else DUGKS_HOT_OUT(8, 64); }
+#endif
 #undef DUGKS_HOT_OUT
 }
 template <bool H>
 static void launch_hot_update(dugks_handle* h, const StepArgs& a) {
+#ifndef DUGKS_DEV_BUILD
     if (h->hot_ne == 4) k_hot_update<H, 4, CI_UPD><<<h->hot_grid_upd, HOT_WARPS * 32, h->hsmem_upd, h->stream>>>(a);
-    else if (h->hot_ne == 6) k_hot_update<H, 6, CI_UPD><<<h->hot_grid_upd, HOT_WARPS * 32, h->hsmem_upd, h->stream>>>(a);
+    else
+#endif
+    if (h->hot_ne == 6) k_hot_update<H, 6, CI_UPD><<<h->hot_grid_upd, HOT_WARPS * 32, h->hsmem_upd, h->stream>>>(a);
+#ifndef DUGKS_DEV_BUILD
     else k_hot_update<H, 8, CI_UPD><<<h->hot_grid_upd, HOT_WARPS * 32, h->hsmem_upd, h->stream>>>(a);
+#endif
 }
 template <bool H>
 static void launch_hot_relax(dugks_handle* h, const StepArgs& a) {
@@ -321,9 +343,13 @@ static void launch_hot_relax(dugks_handle* h, const StepArgs& a) {
         else if (h->wmode) k_hot_relax_update<H, NE_, TW_, CI_RLX, 1><<<h->hot_grid_rlx_w, HOT_WARPS * 32, h->hsmem_rlx_w, h->stream>>>(a); \
         else k_hot_relax_update<H, NE_, TW_, CI_RLX, 0><<<h->hot_grid_rlx, HOT_WARPS * 32, h->hsmem_rlx, h->stream>>>(a);             \
     } while (0)
+#ifdef DUGKS_DEV_BUILD
+    DUGKS_HOT_RLX(6, 32);
+#else
     if (h->hot_ne == 4) { if (tw == 32) DUGKS_HOT_RLX(4, 32); else DUGKS_HOT_RLX(4, 64); }
     else if (h->hot_ne == 6) { if (tw == 32) DUGKS_HOT_RLX(6, 32); else DUGKS_HOT_RLX(6, 64); }
     else { if (tw == 32) DUGKS_HOT_RLX(8, 32); else DUGKS_HOT_RLX(8, 64); }
+#endif
 #undef DUGKS_HOT_RLX
 }
 template <bool H, int NE, int TW>
@@ -364,21 +390,29 @@ static int hot_configure(dugks_handle* h) {
         if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], k_hot_update<H, NE_, CI_UPD>, HOT_WARPS * 32, h->hsmem_upd); \
         if (e == cudaSuccess) e = tw == 32 ? hot_cfg_rlx<H, NE_, 32>(h, &occ[3]) : hot_cfg_rlx<H, NE_, 64>(h, &occ[3]); \
     } while (0)
+#ifdef DUGKS_DEV_BUILD
+    if (h->hot_ne != 6 || tw != 32) return fail(h, DUGKS_ERR_UNSUPPORTED, "DUGKS_DEV_BUILD holds the 3-D hex, h-elided, unchunked-row kernels only");
+    DUGKS_HOT_CFG(6);
+#else
     if (h->hot_ne == 4) DUGKS_HOT_CFG(4);
     else if (h->hot_ne == 6) DUGKS_HOT_CFG(6);
     else DUGKS_HOT_CFG(8);
+#endif
 #undef DUGKS_HOT_CFG
     if (e != cudaSuccess) return fail(h, DUGKS_ERR_CUDA, "cudaFuncSetAttribute (hot kernels): %s", cudaGetErrorString(e));
     int occ_axis = 1;
     h->split_axis = false;
     if (e == cudaSuccess && (h->hot_ne == 4 || h->hot_ne == 6) && h->want_split && h->axis_ne == h->hot_ne) {
         // axis-aligned cells in their own launch (hot_axis_item, 3 CTAs/SM; 64^3 x 28^3: phase 1 2.90 -> 2.13 ms per slab)
+#ifndef DUGKS_DEV_BUILD
         if (h->hot_ne == 4) {
             h->hsmem_axis = HotPlan<1, H, 4, 32, CI_AXIS>::total(ntab);
             e = cudaFuncSetAttribute(k_hot_outgoing<1, H, 4, 32, CI_AXIS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->hsmem_axis);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_hot_outgoing<1, H, 4, 32, CI_OUT1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->hsmem_out1);
             if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_axis, k_hot_outgoing<1, H, 4, 32, CI_AXIS, 1>, HOT_WARPS * 32, h->hsmem_axis);
-        } else {
+        } else
+#endif
+        {
             h->hsmem_axis = HotPlan<1, H, 6, 32, CI_AXIS>::total(ntab);
             e = cudaFuncSetAttribute(k_hot_outgoing<1, H, 6, 32, CI_AXIS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->hsmem_axis);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_hot_outgoing<1, H, 6, 32, CI_OUT1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->hsmem_out1);
@@ -1524,6 +1558,15 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
     memset(&A, 0, sizeof A);
     A.gas = h->gas; A.nm = h->nm;
     A.limiter_k = par->limiter_k;
+    {   // L2 cache policies as kernel arguments (dugks_hot.cuh, RLX_POL)
+        unsigned long long* d_pol = nullptr;
+        unsigned long long pol[2] = {0, 0};
+        TRYB(dev_alloc(h, &d_pol, 2));
+        k_make_policies<<<1, 1, 0, h->stream>>>(d_pol);
+        CUDA_TRY(h, cudaMemcpyAsync(pol, d_pol, sizeof pol, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        A.pol_ef = pol[0]; A.pol_el = pol[1];
+    }
     DevMesh& M = A.m;
     M.nc = nc; M.nif = nif; M.nbf = nbf; M.nf = nf;
     int *d_i; double* d_d;
@@ -1806,7 +1849,7 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
 
     // ---- second-generation kernels: shared-memory plan, static upwind range codes
     if (h->tabw > 64 || L > 32) h->use_hot = false;
-    if (h->use_hot) TRYB(h->hasH ? hot_configure<true>(h) : hot_configure<false>(h));
+    if (h->use_hot) TRYB(DUGKS_BY_H(h, hot_configure, h));
     if (h->use_hot) {
         uint4* d_upw = nullptr;
         int* d_bad = nullptr;
@@ -1888,7 +1931,7 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
         if (nrc) { fail(h, DUGKS_ERR_COMM, "ncclCommInitRank failed: %s", g_nccl.errstr ? g_nccl.errstr(nrc) : "?"); return bail(DUGKS_ERR_COMM); }
     }
 
-    TRYB(h->hasH ? init_state<true>(h) : init_state<false>(h));
+    TRYB(DUGKS_BY_H(h, init_state, h));
     // Told = T; rhoOld = rho; Uold = U (createFields.H:80-82)
     k_convergence_init<<<(nc + 255) / 256, 256, 0, h->stream>>>(h->A, h->d_conv_old);
     TRYB(check_launch(h, "k_convergence_init"));
@@ -1904,7 +1947,7 @@ extern "C" int dugks_step(dugks_handle_t* h, double dt) {
     if (!h) return DUGKS_ERR_INVALID;
     if (!(dt > 0.0)) return fail(h, DUGKS_ERR_INVALID, "dugks_step: dt must be positive");
     CUDA_TRY(h, cudaSetDevice(h->device));
-    return h->hasH ? step_impl<true>(h, dt) : step_impl<false>(h, dt);
+    return DUGKS_BY_H(h, step_impl, h, dt);
 }
 
 extern "C" int dugks_sync(dugks_handle_t* h) {
@@ -2008,7 +2051,7 @@ extern "C" int dugks_set_boundary_macros(dugks_handle_t* h, const double* rho_b,
     k_set_bmac<<<(h->nbf + 127) / 128, 128, 0, h->stream>>>(h->A, h->d_bc, d_rho, d_U, d_T);
     int rc = check_launch(h, "k_set_bmac");
     if (rc) return rc;
-    rc = h->hasH ? compute_wall_constants<true>(h) : compute_wall_constants<false>(h);
+    rc = DUGKS_BY_H(h, compute_wall_constants, h);
     if (rc) return rc;
     // the caller's arrays are borrowed for the call only: copies from pinned memory must have run
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));

@@ -139,6 +139,10 @@ __device__ __forceinline__ unsigned long long l2_evict_last_policy() {
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
+__global__ void k_make_policies(unsigned long long* out) {
+    out[0] = l2_evict_first_policy();
+    out[1] = l2_evict_last_policy();
+}
 __device__ __forceinline__ void cp_async16_ef(uint32_t sdst, const void* gsrc, unsigned long long pol) {
     asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(sdst), "l"(gsrc), "l"(pol));
 }
@@ -270,6 +274,24 @@ __device__ __forceinline__ void hot_stage_one_ef(uint32_t sdst, const double* ba
 #pragma unroll
     for (int part = 0; part < CI * 256 / 512; part++) cp_async16_ef(sdst + part * 512, p + part * 512, pol);
 }
+
+// one stream block of a chunk from the byte address `p` (the lane's 16 bytes included)
+#ifdef DUGKS_RLX_NOHINT
+#define RLX_HINT false
+#else
+#define RLX_HINT true
+#endif
+template <int CI>
+__device__ __forceinline__ void hot_stage_at(uint32_t sdst, unsigned long long p, unsigned long long pol) {
+#pragma unroll
+    for (int part = 0; part < CI * 256 / 512; part++) {
+        if (RLX_HINT) cp_async16_ef(sdst + part * 512, reinterpret_cast<const char*>(p) + part * 512, pol);
+        else cp_async16(sdst + part * 512, reinterpret_cast<const char*>(p) + part * 512);
+    }
+}
+// L2 hints of the relax+update kernel come from the kernel arguments (uniform registers; a policy made with
+// createpolicy inside the kernel lives in a vector register and costs two R2UR per LDGSTS)
+#define RLX_POL(x) (x)
 
 // interior cells: every stream lives in the same slab array, so 32-bit offsets (16-byte units, already
 // including the lane's 16 bytes) in registers replace the pointer table: one 64-bit multiply-add + CI/2
@@ -1345,8 +1367,6 @@ k_hot_relax_update(StepArgs a) {
         if (WMODE == 2 && lane < FCOEF_N / 2)   // half-step coefficient record of the cell (k_cell_coef)
             cp_async16(sd + (NE * (FCOEF_N + 4) + 2 * lane) * 8, a.ccoef + (size_t)M.c * FCOEF_N + 2 * lane);
     };
-    const unsigned long long pol_ef = l2_evict_first_policy();
-    const unsigned long long pol_el = l2_evict_last_policy();
     const int nw = gridDim.x * HOT_WARPS;
     int item = blockIdx.x * HOT_WARPS + wib;
     uint32_t q = 0;
@@ -1396,11 +1416,21 @@ k_hot_relax_update(StepArgs a) {
             const uint32_t sdst = smem_u32(st) + (uint32_t)lane * 16u, coff = (uint32_t)ch * (CI * 256u);
 #pragma unroll
             for (int fld = 0; fld < P::NFLD; fld++) {
-                hot_stage_one_ef<CI>(sdst + (fld * NSLOT + 0) * (CI * 256), fld ? hts : gts, offc, coff, pol_ef);
-                if (WMODE == 0) hot_stage_one_ef<CI>(sdst + (fld * NSLOT + 1) * (CI * 256), fld ? hbs : gbs, offc, coff, pol_ef);
+                // array base + chunk offset once per chunk and array, kept opaque: a stream then costs one 64-bit
+                // multiply-add and its LDGSTS (folded into every stream it was three integer instructions each)
+                unsigned long long bc = (unsigned long long)(fld ? hts : gts) + coff;
+                unsigned long long bf = (unsigned long long)(fld ? fk_h : fk_g) + coff;
+                asm volatile("" : "+l"(bc));
+                asm volatile("" : "+l"(bf));
+                hot_stage_at<CI>(sdst + (fld * NSLOT + 0) * (CI * 256), bc + (unsigned long long)offc * 16u, RLX_POL(a.pol_ef));
+                if (WMODE == 0) {
+                    unsigned long long bb = (unsigned long long)(fld ? hbs : gbs) + coff;
+                    asm volatile("" : "+l"(bb));
+                    hot_stage_at<CI>(sdst + (fld * NSLOT + 1) * (CI * 256), bb + (unsigned long long)offc * 16u, RLX_POL(a.pol_ef));
+                }
 #pragma unroll
                 for (int j = 0; j < NE; j++)   // every face block is read by two cells: keep it in L2 for the second one
-                    hot_stage_one_ef<CI>(sdst + (fld * NSLOT + NPRE + j) * (CI * 256), fld ? fk_h : fk_g, offf[j], coff, pol_el);
+                    hot_stage_at<CI>(sdst + (fld * NSLOT + NPRE + j) * (CI * 256), bf + (unsigned long long)offf[j] * 16u, RLX_POL(a.pol_el));
             }
         };
         // outward area vectors (sign folded in) and the face equilibria of the internal faces
@@ -1437,7 +1467,7 @@ k_hot_relax_update(StepArgs a) {
             }
         }
         // WMODE 2: half-step table of the cell itself (the operations of k_hot_halfstep)
-        double cEYZ = 0.0, cYZ2 = 0.0, cQYZ = 0.0, comrf = 0.0, cRT = 0.0;
+        double cEYZ = 0.0, cYZ2 = 0.0, cQYZ = 0.0, comrf = 0.0, cRT = 0.0, cqx = 0.0;
         if (WMODE == 2) {
             const double* rc = rec_s + NE * 4;                            // Ux Uy Uz a pre qx qy qz omrf RT (k_cell_coef)
             for (int tt = lane; tt < span; tt += 32) {
@@ -1450,7 +1480,8 @@ k_hot_relax_update(StepArgs a) {
             const double yz2 = (cy * cy + cz * cz) * rc[3];
             cEYZ = rc[4] * exp(-0.5 * yz2);
             cYZ2 = yz2 - a.gas.D - 2.0;
-            cQYZ = cy * rc[6] + cz * rc[7];
+            cQYZ = fma(-rc[0], rc[5], cy * rc[6] + cz * rc[7]);           // (xi - U).q = x qx + cQYZ, as the pencils form it
+            cqx = rc[5];
             comrf = rc[8];
             cRT = rc[9];
         }
@@ -1481,9 +1512,10 @@ k_hot_relax_update(StepArgs a) {
 #pragma unroll
             for (int fld = 0; fld < P::NFLD; fld++) {
                 const double* sf = sg + fld * NSLOT * CI * 32;
-                double sum[CI];
+                // two partial sums per point (even / odd entries): half the depth of the dependent FMA chain
+                double sum[CI], sum2[CI];
 #pragma unroll
-                for (int u = 0; u < CI; u++) sum[u] = 0.0;
+                for (int u = 0; u < CI; u++) sum[u] = sum2[u] = 0.0;
 #pragma unroll
                 for (int j = 0; j < NE; j++) {
                     if (j < nint) {
@@ -1499,14 +1531,20 @@ k_hot_relax_update(StepArgs a) {
                             if (fld == 0) eq = fma(cq, cc, 1.0) * gM;                                  // :1042
                             else eq = (kd + cq * ((cc + 2.0) * kd - 2.0 * a.gas.K)) * gM * frt;        // :1043
                             const double gf = fma(omrf, sf[((NPRE + j) * CI + u) * 32], eq);          // :880-881
-                            sum[u] = fma(fma(xx[u], Sx[j], cyz[j]), gf, sum[u]);                       // :952-955
+                            double& acc = (j & 1) ? sum2[u] : sum[u];
+                            acc = fma(fma(xx[u], Sx[j], cyz[j]), gf, acc);                             // :952-955
                         }
                     } else if (j < ne) {
 #pragma unroll
-                        for (int u = 0; u < CI; u++)
-                            sum[u] = fma(fma(xx[u], Sx[j], cyz[j]), sf[((NPRE + j) * CI + u) * 32], sum[u]);
+                        for (int u = 0; u < CI; u++) {
+                            double& acc = (j & 1) ? sum2[u] : sum[u];
+                            acc = fma(fma(xx[u], Sx[j], cyz[j]), sf[((NPRE + j) * CI + u) * 32], acc);
+                        }
                     }
                 }
+                // new values of the whole chunk first (one basic block: the chains of its points interleave), stores and
+                // moment sums after
+                double vnew[CI];
 #pragma unroll
                 for (int u = 0; u < CI; u++) {
                     double wcell;
@@ -1515,20 +1553,23 @@ k_hot_relax_update(StepArgs a) {
                     else {
                         const double* xt = ctab + (size_t)(tb + u - tmin) * 4;
                         const double2 x01 = lds2(xt);
-                        const double cc = x01.y + cYZ2, cq = xt[2] + cQYZ, gM = x01.x * cEYZ;
+                        const double cc = x01.y + cYZ2, cq = fma(xx[u], cqx, cQYZ), gM = x01.x * cEYZ;
                         const double t_i = sf[u * 32];
                         const double b_i = fld == 0 ? fma(comrf, t_i, fma(cq, cc, 1.0) * gM)                                      // :405,1042
                                                     : fma(comrf, t_i, (kd + cq * ((cc + 2.0) * kd - 2.0 * a.gas.K)) * gM * cRT);   // :406,1043
                         wcell = hot_w_combine(t_i, b_i);
                     }
-                    const double vnew = fma(-sum[u], dtv, wcell);                                      // :937,952
+                    vnew[u] = fma(-(sum[u] + sum2[u]), dtv, wcell);                                    // :937,952
+                }
+#pragma unroll
+                for (int u = 0; u < CI; u++) {
                     if (i0 + u >= Ln) continue;   // tail chunk (warp-uniform)
-                    __stcs((fld == 0 ? gdst : hdst) + (i0 + u) * 32, vnew);
+                    __stcs((fld == 0 ? gdst : hdst) + (i0 + u) * 32, vnew[u]);
                     if (fld == 0) {
-                        A[0] = fma(W[u][0], vnew, A[0]); A[1] = fma(W[u][1], vnew, A[1]);
-                        A[2] = fma(W[u][2], vnew, A[2]); A[3] = fma(W[u][3], vnew, A[3]);
+                        A[0] = fma(W[u][0], vnew[u], A[0]); A[1] = fma(W[u][1], vnew[u], A[1]);
+                        A[2] = fma(W[u][2], vnew[u], A[2]); A[3] = fma(W[u][3], vnew[u], A[3]);
                     } else {
-                        B[0] = fma(W[u][0], vnew, B[0]); B[1] = fma(W[u][1], vnew, B[1]);
+                        B[0] = fma(W[u][0], vnew[u], B[0]); B[1] = fma(W[u][1], vnew[u], B[1]);
                     }
                 }
             }

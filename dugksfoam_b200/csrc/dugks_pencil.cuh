@@ -77,7 +77,7 @@ __device__ __forceinline__ double pen_reduce13(double (&v)[NM_G], double* scratc
 
 // coefficients of one half-step conversion table (per lane: the y/z factor of the separable equilibrium)
 struct PenEq {
-    double EYZ, YZ2, QYZ, omrf, Ux, qx;
+    double EYZ, YZ2, QYZ, omrf, qx;   // QYZ = (y - Uy) qy + (z - Uz) qz - Ux qx: (xi - U).q = x qx + QYZ is one FMA per point
 };
 
 template <bool FUSE>
@@ -154,16 +154,15 @@ k_pencil_phase1(StepArgs a, PenArgs P) {
         const double yz2 = (cy * cy + cz * cz) * ia;
         E.EYZ = rc[4] * exp(-0.5 * yz2);
         E.YZ2 = yz2 - a.gas.D - 2.0;
-        E.QYZ = cy * rc[6] + cz * rc[7];
+        E.QYZ = fma(-Ux, rc[5], cy * rc[6] + cz * rc[7]);
         E.omrf = rc[8];
-        E.Ux = Ux;
         E.qx = rc[5];
     };
-    // gBarP of one value (same operations as k_hot_halfstep): xt = table row of the point, x = its abscissa
+    // gBarP of one value (the half step of k_hot_halfstep; (xi - U).q formed as x qx + const): xt = table row of the point, x = its abscissa
     auto convert = [&](double raw, const double* xt, double x, const PenEq& E) {
         const double2 x01 = lds2(xt);
         const double cc = x01.y + E.YZ2;
-        const double cq = __dadd_rn(__dmul_rn(x - E.Ux, E.qx), E.QYZ);
+        const double cq = fma(x, E.qx, E.QYZ);
         const double gM = x01.x * E.EYZ;
         return fma(E.omrf, raw, fma(cq, cc, 1.0) * gM);
     };
@@ -191,6 +190,12 @@ k_pencil_phase1(StepArgs a, PenArgs P) {
         }
         HotMeta cur{}, nxt{};
         hot_meta_issue(a, I.item0 + wl, lane, cur);
+        // cell ids one step ahead of their first use (read where they are needed, each is an exposed L2 round trip per
+        // step or chunk: 10 % of the stall samples, profiles/r02/ncu48s/): halo cells of this step and of the next one,
+        // own cell two positions ahead
+        int hy_c = htab[0], hz_c = htab[1];
+        int hy_nn = (1 < ns) ? ldg_early(htab + 8) : -1, hz_nn = (1 < ns) ? ldg_early(htab + 9) : -1;
+        int own2_n = (2 <= ns) ? ldg_early(ctab + 3 * 4) : -1;
         cp_async_commit();
         cp_async_wait<0>();
         __syncwarp();
@@ -220,9 +225,11 @@ k_pencil_phase1(StepArgs a, PenArgs P) {
             const int gsel = k & 1;
             const double* gb_ = geo + gsel * ((1 + PEN_NE) * 6);
             // ---- meta of this cell (issued one step ahead), of the next one
-            const int own_k2 = (k + 2 <= ns) ? ctab[(k + 3) * 4] : -1;          // position k + 2 (window prefetch)
-            const int hy_n = (k + 1 < ns) ? htab[(k + 1) * 8] : -1, hz_n = (k + 1 < ns) ? htab[(k + 1) * 8 + 1] : -1;
-            const int own_k2m = (k + 2 <= ns) ? own_k2 : -1;
+            const int own_k2m = own2_n;                                         // position k + 2 (window prefetch), -1 past the item
+            const int hy_n = hy_nn, hz_n = hz_nn;                               // halo cells of step k + 1
+            own2_n = (k + 3 <= ns) ? ldg_early(ctab + (k + 4) * 4) : -1;
+            hy_nn = (k + 2 < ns) ? ldg_early(htab + (k + 2) * 8) : -1;
+            hz_nn = (k + 2 < ns) ? ldg_early(htab + (k + 2) * 8 + 1) : -1;
             if (k + 1 < ns) hot_meta_issue(a, I.item0 + (k + 1) * 4 + wl, lane, nxt);
             {   // unpack the record of the current cell
                 const bool valid = lane < PEN_NE;
@@ -293,7 +300,7 @@ k_pencil_phase1(StepArgs a, PenArgs P) {
                 // ---- prefetch: window block of position k + 2 (this chunk: its x- use is over), next halo chunk
                 {
                     double* st_n = halo + ((q & 1) ^ 1) * (2 * PEN_CI * 32);
-                    if (ch + 1 < nchunk) load_halo(htab[k * 8], htab[k * 8 + 1], ch + 1, st_n);
+                    if (ch + 1 < nchunk) load_halo(hy_c, hz_c, ch + 1, st_n);
                     else if (k + 1 < ns) {
                         load_halo(hy_n, hz_n, 0, st_n);
                         hot_stage_geo(a.geo6 + (size_t)(nxt.e0 + nxt.c) * 6, PEN_NE, geo + (gsel ^ 1) * ((1 + PEN_NE) * 6), lane);
@@ -432,6 +439,7 @@ k_pencil_phase1(StepArgs a, PenArgs P) {
                 }
             }
             cur = nxt;
+            hy_c = hy_n; hz_c = hz_n;
             // next step: the other warps read this line's slot of position k + 1 (converted above, landed long ago)
             __syncthreads();
         }

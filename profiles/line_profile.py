@@ -21,7 +21,7 @@ for l in txt[start + 1:]:
     m = re.search(r'//## File "([^"]+)", line (\d+)', l)
     if m:
         cur = (m.group(1).split("/")[-1], int(m.group(2)))
-    elif re.match(r"\s+/\*[0-9a-f]{4}\*/", l):
+    elif re.match(r"\s+/\*[0-9a-f]{4,6}\*/", l):
         lines.append(cur)
 rows = list(csv.reader(open(src_csv)))
 hdr = rows[1]
