@@ -14,7 +14,7 @@ import numpy as np
 
 from . import dvset as _dvset
 from . import foam
-from .polymesh import Geometry, PolyMesh, compute_geometry, hex_block, ogrid_cylinder, tri_prism_2d
+from .polymesh import Geometry, PolyMesh, compute_geometry, hex_block, ogrid_cylinder, ratchet_profile, tri_prism_2d
 
 # dugks_patch_kind (include/dugks.h)
 PATCH_ZERO_GRADIENT, PATCH_MIXED, PATCH_MAXWELL_WALL, PATCH_FAR_FIELD = 0, 1, 2, 3
@@ -229,6 +229,22 @@ def tri_cavity_case(n: int, nDV: int = 28, *, distort: float = 0.15, wall_T=None
     Xis, w = gh_set(nDV)
     return _uniform_case(mesh, Xis, w, {}, wall_T=wall_T or {"movingWall": 300.0}, name=f"tri_{n}x{n}_GH{nDV}",
                          perturb=perturb)
+
+
+def ratchet_channel_case(nx: int, ny: int, nDV: int = 28, *, teeth: int = 4, tooth_height: float = 0.3, aspect: float = 4.0,
+                         T_ratchet: float = 0.9 * T0, T_top: float = 1.1 * T0, distort: float = 0.1, perturb: float = 0.0) -> Case:
+    """2-D micro-channel with a ratchet (saw-tooth) lower wall on an unstructured triangular mesh, every solid wall a
+    diffuse Maxwell wall at its own temperature (BASELINE config 4): the ratchet at `T_ratchet`, the flat upper wall at
+    `T_top`, the two end walls at the mean - a thermally driven (Knudsen-pump) flow, no moving wall.  The reference case
+    closes the channel with cyclic patches, which are out of scope: walls stand in for them.
+    2 nx ny triangular prisms: nx = 632, ny = 158 gives 199,712 cells."""
+    L = aspect
+    mesh = tri_prism_2d(nx, ny, (L, 1.0, 0.1), distort=distort, bottom=ratchet_profile(teeth, tooth_height, L),
+                        patch_names={"ymax": "topWall", "ymin": "ratchet", "xmin": "endWalls", "xmax": "endWalls"})
+    Xis, w = gh_set(nDV)
+    return _uniform_case(mesh, Xis, w, {}, lid_patch="none",
+                         wall_T={"ratchet": T_ratchet, "topWall": T_top, "endWalls": 0.5 * (T_ratchet + T_top)},
+                         name=f"ratchet_{nx}x{ny}_GH{nDV}", perturb=perturb)
 
 
 def cylinder_case(ntheta: int, nr: int, nDV: int = 81, *, mach: float = 5.0, quad: str = "NC", xiMax: Optional[float] = None,

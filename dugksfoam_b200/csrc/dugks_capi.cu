@@ -434,7 +434,8 @@ static int hot_configure(dugks_handle* h) {
     h->hot_grid_out1 = std::max(1, std::min(dev_sms * std::max(occ[0], 1), max_ctas));
     h->hot_grid_out2 = std::max(1, std::min(dev_sms * std::max(occ[1], 1), max_ctas));
     h->hot_grid_upd = std::max(1, std::min(dev_sms * std::max(occ[2], 1), max_ctas));
-    if (const char* e = getenv("DUGKS_RLX_CTAS")) occ[3] = std::max(1, std::min(occ[3], atoi(e)));   // experiment hook
+    if (const char* e = getenv("DUGKS_RLX_CTAS"))   // experiment hook
+        for (int k = 3; k < 6; k++) occ[k] = std::max(1, std::min(occ[k], atoi(e)));
     if (const char* e = getenv("DUGKS_UPD_CTAS")) occ[2] = std::max(1, std::min(occ[2], atoi(e)));
     h->hot_grid_upd = std::max(1, std::min(dev_sms * std::max(occ[2], 1), max_ctas));
     h->hot_grid_rlx = std::max(1, std::min(dev_sms * std::max(occ[3], 1), max_ctas));
@@ -1584,7 +1585,7 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
         if (const char* e = getenv("DUGKS_WAVE")) nwarps = std::max(1, atoi(e));
         int tile = 0;
         if (const char* e = getenv("DUGKS_TILE")) tile = std::max(1, atoi(e));
-        std::vector<int> order;
+        std::vector<int> order, order2;   // order2: traversal of the phase-2 kernels of face-storage slabs where it differs
         build_cell_order(nc, D, mesh->C, h->want_split ? cell_cls.data() : nullptr, ord_env ? ord_env : "wave", tile, nwarps, order);
         // CTA pencils of phase 1 (3-D, h elided, every cell within the compile-time face count): DUGKS_PENCIL =
         // 2 (default: the pencil applies the half step itself) | 1 (pencil reads gBarP) | 0 (off)
@@ -1607,6 +1608,23 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
                     for (int c : order) if (!inpen[c]) rest.push_back(c);
                     order = ph.order;
                     order.insert(order.end(), rest.begin(), rest.end());
+                    // Phase 2 (k_hot_relax_update: warp w takes items w, w + nWarps, ...) walks the pencil cells with
+                    // nWarps / 4 work items in lock-step along x: both readers of a face then run within one sweep of
+                    // the grid (50 MB of traffic apart).  In work-item order the z neighbour of a bundle was 4 sweeps
+                    // away and the second read of its faces came from DRAM (1.2 of 9 GB per launch).
+                    if (getenv("DUGKS_ORDER2_OFF") == nullptr) {
+                        const int per_round = std::max(1, nwarps / PEN_WARPS);
+                        for (size_t i0 = 0; i0 < ph.items.size(); i0 += per_round) {
+                            const size_t i1 = std::min(ph.items.size(), i0 + per_round);
+                            int smax = 0;
+                            for (size_t i = i0; i < i1; i++) smax = std::max(smax, ph.items[i].nsteps);
+                            for (int k = 0; k < smax; k++)
+                                for (size_t i = i0; i < i1; i++)
+                                    if (k < ph.items[i].nsteps)
+                                        for (int l = 0; l < PEN_WARPS; l++) order2.push_back(ph.order[ph.items[i].item0 + PEN_WARPS * k + l]);
+                        }
+                        order2.insert(order2.end(), rest.begin(), rest.end());
+                    }
                     PenItem* d_items = nullptr;
                     int *d_pc = nullptr, *d_ph = nullptr;
                     TRYB(dev_upload(h, &d_items, ph.items));
@@ -1629,23 +1647,32 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
             }
         }
         // per-cell record (CMETA_N ints) in traversal order: everything a warp needs to start a cell in one load level
-        std::vector<int> cmeta((size_t)nc * CMETA_N, 0);
-        for (int item = 0; item < nc; item++) {
-            const int c = order[item];
-            int* rec = &cmeta[(size_t)item * CMETA_N];
-            rec[20] = c;
-            rec[0] = off[c];
-            rec[1] = (cnt[c] & 0xff) | ((cnt_int[c] & 0xff) << 8) | ((int)cell_cls[c] << 16);
-            unsigned char* kinds = reinterpret_cast<unsigned char*>(rec + 18);
-            for (int j = 0; j < 8; j++) kinds[j] = 0xff;
-            for (int j = 0; j < cnt[c] && j < 8; j++) {
-                const int e = off[c] + j;
-                rec[2 + j] = e_other[e];
-                rec[10 + j] = e_face[e] | (e_owner[e] ? (int)0x80000000u : 0);
-                if (e_other[e] < 0) kinds[j] = (unsigned char)b_kind[-1 - e_other[e]];
+        auto build_cmeta = [&](const std::vector<int>& ord, std::vector<int>& cmeta) {
+            cmeta.assign((size_t)nc * CMETA_N, 0);
+            for (int item = 0; item < nc; item++) {
+                const int c = ord[item];
+                int* rec = &cmeta[(size_t)item * CMETA_N];
+                rec[20] = c;
+                rec[0] = off[c];
+                rec[1] = (cnt[c] & 0xff) | ((cnt_int[c] & 0xff) << 8) | ((int)cell_cls[c] << 16);
+                unsigned char* kinds = reinterpret_cast<unsigned char*>(rec + 18);
+                for (int j = 0; j < 8; j++) kinds[j] = 0xff;
+                for (int j = 0; j < cnt[c] && j < 8; j++) {
+                    const int e = off[c] + j;
+                    rec[2 + j] = e_other[e];
+                    rec[10 + j] = e_face[e] | (e_owner[e] ? (int)0x80000000u : 0);
+                    if (e_other[e] < 0) kinds[j] = (unsigned char)b_kind[-1 - e_other[e]];
+                }
             }
-        }
+        };
+        std::vector<int> cmeta;
+        build_cmeta(order, cmeta);
         TRYB(dev_upload(h, &d_i, cmeta)); A.cmeta = d_i;
+        A.cmeta2 = A.cmeta;
+        if ((int)order2.size() == nc) {
+            build_cmeta(order2, cmeta);
+            TRYB(dev_upload(h, &d_i, cmeta)); A.cmeta2 = d_i;
+        }
     }
     TRYB(dev_upload(h, &d_i, e_other)); M.e_other = d_i;
     TRYB(dev_upload(h, &d_i, e_face)); M.e_face = d_i;

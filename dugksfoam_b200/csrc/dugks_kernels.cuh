@@ -47,7 +47,8 @@ struct StepArgs {
     const uint4 *upw;                       // [nslab][nc][32] upwind range codes (k_build_upwind)
     double *fcoef;                          // [nf][12] face equilibrium records (k_face_macros)
     int item0, item1;                       // item range of a split launch (0, 0 = all cells)
-    const int *cmeta;                       // [nc][20] per-cell record of the second-generation kernels (dugks_hot.cuh)
+    const int *cmeta;                       // [nc][24] per-cell record of the second-generation kernels (dugks_hot.cuh)
+    const int *cmeta2;                      // the same records in the traversal order of k_hot_relax_update (= cmeta unless pencils are on)
     const unsigned char *cell_cls;          // [nc] 1: axis-aligned interior cell (entries in axis order), else 0
     double *fkeep_g, *fkeep_h;              // [n_keep_slabs][nif][L][32] reconstructed face values (face-storage slabs) or null
     double *ccoef;                          // [nc][12] half-step equilibrium records of the cells (k_cell_coef)

@@ -512,12 +512,27 @@ def ogrid_cylinder(ntheta: int, nr: int, r_in: float = 0.5, r_out: float = 15.0,
                     patches=patches, nCells=ntheta * nr)
 
 
+def ratchet_profile(teeth: int, height: float, length: float, rise: float = 0.8):
+    """Saw-tooth (ratchet) wall y_b(x): `teeth` asymmetric teeth over [0, length], each rising linearly to
+    `height` over the fraction `rise` of its period and falling back over the rest."""
+    period = length / teeth
+
+    def yb(x):
+        s = np.mod(x, period) / period
+        s = np.where(np.isclose(x, length), 0.0, s)
+        return height * np.where(s <= rise, s / rise, (1.0 - s) / (1.0 - rise))
+    return yb
+
+
 def tri_prism_2d(nx: int, ny: int, lengths=(1.0, 1.0, 0.1), *, distort: float = 0.0,
-                 seed: int = 20260101, patch_names: Optional[Dict[str, str]] = None) -> PolyMesh:
+                 seed: int = 20260101, patch_names: Optional[Dict[str, str]] = None,
+                 bottom=None) -> PolyMesh:
     """2-D unstructured triangular mesh (each quad of an nx*ny grid split along
     alternating diagonals, optionally distorted), extruded one cell in z with an
     ``empty`` frontAndBack patch — the shape of BASELINE config 4 (tri mesh,
-    Maxwell walls).  Cells are triangular prisms: 3 quad side faces + 2 triangles."""
+    Maxwell walls).  Cells are triangular prisms: 3 quad side faces + 2 triangles.
+    `bottom(x)`: profile of the lower wall (ratchet_profile); the columns of the mesh are
+    compressed between it and the flat upper wall."""
     Lx, Ly, Lz = lengths
     px, py = nx + 1, ny + 1
     xs = np.linspace(0, Lx, px); ys = np.linspace(0, Ly, py)
@@ -530,7 +545,11 @@ def tri_prism_2d(nx: int, ny: int, lengths=(1.0, 1.0, 0.1), *, distort: float = 
         h = np.array([Lx / nx, Ly / ny])
         xy[interior] += ((rng.random((len(xy), 2)) - 0.5) * 2 * distort * h)[interior]
     npl = len(xy)
-    points = np.concatenate([np.column_stack([xy, np.zeros(npl)]), np.column_stack([xy, np.full(npl, Lz)])])
+    xyp = xy.copy()    # patches are told apart on the unmapped rectangle
+    if bottom is not None:
+        yb = np.asarray(bottom(xyp[:, 0]), dtype=np.float64)
+        xyp[:, 1] = yb + xy[:, 1] * (Ly - yb) / Ly
+    points = np.concatenate([np.column_stack([xyp, np.zeros(npl)]), np.column_stack([xyp, np.full(npl, Lz)])])
 
     def p2(i, j):
         return i + px * j

@@ -137,6 +137,7 @@ def test_every_kernel_path(oracle_lib, monkeypatch, path, env):
            ("cavity3d_10_gh8_storeh", cs.cavity3d_case(10, 8, perturb=0.01), True),   # axis-only launch, 6 faces, with h
            ("cavity2d_9_nc9_ties", cs.cavity2d_case(9, 9, quad="NC", perturb=0.01), False),
            ("tri_8_gh8", cs.tri_cavity_case(8, 8, perturb=0.01), False),
+           ("ratchet_20x8_gh8", cs.ratchet_channel_case(20, 8, 8, teeth=2, perturb=0.01), False),   # config 4 as named
            ("cavity3d_4_gh8_storeh", cs.cavity3d_case(4, 8, perturb=0.01), True)]
     for name, case, store_h in zoo:
         dv = capi.fvDVM(case, store_h=store_h)

@@ -65,6 +65,29 @@ def test_golden_case_facts():
     assert abs(GOLD["gas"]["R"] - 208.244343891) < 1e-12 and GOLD["lid_U"] == [50.0, 0.0, 0.0]
 
 
+def test_ratchet_channel_mesh():
+    """BASELINE config 4: channel with a saw-tooth lower wall on triangular prisms, walls at three temperatures."""
+    from dugksfoam_b200.polymesh import cell_centres_and_volumes, face_centres_and_areas
+    c = cs.ratchet_channel_case(40, 10, 8, teeth=4, tooth_height=0.3)
+    m = c.mesh
+    Cf, Sf = face_centres_and_areas(m)
+    C, V = cell_centres_and_volumes(m, Cf, Sf)
+    nif = m.nInternalFaces
+    closure = np.zeros((m.nCells, 3))
+    np.add.at(closure, m.owner, Sf)
+    np.add.at(closure, m.neighbour, -Sf[:nif])
+    assert m.nCells == 2 * 40 * 10 and V.min() > 0 and np.abs(closure).max() < 1e-15
+    assert abs(V.sum() - (4.0 - 0.5 * 0.3 * 4.0) * 0.1) < 1e-13          # rectangle minus the four triangular teeth
+    sizes = {p.name: p.size for p in c.patches}
+    assert sizes == {"topWall": 40, "ratchet": 40, "endWalls": 20}
+    # the ratchet wall really is a saw tooth: its face normals alternate between the two flanks
+    pr = [p for p in c.patches if p.name == "ratchet"][0]
+    nx_ = Sf[nif + pr.start: nif + pr.start + pr.size, 0]
+    assert (nx_ > 0).sum() == 32 and (nx_ < 0).sum() == 8                # rising flank 80 % of a period (outward normal tilts to +x... of the gas side), falling 20 %
+    Tb = {p.name: set(np.round(c.T_b[p.start:p.start + p.size], 9)) for p in c.patches}
+    assert Tb == {"topWall": {300.3}, "ratchet": {245.7}, "endWalls": {273.0}}
+
+
 # ---- geometry identities ---------------------------------------------------------------
 @pytest.mark.parametrize("mesh", [hex_block(5, 4, 3, (1.0, 0.8, 0.6), distort=0.2),
                                   hex_block(6, 5, 1, (1.0, 1.0, 0.1), two_d=True, distort=0.2),
