@@ -15,6 +15,7 @@
 #include "../../include/dugks.h"
 #include "dugks_hot.cuh"
 #include "dugks_pencil.cuh"
+#include "dugks_pencil_ws.cuh"
 
 // ------------------------------------------------------------------------------
 // NCCL through dlopen (the library is present in every torch install and on the
@@ -72,6 +73,9 @@ struct dugks_handle {
     int nvl = 0;                   // local (real) DVs
     bool hasH = true;
     int nm = NM_MAX;
+    std::vector<double> tx_host;   // [5][ntab] abscissae and moment weights of a row (DevDV::tx)
+    bool pen_ws = false;           // phase 1 of the fused slabs by the warp-specialised pencil kernel
+    size_t pen_ws_smem = 0;
     int rank = 0, nranks = 1;
     double xiMax = 0;
     DevGas gas{};
@@ -265,6 +269,9 @@ constexpr int CI_OUT1 = DUGKS_CI_OUT1, CI_OUT2 = 2, CI_RLX = DUGKS_CI_RLX;
 constexpr int CI_AXIS = DUGKS_CI_AXIS;
 // update kernel of the flux-buffer path: 4 points per chunk, 2 when h doubles the streams (shared memory per CTA)
 #define CI_UPD (H ? 2 : 4)
+#ifndef DUGKS_PENCIL_WS_DEFAULT
+#define DUGKS_PENCIL_WS_DEFAULT 0
+#endif
 // DUGKS_DEV_BUILD (experiment builds, profiles/ab_bench.py): only the instantiations of the 3-D, h-elided case with
 // unchunked rows are compiled (a tenth of the build time); every other case fails with DUGKS_ERR_UNSUPPORTED.
 #ifdef DUGKS_DEV_BUILD
@@ -296,7 +303,8 @@ static void launch_hot_outgoing(dugks_handle* h, const StepArgs& a) {
         const int grid1 = std::max(1, std::min(h->hot_grid_axis, (a1.item1 - a1.item0 + HOT_WARPS - 1) / HOT_WARPS));
         if (!H && pm) {
             // CTA pencils (dugks_pencil.cuh) take the bundled x-lines; the axis-only launch what is left of the axis-aligned cells
-            if (pm == 2) k_pencil_phase1<true><<<h->pen_grid, PEN_WARPS * 32, h->pen_smem, h->stream>>>(a, h->pen);
+            if (pm == 2 && h->pen_ws) k_pencil_ws<<<h->pen_grid, 2 * PEN_WARPS * 32, h->pen_ws_smem, h->stream>>>(a, h->pen);
+            else if (pm == 2) k_pencil_phase1<true><<<h->pen_grid, PEN_WARPS * 32, h->pen_smem, h->stream>>>(a, h->pen);
             else k_pencil_phase1<false><<<h->pen_grid, PEN_WARPS * 32, h->pen_smem, h->stream>>>(a, h->pen);
             h->launches++;
         }
@@ -452,6 +460,20 @@ static int hot_configure(dugks_handle* h) {
             if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_pen, k_pencil_phase1<true>, PEN_WARPS * 32, h->pen_smem);
             if (e != cudaSuccess) return fail(h, DUGKS_ERR_CUDA, "pencil kernel configuration: %s", cudaGetErrorString(e));
             if (occ_pen < 1) h->pen_mode = 0;
+            // warp-specialised variant (dugks_pencil_ws.cuh): producer + consumer warp per line, same shared-memory budget
+            h->pen_ws = false;
+            const char* ws_env = getenv("DUGKS_PENCIL_WS");
+            const int min_len = h->Lt > 0 ? std::min(h->L, h->Lt) : h->L;
+            if (h->pen_mode == 2 && (ws_env ? atoi(ws_env) != 0 : DUGKS_PENCIL_WS_DEFAULT) && min_len >= PWS_STAGES * PWS_CH && min_len % PWS_CH == 0) {
+                h->pen_ws_smem = PwsPlan::total(h->L, ntab, h->tabw);
+                int occ_ws = 0;
+                e = cudaFuncSetAttribute(k_pencil_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->pen_ws_smem);
+                if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ws, k_pencil_ws, 2 * PEN_WARPS * 32, h->pen_ws_smem);
+                if (e != cudaSuccess) { (void)cudaGetLastError(); occ_ws = 0; }
+                h->pen_ws = occ_ws >= 2;
+                if (getenv("DUGKS_VERBOSE"))
+                    fprintf(stderr, "dugks: warp-specialised pencils: %zu B shared memory per CTA, %d CTAs/SM -> %s\n", h->pen_ws_smem, occ_ws, h->pen_ws ? "on" : "off");
+            }
         }
         if (getenv("DUGKS_VERBOSE"))
             fprintf(stderr, "dugks: pencils mode %d, %d of %d axis-aligned cells in %d work items, %zu B shared memory per CTA, %d CTAs/SM, %d cells in the half-step list\n",
@@ -694,6 +716,20 @@ static int step_impl(dugks_handle* h, double dt) {
     size_t nslots = (size_t)2 * h->nif + h->nbf;
     CUDA_TRY(h, cudaMemsetAsync(a.fslot, 0, nslots * h->nm * sizeof(double), h->stream));
     CUDA_TRY(h, cudaMemsetAsync(a.cslot, 0, (size_t)h->nc * h->nm * sizeof(double), h->stream));
+    if (h->pen_mode) {
+        // the per-point constants of a row {-dt/2 x, w, w x, w x^2, w x^3, x} for the pencils' stencil loop: constant bank
+        // instead of three shared-memory loads per point (the copy is staged by the driver: the buffer may be reused)
+        double t6[(NT_MAX + HOT_CI_MAX) * 6];
+        const int nt = h->ntab;
+        for (int k = 0; k < nt + HOT_CI_MAX; k++) {
+            const int kk = std::min(k, nt - 1);
+            const bool real = k < nt;
+            t6[k * 6 + 0] = -0.5 * dt * h->tx_host[kk];
+            for (int m = 1; m <= 4; m++) t6[k * 6 + m] = real ? h->tx_host[(size_t)m * nt + kk] : 0.0;
+            t6[k * 6 + 5] = h->tx_host[kk];
+        }
+        CUDA_TRY(h, cudaMemcpyToSymbolAsync(c_txs, t6, sizeof(double) * (size_t)(nt + HOT_CI_MAX) * 6, 0, cudaMemcpyHostToDevice, h->stream));
+    }
     if (h->pen_mode == 2) {
         k_cell_coef<<<(h->nc + 127) / 128, 128, 0, h->stream>>>(a);
         if ((rc = check_launch(h, "k_cell_coef"))) return rc;
@@ -1737,6 +1773,7 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
     DevDV& V = A.dv;
     V.L = L; V.Lt = h->Lt; V.Rs = h->Rs; V.nslab = h->nslab; V.ntab = h->ntab; V.hasH = h->hasH; V.tabw = h->tabw;
     TRYB(dev_upload(h, &d_d, tx)); V.tx = d_d;
+    h->tx_host = tx;
     TRYB(dev_upload(h, &d_d, row_y)); V.row_y = d_d;
     TRYB(dev_upload(h, &d_d, row_z)); V.row_z = d_d;
     TRYB(dev_upload(h, &d_d, row_w)); V.row_w = d_d;

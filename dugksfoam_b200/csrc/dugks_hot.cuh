@@ -345,6 +345,13 @@ struct HotPlan {
     static __host__ size_t total(int ntab) { return txs_bytes(ntab) + HOT_WARPS * PER_WARP; }
 };
 
+// the same table in the constant bank, filled by the host before every step (pencil kernel: uniform reads that
+// cost no shared-memory instruction)
+__constant__ double c_txs[(NT_MAX + HOT_CI_MAX) * 6];
+#ifndef RLX_CTXS
+#define RLX_CTXS 0
+#endif
+
 // txs[t] = { -0.5 dt x, W0, W1, W2, W3, x }, zero weights past the table
 __device__ __forceinline__ void hot_fill_txs(const DevDV& dv, double hd, double* txs) {
     for (int k = threadIdx.x; k < dv.ntab + HOT_CI_MAX; k += blockDim.x) {
@@ -1520,8 +1527,13 @@ k_hot_relax_update(StepArgs a) {
             double xx[CI], W[CI][4];
 #pragma unroll
             for (int u = 0; u < CI; u++) {
+#if RLX_CTXS
+                const double* ct = c_txs + (tb + u) * 6;          // constant bank (filled per step by the host when pencils are on)
+                W[u][0] = ct[1]; W[u][1] = ct[2]; W[u][2] = ct[3]; W[u][3] = ct[4]; xx[u] = ct[5];
+#else
                 const double2 t0 = lds2(txs + (tb + u) * 6), t1 = lds2(txs + (tb + u) * 6 + 2), t2 = lds2(txs + (tb + u) * 6 + 4);
                 W[u][0] = t0.y; W[u][1] = t1.x; W[u][2] = t1.y; W[u][3] = t2.x; xx[u] = t2.y;
+#endif
             }
 #pragma unroll
             for (int fld = 0; fld < P::NFLD; fld++) {

@@ -26,6 +26,12 @@
 #define PEN_CI 4         // points per staged chunk (1 KB per block and chunk)
 #define PEN_CU 2         // points advanced together
 #define PEN_NE 6
+#ifndef PEN_CTXS
+#define PEN_CTXS 1       // per-point row constants of the stencil loop from the constant bank (c_txs) instead of shared memory
+#endif
+#ifndef PEN_PREPASS
+#define PEN_PREPASS 0    // fused half step as passes of their own (block of the own line, halo chunks) instead of inside the stencil loop
+#endif
 
 // One work item: `nsteps` consecutive x positions of a bundle.
 //   cells: offset into pen_cells of [(nsteps + 2)][4] cell ids, positions -1 .. nsteps of the four lines
@@ -244,6 +250,19 @@ k_pencil_phase1(StepArgs a, PenArgs P) {
                 build_table(mr + FCOEF_N, xtab + TW * 2, Ehy);
                 build_table(mr + 2 * FCOEF_N, xtab + 2 * TW * 2, Ehz);
                 __syncwarp();
+#if PEN_PREPASS
+                // own(k + 1) enters the window converted, in a pass of its own: Ln independent conversions hide the FP64
+                // latency that two points at a time inside the stencil loop cannot.  Its last chunk may still be in flight
+                // (newest commit group): that one is converted where the chunk loop has waited for it.
+                {
+                    double* blkp = wslot(k + 1, wl) + lane;
+                    const double* xt0 = xtab + (cb - tmin) * 2;
+                    const double* tx0 = txs + cb * 6 + 5;
+                    const int npre = (nchunk - 1) * PEN_CI;
+#pragma unroll 4
+                    for (int i = 0; i < npre; i++) blkp[i * 32] = convert(blkp[i * 32], xt0 + i * 2, tx0[i * 6], Exp);
+                }
+#endif
             }
             // ---- upwind sets (static codes), store pointers, accumulators: as hot_axis_item
             const unsigned ownmask = __ballot_sync(0xffffffffu, cur.own != 0);
@@ -327,9 +346,29 @@ k_pencil_phase1(StepArgs a, PenArgs P) {
                 const double* const cy_ = wy + c0 * 32;
                 const double* const cz_ = wz + c0 * 32;
                 const double* const ctx = txs + (cb + c0) * 6;
+#if PEN_CTXS
+                const double* const cct = c_txs + (cb + c0) * 6;  // uniform except in the short-row tail slab (two chunk bases per warp)
+#endif
                 const double* const cxt = xtab + (cb + c0 - tmin) * 2;
                 double* const kxc[2] = {kx[0] + c0 * 32, kx[1] + c0 * 32};
                 double* const kpc[2] = {kp[0] + c0 * 32, kp[1] + c0 * 32};
+#if PEN_PREPASS
+                if (FUSE) {
+                    // the two halo blocks of this chunk, converted in place (each lane owns its column of the stage)
+                    double* sgw = halo + (q & 1) * (2 * PEN_CI * 32) + lane;
+#pragma unroll
+                    for (int u = 0; u < PEN_CI; u++) {
+                        const double xq = ctx[u * 6 + 5];
+                        sgw[u * 32] = convert(sgw[u * 32], cxt + (TW + u) * 2, xq, Ehy);
+                        sgw[(PEN_CI + u) * 32] = convert(sgw[(PEN_CI + u) * 32], cxt + (2 * TW + u) * 2, xq, Ehz);
+                    }
+                    if (ch == nchunk - 1) {
+#pragma unroll
+                        for (int u = 0; u < PEN_CI; u++)
+                            if (c0 + u < Ln) cp[u * 32] = convert(cp[u * 32], cxt + u * 2, ctx[u * 6 + 5], Exp);
+                    }
+                }
+#endif
 #pragma unroll
                 for (int sub = 0; sub < PEN_CI / PEN_CU; sub++) {
                     if (sub >= nsub) break;                                        // warp-uniform (short last chunk)
@@ -338,7 +377,13 @@ k_pencil_phase1(StepArgs a, PenArgs P) {
                     double v[PEN_CU], g0[PEN_CU], g1[PEN_CU], g2[PEN_CU], base[PEN_CU], W[PEN_CU][4];
 #pragma unroll
                     for (int u = 0; u < PEN_CU; u++) {
+#if PEN_CTXS
+                        double2 t0, t1, t2;
+                        t0.x = cct[(so + u) * 6]; t0.y = cct[(so + u) * 6 + 1]; t1.x = cct[(so + u) * 6 + 2];
+                        t1.y = cct[(so + u) * 6 + 3]; t2.x = cct[(so + u) * 6 + 4]; t2.y = cct[(so + u) * 6 + 5];
+#else
                         const double2 t0 = lds2(ctx + (so + u) * 6), t1 = lds2(ctx + (so + u) * 6 + 2), t2 = lds2(ctx + (so + u) * 6 + 4);
+#endif
                         W[u][0] = t0.y; W[u][1] = t1.x; W[u][2] = t1.y; W[u][3] = t2.x;
                         const double xq = t2.y;
                         v[u] = ck[(so + u) * 32];
@@ -346,12 +391,16 @@ k_pencil_phase1(StepArgs a, PenArgs P) {
                         double vxp = cp[(so + u) * 32];
                         const double vyi = cy_[(so + u) * 32], vzi = cz_[(so + u) * 32];
                         double vyh = sg[(so + u) * 32], vzh = sg[(PEN_CI + so + u) * 32];
+#if !PEN_PREPASS
                         if (FUSE) {
                             vxp = convert(vxp, cxt + (so + u) * 2, xq, Exp);
                             cp[(so + u) * 32] = vxp;                      // from now on the block holds gBarP
                             vyh = convert(vyh, cxt + (TW + so + u) * 2, xq, Ehy);
                             vzh = convert(vzh, cxt + (2 * TW + so + u) * 2, xq, Ehz);
                         }
+#else
+                        (void)xq;
+#endif
                         // gradient (stock leastSquaresGrad, zeroBoundaryGrad.C:90-99): one component per face
                         g0[u] = fma(Gxp, vxp, fma(Gxm, vxm, G0x * v[u]));
                         g1[u] = fma(Gyh, vyh, fma(Gyi, vyi, G0y * v[u]));
