@@ -1,9 +1,9 @@
 // dugks_pencil_ws.cuh — the fused CTA pencil of dugks_pencil.cuh, WARP-SPECIALISED: every x-line of the 2 x 2 bundle
 // has two warps,
-//   * a PRODUCER (warp group 1, 88 registers per thread) that fetches the halo chunks and the window block two
+//   * a PRODUCER (warp group 1, 96 registers per thread) that fetches the halo chunks and the window block two
 //     positions ahead (cp.async), builds the half-step tables (the exponentials) and converts gTilde -> gBarP in
 //     shared memory (discreteVelocity.C:393-406), and
-//   * a CONSUMER (warp group 0, 168 registers) that runs the stencil on converted values only: least-squares
+//   * a CONSUMER (warp group 0, 160 registers) that runs the stencil on converted values only: least-squares
 //     gradient, upwind reconstruction, face values, face moments (:412-530, fvDVM.C:473-516).
 // Why: the one-warp-per-line pencil is latency bound at 8 warps per SM (255 registers, 114 KB of
 // shared memory per CTA): 40 % of its stall samples sit on the conversion and the table builds, which feed the stencil's
@@ -18,8 +18,8 @@
 
 #define PWS_CH 2          // points per hand-over chunk
 #define PWS_STAGES 3      // halo ring: one stage in use by the consumer, one converted / converting, one in flight
-#define PWS_CONS_REGS 168
-#define PWS_PROD_REGS 88
+#define PWS_CONS_REGS 160
+#define PWS_PROD_REGS 96
 
 struct PwsPlan {
     static __host__ __device__ size_t txs_bytes(int ntab) { return PenPlan::txs_bytes(ntab); }
