@@ -91,6 +91,7 @@ struct dugks_handle {
     StepArgs A{};                      // template argument block (slab, dt patched per launch)
     double *gam_a_g = nullptr, *gam_a_h = nullptr, *gam_b_g = nullptr, *gam_b_h = nullptr;
     bool gam_flip = false;
+    bool gam_single = false;   // one copy of the lagged boundary gradient, updated in place (second-generation kernels only)
     double *wall_cin = nullptr, *wall_in = nullptr;
     int* d_bc = nullptr;
     double* d_pres = nullptr;
@@ -708,7 +709,7 @@ static int step_impl(dugks_handle* h, double dt) {
     StepArgs a = h->A;
     a.dt = dt;
     // lagged boundary gradient: last step's new values become this step's old ones
-    h->gam_flip = !h->gam_flip;
+    if (!h->gam_single) h->gam_flip = !h->gam_flip;
     a.gam_old_g = h->gam_flip ? h->gam_b_g : h->gam_a_g;
     a.gam_old_h = h->gam_flip ? h->gam_b_h : h->gam_a_h;
     a.gam_new_g = h->gam_flip ? h->gam_a_g : h->gam_b_g;
@@ -717,18 +718,15 @@ static int step_impl(dugks_handle* h, double dt) {
     CUDA_TRY(h, cudaMemsetAsync(a.fslot, 0, nslots * h->nm * sizeof(double), h->stream));
     CUDA_TRY(h, cudaMemsetAsync(a.cslot, 0, (size_t)h->nc * h->nm * sizeof(double), h->stream));
     if (h->pen_mode) {
-        // the per-point constants of a row {-dt/2 x, w, w x, w x^2, w x^3, x} for the pencils' stencil loop: constant bank
-        // instead of three shared-memory loads per point (the copy is staged by the driver: the buffer may be reused)
-        double t6[(NT_MAX + HOT_CI_MAX) * 6];
+        // the per-point constants of a row for the pencils' stencil loop (PenArgs::tx6), this step's dt folded in
         const int nt = h->ntab;
-        for (int k = 0; k < nt + HOT_CI_MAX; k++) {
+        for (int k = 0; k < nt + HOT_CI_MAX && k < 32 + HOT_CI_MAX; k++) {
             const int kk = std::min(k, nt - 1);
             const bool real = k < nt;
-            t6[k * 6 + 0] = -0.5 * dt * h->tx_host[kk];
-            for (int m = 1; m <= 4; m++) t6[k * 6 + m] = real ? h->tx_host[(size_t)m * nt + kk] : 0.0;
-            t6[k * 6 + 5] = h->tx_host[kk];
+            h->pen.tx6[k * 6 + 0] = -0.5 * dt * h->tx_host[kk];
+            for (int m = 1; m <= 4; m++) h->pen.tx6[k * 6 + m] = real ? h->tx_host[(size_t)m * nt + kk] : 0.0;
+            h->pen.tx6[k * 6 + 5] = h->tx_host[kk];
         }
-        CUDA_TRY(h, cudaMemcpyToSymbolAsync(c_txs, t6, sizeof(double) * (size_t)(nt + HOT_CI_MAX) * 6, 0, cudaMemcpyHostToDevice, h->stream));
     }
     if (h->pen_mode == 2) {
         k_cell_coef<<<(h->nc + 127) / 128, 128, 0, h->stream>>>(a);
@@ -1666,7 +1664,8 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
                     TRYB(dev_upload(h, &d_items, ph.items));
                     TRYB(dev_upload(h, &d_pc, ph.cells));
                     TRYB(dev_upload(h, &d_ph, ph.halo));
-                    h->pen = PenArgs{d_items, (int)ph.items.size(), d_pc, d_ph};
+                    h->pen = PenArgs{};
+                    h->pen.items = d_items; h->pen.nitems = (int)ph.items.size(); h->pen.cells = d_pc; h->pen.halo = d_ph;
                     h->pen_grid = std::min(h->pen_grid, (int)ph.items.size());
                     // fused mode: the kernels of the other cells still read gBarP of those cells and of their neighbours
                     std::vector<char> need(nc, 0);
@@ -1837,14 +1836,12 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
     TRYB(dev_alloc(h, &A.gt, ncell_dv + HOT_PAD));
     // gBarP (A.gb, A.hb) is allocated with the face storage below: how much of it must persist depends on it
     TRYB(dev_alloc(h, &A.gsb, nb_dv + HOT_PAD));
-    TRYB(dev_alloc(h, &h->gam_a_g, nb_dv + HOT_PAD));
-    TRYB(dev_alloc(h, &h->gam_b_g, nb_dv + HOT_PAD));
+    TRYB(dev_alloc(h, &h->gam_a_g, nb_dv + HOT_PAD));   // the second copy (ping-pong), where one is needed, follows the kernel choice below
     // the flux buffer of the recompute path (A.fbuf_*) is placed with the face storage below
     if (h->hasH) {
         TRYB(dev_alloc(h, &A.ht, ncell_dv + HOT_PAD));
         TRYB(dev_alloc(h, &A.hsb, nb_dv + HOT_PAD));
         TRYB(dev_alloc(h, &h->gam_a_h, nb_dv + HOT_PAD));
-        TRYB(dev_alloc(h, &h->gam_b_h, nb_dv + HOT_PAD));
     }
     TRYB(dev_alloc(h, &A.fcoef, (size_t)nf * FCOEF_N));
     TRYB(dev_alloc(h, &A.ccoef, (size_t)nc * FCOEF_N));
@@ -1864,7 +1861,7 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
     TRYB(dev_alloc(h, &h->d_conv, 6 + 6 * COURANT_BLOCKS));
     TRYB(dev_alloc(h, &h->d_bstage, (size_t)5 * nbf));
     A.wall_cin = h->wall_cin; A.wall_in = h->wall_in;
-    A.gam_old_g = h->gam_a_g; A.gam_old_h = h->gam_a_h; A.gam_new_g = h->gam_b_g; A.gam_new_h = h->gam_b_h;
+    A.gam_old_g = h->gam_a_g; A.gam_old_h = h->gam_a_h;
 
     // ---- dynamic shared memory sizes
     h->smem_out1 = (size_t)5 * NT_MAX * 8 + (size_t)WARPS_PER_CTA * STAGE_BYTES;
@@ -1937,6 +1934,19 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
         A.upw = d_upw;
     }
     if (!h->use_hot || h->hsmem_half == 0) h->pen_mode = 0;
+    // Lagged boundary gradient (discreteVelocity.C:462-468): the second-generation kernels update it IN PLACE - the warp
+    // that owns a boundary cell reads the old value of a (face, velocity) before it writes the new one, in phase 1 for
+    // the face-storage slabs and in the second gradient pass (phase 2) for the recompute slabs, which read the old value
+    // twice.  The first-generation kernels and k_bnd_outgoing (far-field / pressure patches) read the old array after the
+    // cell kernel has run: they keep two copies.  One copy less is 4.4 GB at 64^3 x 28^3: one more face-storage slab.
+    h->gam_single = h->use_hot && h->n_big == 0 && !h->has_far && getenv("DUGKS_GAM_PINGPONG") == nullptr;
+    if (h->gam_single) { h->gam_b_g = h->gam_a_g; h->gam_b_h = h->gam_a_h; }
+    else {
+        TRYB(dev_alloc(h, &h->gam_b_g, nb_dv + HOT_PAD));
+        if (h->hasH) TRYB(dev_alloc(h, &h->gam_b_h, nb_dv + HOT_PAD));
+    }
+    A.gam_new_g = h->gam_b_g; A.gam_new_h = h->gam_b_h;
+    A.gam_late = h->gam_single ? 1 : 0;
 
     // ---- face-storage slabs: as many as device memory allows (all of them from 2 GPUs up at the
     // 64^3 x 28^3 size; about half on one GPU).  Cells with too many faces need the flux-buffer path.
@@ -1950,7 +1960,7 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
         const size_t per_slab = (size_t)nif * L * h->Rs * sizeof(double) * nfld;      // face values of a slab
         const size_t per_gb = (size_t)nc * L * h->Rs * sizeof(double) * nfld;          // gBarP of a slab
         // left free: CUDA context growth and the caller's own allocations; NCCL buffers when there are peers
-        const size_t reserve = nranks > 1 ? (size_t)3 << 30 : (size_t)3 << 29;
+        const size_t reserve = nranks > 1 ? (size_t)3 << 30 : (size_t)1 << 30;   // 1 GiB alone (everything else of the handle is allocated by now), 3 GiB with peers
         const bool can_w = h->hsmem_half > 0 && getenv("DUGKS_NO_WMODE") == nullptr;   // test hook: persistent gBarP everywhere
         long long avail = free2 > reserve ? (long long)(free2 - reserve) : 0;
         // dugks_par_t.scratch_bytes: the caller's cap on what the kept face values (and the gBarP blocks that go
@@ -1964,6 +1974,9 @@ extern "C" int dugks_create(const dugks_mesh_t* mesh, const dugks_patch_t* patch
             const long long blocks = can_w ? (h->nslab - k) + 1 : h->nslab;
             if (blocks * (long long)per_gb + k * (long long)per_slab <= avail) { fit = k; break; }
         }
+        if (getenv("DUGKS_VERBOSE"))
+            fprintf(stderr, "dugks: face storage: %.3f GB free of %.3f, reserve %.3f, available %.3f; %.3f GB of face values and %.3f GB of gBarP per slab: %lld of %d slabs keep their face values (held so far %.3f GB)\n",
+                    free2 / 1e9, total2 / 1e9, reserve / 1e9, avail / 1e9, per_slab / 1e9, per_gb / 1e9, fit, h->nslab, h->dev_bytes / 1e9);
         if (const char* e = getenv("DUGKS_KEEP_SLABS")) fit = std::min<long long>(fit, atoll(e));   // test hook
         h->n_keep = (int)std::max<long long>(0, std::min<long long>(fit, h->nslab));
         h->wmode = can_w && h->n_keep > 0;

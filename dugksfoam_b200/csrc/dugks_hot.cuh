@@ -345,13 +345,6 @@ struct HotPlan {
     static __host__ size_t total(int ntab) { return txs_bytes(ntab) + HOT_WARPS * PER_WARP; }
 };
 
-// the same table in the constant bank, filled by the host before every step (pencil kernel: uniform reads that
-// cost no shared-memory instruction)
-__constant__ double c_txs[(NT_MAX + HOT_CI_MAX) * 6];
-#ifndef RLX_CTXS
-#define RLX_CTXS 0
-#endif
-
 // txs[t] = { -0.5 dt x, W0, W1, W2, W3, x }, zero weights past the table
 __device__ __forceinline__ void hot_fill_txs(const DevDV& dv, double hd, double* txs) {
     for (int k = threadIdx.x; k < dv.ntab + HOT_CI_MAX; k += blockDim.x) {
@@ -593,7 +586,10 @@ __device__ __forceinline__ void hot_out_item(const StepArgs& a, const HotCtx& x,
             }
             // ---- boundary faces of this cell (PHASE 1): lagged normal gradient (:436-470) and the
             // outgoing half of the patch rules (:533-690)
-            if (!AXIS && PHASE == 1 && nint < ne) {
+            // gam_late (one in-place copy of the lagged gradient): a slab that recomputes its gradient in phase 2 still
+            // needs the old values then, so it writes the new ones there (same gx, gy, gz: same bits)
+            const bool gam_here = PHASE == 1 ? (!a.gam_late || fkeep_g != nullptr) : a.gam_late != 0;
+            if (!AXIS && (PHASE == 1 || gam_here) && nint < ne) {
                 for (int j = nint; j < ne; j++) {
                     const int kind = __shfl_sync(0xffffffffu, cur.kind, j);
                     const int b = -1 - __shfl_sync(0xffffffffu, cur.other, j);
@@ -605,12 +601,13 @@ __device__ __forceinline__ void hot_out_item(const StepArgs& a, const HotCtx& x,
 #pragma unroll
                     for (int jj = 0; jj < NE; jj++) if (jj == j) fj = full[jj];
                     const unsigned ob = fj >> i0;
-                    if (kind != K_SYMMETRY_PLANE) {
+                    if (gam_here && kind != K_SYMMETRY_PLANE) {
                         const double n0 = a.m.b_n[(size_t)b * 3], n1 = a.m.b_n[(size_t)b * 3 + 1], n2 = a.m.b_n[(size_t)b * 3 + 2];
 #pragma unroll
                         for (int u = 0; u < CI; u++)
                             if (i0 + u < L) gam_new[bo + u * 32] = gx[u] * n0 + gy[u] * n1 + gz[u] * n2;
                     }
+                    if (PHASE != 1) continue;
 #pragma unroll
                     for (int u = 0; u < CI; u++) {
                         if ((ob >> u) & 1u) {
@@ -1527,13 +1524,8 @@ k_hot_relax_update(StepArgs a) {
             double xx[CI], W[CI][4];
 #pragma unroll
             for (int u = 0; u < CI; u++) {
-#if RLX_CTXS
-                const double* ct = c_txs + (tb + u) * 6;          // constant bank (filled per step by the host when pencils are on)
-                W[u][0] = ct[1]; W[u][1] = ct[2]; W[u][2] = ct[3]; W[u][3] = ct[4]; xx[u] = ct[5];
-#else
                 const double2 t0 = lds2(txs + (tb + u) * 6), t1 = lds2(txs + (tb + u) * 6 + 2), t2 = lds2(txs + (tb + u) * 6 + 4);
                 W[u][0] = t0.y; W[u][1] = t1.x; W[u][2] = t1.y; W[u][3] = t2.x; xx[u] = t2.y;
-#endif
             }
 #pragma unroll
             for (int fld = 0; fld < P::NFLD; fld++) {

@@ -53,6 +53,7 @@ struct StepArgs {
     double *fkeep_g, *fkeep_h;              // [n_keep_slabs][nif][L][32] reconstructed face values (face-storage slabs) or null
     double *ccoef;                          // [nc][12] half-step equilibrium records of the cells (k_cell_coef)
     double limiter_k;                       // > 0: Venkatakrishnan-limited least-squares gradient (generic kernels only)
+    int gam_late;                           // 1: one copy of the lagged boundary gradient; recompute slabs write it in phase 2
     unsigned long long pol_ef, pol_el;      // L2 cache policies (createpolicy evict_first / evict_last), made once at create
 };
 

@@ -27,7 +27,7 @@
 #define PEN_CU 2         // points advanced together
 #define PEN_NE 6
 #ifndef PEN_CTXS
-#define PEN_CTXS 1       // per-point row constants of the stencil loop from the constant bank (c_txs) instead of shared memory
+#define PEN_CTXS 1       // per-point row constants of the stencil loop from the constant bank (PenArgs::tx6) instead of shared memory
 #endif
 #ifndef PEN_PREPASS
 #define PEN_PREPASS 0    // fused half step as passes of their own (block of the own line, halo chunks) instead of inside the stencil loop
@@ -39,11 +39,15 @@
 //   item0: traversal item of (step 0, line 0); (step k, line l) is item0 + 4 k + l (cmeta / upwind codes)
 struct PenItem { int cells, halo, item0, nsteps; };
 
+#define PEN_TX6 ((32 + HOT_CI_MAX) * 6)
 struct PenArgs {
     const PenItem* items;
     int nitems;
     const int* cells;
     const int* halo;
+    // per-point constants of a row {-dt/2 x, w, w x, w x^2, w x^3, x} (pencils run on unchunked rows: at most 32 points):
+    // kernel parameters live in the constant bank, so the stencil loop reads them without a shared-memory instruction
+    double tx6[PEN_TX6];
 };
 
 // shared-memory plan (bytes), L = points per row
@@ -347,7 +351,7 @@ k_pencil_phase1(StepArgs a, PenArgs P) {
                 const double* const cz_ = wz + c0 * 32;
                 const double* const ctx = txs + (cb + c0) * 6;
 #if PEN_CTXS
-                const double* const cct = c_txs + (cb + c0) * 6;  // uniform except in the short-row tail slab (two chunk bases per warp)
+                const double* const cct = P.tx6 + (cb + c0) * 6;  // uniform except in the short-row tail slab (two chunk bases per warp)
 #endif
                 const double* const cxt = xtab + (cb + c0 - tmin) * 2;
                 double* const kxc[2] = {kx[0] + c0 * 32, kx[1] + c0 * 32};

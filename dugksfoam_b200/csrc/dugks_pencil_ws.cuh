@@ -338,7 +338,7 @@ k_pencil_ws(StepArgs a, PenArgs P) {
                     mbar_wait(full + st, (q / PWS_STAGES) & 1u);
                     const double* sg = ring + st * (2 * PWS_CH * 32) + lane;
                     const int i0 = ch * PWS_CH;
-                    const double* const cct = c_txs + (cb + i0) * 6;
+                    const double* const cct = P.tx6 + (cb + i0) * 6;
                     double v[PWS_CH], g0[PWS_CH], g1[PWS_CH], g2[PWS_CH], base[PWS_CH], W[PWS_CH][4];
 #pragma unroll
                     for (int u = 0; u < PWS_CH; u++) {

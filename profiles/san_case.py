@@ -12,9 +12,12 @@ runs = [("cavity3d_16_gh8 pencils fused", cs.cavity3d_case(16, 8, perturb=0.01),
         ("cavity3d_13 (odd interior: leftover lines)", cs.cavity3d_case(13, 8, perturb=0.01), {}),
         ("cavity2d_24_gh28 axis-only launch with h", cs.cavity2d_case(24, 28, perturb=0.01), {}),
         ("cavity2d_10_nc37 chunked rows", cs.cavity2d_case(10, 37, quad="NC", perturb=0.01), {}),
-        ("tri_8_gh8 general path", cs.tri_cavity_case(8, 8, perturb=0.01), {})]
+        ("tri_8_gh8 general path", cs.tri_cavity_case(8, 8, perturb=0.01), {}),
+        ("cavity3d_16_gh8 warp-specialised pencils (producer / consumer warps, mbarrier ring)", cs.cavity3d_case(16, 8, perturb=0.01), {"DUGKS_PENCIL_WS": "1"}),
+        ("cavity3d_12_gh8 recompute path (lagged boundary gradient written in place in phase 2)", cs.cavity3d_case(12, 8, perturb=0.01), {"DUGKS_KEEP_SLABS": "0"}),
+        ("ratchet_20x8_gh8 saw-tooth channel", cs.ratchet_channel_case(20, 8, 8, teeth=2, perturb=0.01), {})]
 for name, case, env in runs:
-    for k in ("DUGKS_PENCIL", "DUGKS_KEEP_SLABS"):
+    for k in ("DUGKS_PENCIL", "DUGKS_KEEP_SLABS", "DUGKS_PENCIL_WS"):
         os.environ.pop(k, None)
     os.environ.update(env)
     dv = capi.fvDVM(case)
