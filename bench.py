@@ -281,7 +281,7 @@ def main():
     # device time by timing class of the library (dugks_kernel_timing): 0 = reconstruction / out-flux kernels
     # (k_pencil_phase1, k_hot_outgoing), 1 = relax + update kernels (k_hot_relax_update, k_hot_update), 2 = half step
     tcls = {}
-    for which in (0, 1, 2):
+    for which in (0, 1, 2, 3):
         ms, n = dv.kernel_timing(-1, which)
         tcls[which] = (ms / K, n / K)
     dv.kernel_timing(0)
@@ -388,6 +388,8 @@ def main():
         "e2e": {"value": e2e_gups, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s / K * 1e3},
         "gpu_launches": launches,
+        "allreduce": {"ms_per_step": tcls[3][0], "calls_per_step": tcls[3][1],
+                      "note": "rank 0, CUDA events around the collectives of a step (waiting for the slowest rank included)"} if world > 1 else None,
         "checksum": checksum, "checksum_rel_diff": ck_diff,
         "checksum_reference": "profiles/bench_checksums.json (one-GPU run)" if ref_ck is not None else None,
         "clocks": clocks,

@@ -240,6 +240,7 @@ static int check_launch(dugks_handle* h, const char* name) {
 
 static int do_allreduce(dugks_handle* h, double* buf, size_t n) {
     if (h->nranks <= 1) return 0;
+    Timed t(h, 3);   // dugks_kernel_timing class 3: the collectives (incl. waiting for the slowest rank)
     if (h->reduce) {
         int rc = h->reduce(h->reduce_user, buf, n, (void*)h->stream);
         if (rc) return fail(h, DUGKS_ERR_COMM, "user allreduce callback returned %d", rc);

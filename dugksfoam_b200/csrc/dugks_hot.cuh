@@ -281,13 +281,17 @@ __device__ __forceinline__ void hot_stage_one_ef(uint32_t sdst, const double* ba
 #else
 #define RLX_HINT true
 #endif
+#ifndef RLX_L2_AHEAD
+#define RLX_L2_AHEAD 0   // 1: also pull the chunk after the one being staged into L2 (prefetch.global.L2)
+#endif
 template <int CI>
-__device__ __forceinline__ void hot_stage_at(uint32_t sdst, unsigned long long p, unsigned long long pol) {
+__device__ __forceinline__ void hot_stage_at(uint32_t sdst, unsigned long long p, unsigned long long pol, bool ahead = false) {
 #pragma unroll
     for (int part = 0; part < CI * 256 / 512; part++) {
         if (RLX_HINT) cp_async16_ef(sdst + part * 512, reinterpret_cast<const char*>(p) + part * 512, pol);
         else cp_async16(sdst + part * 512, reinterpret_cast<const char*>(p) + part * 512);
     }
+    if (RLX_L2_AHEAD && ahead) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + CI * 256));
 }
 // L2 hints of the relax+update kernel come from the kernel arguments (uniform registers; a policy made with
 // createpolicy inside the kernel lives in a vector register and costs two R2UR per LDGSTS)
@@ -1423,6 +1427,7 @@ k_hot_relax_update(StepArgs a) {
         for (int j = 0; j < NE; j++) offf[j] = (uint32_t)__shfl_sync(0xffffffffu, cur.face, j) * (uint32_t)(blk / 2) + (uint32_t)lane;
         auto stage_interior = [&](int ch, double* st) {
             const uint32_t sdst = smem_u32(st) + (uint32_t)lane * 16u, coff = (uint32_t)ch * (CI * 256u);
+            const bool ahead = ch + 1 < nchunk;
 #pragma unroll
             for (int fld = 0; fld < P::NFLD; fld++) {
                 // array base + chunk offset once per chunk and array, kept opaque: a stream then costs one 64-bit
@@ -1431,15 +1436,15 @@ k_hot_relax_update(StepArgs a) {
                 unsigned long long bf = (unsigned long long)(fld ? fk_h : fk_g) + coff;
                 asm volatile("" : "+l"(bc));
                 asm volatile("" : "+l"(bf));
-                hot_stage_at<CI>(sdst + (fld * NSLOT + 0) * (CI * 256), bc + (unsigned long long)offc * 16u, RLX_POL(a.pol_ef));
+                hot_stage_at<CI>(sdst + (fld * NSLOT + 0) * (CI * 256), bc + (unsigned long long)offc * 16u, RLX_POL(a.pol_ef), ahead);
                 if (WMODE == 0) {
                     unsigned long long bb = (unsigned long long)(fld ? hbs : gbs) + coff;
                     asm volatile("" : "+l"(bb));
-                    hot_stage_at<CI>(sdst + (fld * NSLOT + 1) * (CI * 256), bb + (unsigned long long)offc * 16u, RLX_POL(a.pol_ef));
+                    hot_stage_at<CI>(sdst + (fld * NSLOT + 1) * (CI * 256), bb + (unsigned long long)offc * 16u, RLX_POL(a.pol_ef), ahead);
                 }
 #pragma unroll
                 for (int j = 0; j < NE; j++)   // every face block is read by two cells: keep it in L2 for the second one
-                    hot_stage_at<CI>(sdst + (fld * NSLOT + NPRE + j) * (CI * 256), bf + (unsigned long long)offf[j] * 16u, RLX_POL(a.pol_el));
+                    hot_stage_at<CI>(sdst + (fld * NSLOT + NPRE + j) * (CI * 256), bf + (unsigned long long)offf[j] * 16u, RLX_POL(a.pol_el), ahead);
             }
         };
         // outward area vectors (sign folded in) and the face equilibria of the internal faces

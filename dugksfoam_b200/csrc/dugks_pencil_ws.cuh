@@ -27,7 +27,7 @@ struct PwsPlan {
     // per line: ring [STAGES][2 (y, z)][CH][32], geometry [2][7 * 6], coefficient records [2][3][FCOEF_N],
     // tables [3][tw][2], reduction scratch [8][NM_G], mbarriers FULL[STAGES] EMPTY[STAGES]
     static __host__ __device__ size_t line_bytes(int tw) {
-        return ((size_t)(PWS_STAGES * 2 * PWS_CH * 32 + 2 * (1 + PEN_NE) * 6 + 2 * 3 * FCOEF_N + 3 * tw * 2 + 8 * NM_G + 2 * PWS_STAGES) * 8 + 127) / 128 * 128;
+        return ((size_t)(PWS_STAGES * 2 * PWS_CH * 32 + 2 * (1 + PEN_NE) * 6 + 2 * 3 * FCOEF_N + 3 * tw * 2 + 8 * NM_G + 2 * PWS_STAGES + 1) * 8 + 127) / 128 * 128;
     }
     static __host__ size_t total(int L, int ntab, int tw) { return txs_bytes(ntab) + win_bytes(L) + PEN_WARPS * line_bytes(tw); }
 };
@@ -40,6 +40,13 @@ __device__ __forceinline__ void pws_setmaxnreg_inc() { asm volatile("setmaxnreg.
 template <int N>
 __device__ __forceinline__ void pws_setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 __device__ __forceinline__ void pws_bar_consumers() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// all eight warps, from either role's code path: an mbarrier all 256 threads arrive at (bar.sync reached from two
+// program locations is what compute-sanitizer's synccheck calls a divergent barrier)
+__device__ __forceinline__ void pws_bar_all(uint64_t* bar, uint32_t& phase) {
+    mbar_arrive(bar);
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+}
 
 // Sum of 13 values per lane over the warp through 8 x 13 doubles of scratch; lanes 0..12 return the totals.
 __device__ __forceinline__ double pws_reduce13(double (&v)[NM_G], double* scratch, int lane) {
@@ -87,7 +94,12 @@ k_pencil_ws(StepArgs a, PenArgs P) {
     double* scratch = xtab + 3 * TW * 2;                     // [8][NM_G]
     uint64_t* full = reinterpret_cast<uint64_t*>(scratch + 8 * NM_G);   // [STAGES]
     uint64_t* empty = full + PWS_STAGES;                     // [STAGES]
+    // the CTA-wide barrier lives in line 0's block
+    uint64_t* cta_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<double*>(dyn + PwsPlan::txs_bytes(dv.ntab) + PwsPlan::win_bytes(L)) +
+                                                    PWS_STAGES * 2 * PWS_CH * 32 + 2 * (1 + PEN_NE) * 6 + 2 * 3 * FCOEF_N + 3 * TW * 2 + 8 * NM_G) + 2 * PWS_STAGES;
+    uint32_t cta_phase = 0;
     if (producer && lane == 0) {
+        if (wl == 0) mbar_init(cta_bar, 2 * PEN_WARPS * 32);
 #pragma unroll
         for (int s = 0; s < PWS_STAGES; s++) { mbar_init(full + s, 32); mbar_init(empty + s, 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -155,7 +167,7 @@ k_pencil_ws(StepArgs a, PenArgs P) {
             const int* ctab = P.cells + I.cells + wl;            // own line: ctab[(p + 1) * 4], p = -1 .. ns
             const int* htab = P.halo + I.halo + wl * 2;          // htab[k * 8 + {0, 1}]
             const int ns = I.nsteps;
-            __syncthreads();                                      // (A) the previous item is finished by all eight warps
+            pws_bar_all(cta_bar, cta_phase);                                        // (A) the previous item is finished by all eight warps
             // ---- prologue: positions -1, 0, 1 of the own line; -1 and 0 enter converted
             const int cm1 = ctab[0], c0 = ctab[4], c1 = ctab[8];
             load_rows(cm1, wslot(-1, wl));
@@ -185,7 +197,7 @@ k_pencil_ws(StepArgs a, PenArgs P) {
             load_mrec(hy_c, mrec + FCOEF_N, 6);
             load_mrec(hz_c, mrec + 2 * FCOEF_N, 12);
             cp_async_commit();
-            __syncthreads();                                      // (B) slots -1 and 0 of every line are converted
+            pws_bar_all(cta_bar, cta_phase);                                        // (B) slots -1 and 0 of every line are converted
             int own2 = (2 <= ns) ? ldg_early(ctab + 3 * 4) : -1;  // position k + 2
             int own_tail = -1;                                    // position k + 1 when its last STAGES chunks are still to be fetched
             int hy_n = (1 < ns) ? ldg_early(htab + 8) : -1, hz_n = (1 < ns) ? ldg_early(htab + 9) : -1;
@@ -265,12 +277,12 @@ k_pencil_ws(StepArgs a, PenArgs P) {
         for (int it = blockIdx.x; it < P.nitems; it += gridDim.x) {
             const PenItem I = P.items[it];
             const int ns = I.nsteps;
-            __syncthreads();                                      // (A)
+            pws_bar_all(cta_bar, cta_phase);                                        // (A)
             HotMeta cur{}, nxt{};
             hot_meta_issue(a, I.item0 + wl, lane, cur);
             hot_stage_geo(a.geo6 + (size_t)(cur.e0 + cur.c) * 6, PEN_NE, geo, lane);
             cp_async_commit();
-            __syncthreads();                                      // (B)
+            pws_bar_all(cta_bar, cta_phase);                                        // (B)
             for (int k = 0; k < ns; k++) {
                 const int gsel = k & 1;
                 const double* gb_ = geo + gsel * ((1 + PEN_NE) * 6);

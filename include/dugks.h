@@ -357,7 +357,9 @@ void* dugks_stream(dugks_handle_t* h);
 /* Accumulated device time (ms, CUDA events) of the dominant kernel family
  * since the last reset, and its launch count; enable before the timed region.
  * which: 0 = cell_outgoing (gradient + reconstruction + face moments / flux),
- *        1 = cell_update, 2 = cell_halfstep. */
+ *        1 = cell_update, 2 = cell_halfstep, 3 = the all-reduces of the moment
+ *        slots (fvDVM.C:363,487-489,519,626-628,725), waiting for the slowest
+ *        rank included. */
 int dugks_kernel_timing(dugks_handle_t* h, int enable, int which,
                         double* total_ms, uint64_t* launches);
 
