@@ -309,7 +309,9 @@ def main():
         dv.set_boundary_macros(None, pin["U"].numpy(), pin["T"].numpy())
         dv.evolution(dt)
         if rank == 0:
-            cm = dv.cell_macros()      # the macro fields go to the host where they are written (dugksFoam.C:63,109: rank 0)
+            # the macro fields go to the host where they are written (dugksFoam.C:63,109: rank 0), into page-locked
+            # field storage (dugks_host_register, what the OpenFOAM adapter does with its volFields)
+            cm = dv.cell_macros(pinned=True)
         co = dv.getCoNum(dt)
     dv.sync()
     barrier()

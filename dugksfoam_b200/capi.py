@@ -33,7 +33,8 @@ EXPORTS = ["dugks_abi_version", "dugks_nccl_unique_id", "dugks_create", "dugks_d
            "dugks_get_df", "dugks_get_state", "dugks_set_state", "dugks_local_dvs", "dugks_sizes",
            "dugks_get_stats", "dugks_stream", "dugks_kernel_timing", "dugks_partition",
            "dugks_get_boundary_df", "dugks_row_layout", "dugks_convergence", "dugks_cell_order",
-           "dugks_checkpoint_size", "dugks_checkpoint_save", "dugks_checkpoint_load", "dugks_pencil_plan"]
+           "dugks_checkpoint_size", "dugks_checkpoint_save", "dugks_checkpoint_load", "dugks_pencil_plan",
+           "dugks_host_register", "dugks_host_unregister"]
 
 
 class DugksError(RuntimeError):
@@ -76,6 +77,8 @@ def load_library():
     L.dugks_set_boundary_macros.argtypes = [C.c_void_p] + [c_double_p] * 3
     L.dugks_get_cell_macros.argtypes = [C.c_void_p] + [c_double_p] * 5
     L.dugks_get_face_macros.argtypes = [C.c_void_p] + [c_double_p] * 5
+    L.dugks_host_register.argtypes = [C.c_void_p, C.c_size_t]
+    L.dugks_host_unregister.argtypes = [C.c_void_p]
     L.dugks_get_boundary_macros.argtypes = [C.c_void_p] + [c_double_p] * 3
     L.dugks_get_wall_diag.argtypes = [C.c_void_p] + [c_double_p] * 2
     L.dugks_courant.argtypes = [C.c_void_p, C.c_double, c_double_p, c_double_p]
@@ -218,9 +221,14 @@ class fvDVM:
         self.L.dugks_sizes(self.h, *(C.cast(C.byref(n, 4 * i), c_int32_p) for i in range(4)))
         self._nXi, self.nXiLocal, self.nCells, self.nFaces = (int(v) for v in n)
         self.nBoundaryFaces = case.geom.nBoundaryFaces
+        self._pinned_cm = None
 
     # -- lifetime -----------------------------------------------------------
     def close(self):
+        if getattr(self, "_pinned_cm", None):
+            for a in self._pinned_cm.values():
+                self.L.dugks_host_unregister(a.ctypes.data_as(C.c_void_p))
+            self._pinned_cm = None
         if getattr(self, "h", None):
             self.L.dugks_destroy(self.h)
             self.h = None
@@ -268,9 +276,21 @@ class fvDVM:
         self._chk(fn(self.h, dptr(rho), dptr(U), dptr(T), dptr(q), dptr(tau)), fn.__name__)
         return dict(rho=rho, U=U, T=T, q=q, tau=tau)
 
-    def cell_macros(self):
-        """rhoVol(), Uvol(), Tvol(), qVol(), tauVol()."""
-        return self._macros(self.L.dugks_get_cell_macros, self.nCells)
+    def cell_macros(self, pinned: bool = False):
+        """rhoVol(), Uvol(), Tvol(), qVol(), tauVol().  pinned: fill (and return) one set of page-locked arrays owned by
+        this object - what a solver does with its field storage (dugks_host_register); valid until the next call."""
+        if not pinned:
+            return self._macros(self.L.dugks_get_cell_macros, self.nCells)
+        if self._pinned_cm is None:
+            n = self.nCells
+            out = dict(rho=np.zeros(n), U=np.zeros((n, 3)), T=np.zeros(n), q=np.zeros((n, 3)), tau=np.zeros(n))
+            for a in out.values():
+                self._chk(self.L.dugks_host_register(a.ctypes.data_as(C.c_void_p), a.nbytes), "dugks_host_register")
+            self._pinned_cm = out
+        o = self._pinned_cm
+        self._chk(self.L.dugks_get_cell_macros(self.h, dptr(o["rho"]), dptr(o["U"]), dptr(o["T"]), dptr(o["q"]), dptr(o["tau"])),
+                  "dugks_get_cell_macros")
+        return o
 
     def face_macros(self):
         """rhoSurf(), Usurf(), Tsurf(), qSurf(), tauSurf() on internal + non-empty boundary faces."""

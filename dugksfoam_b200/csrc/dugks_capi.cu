@@ -115,6 +115,8 @@ struct dugks_handle {
     // host side of the accessors: pinned staging buffer, last boundary macros the caller set
     double* pin = nullptr;
     size_t pin_count = 0;
+    double* d_soa = nullptr;       // accessor staging on the device: the macro fields in the caller's (per-field) layout
+    size_t soa_count = 0;
     std::vector<double> last_rho_b, last_U_b, last_T_b;
     // stats
     uint64_t launches = 0, steps = 0;
@@ -1331,6 +1333,7 @@ extern "C" void dugks_destroy(dugks_handle_t* h) {
     if (h->nccl_comm && g_nccl.destroy) g_nccl.destroy(h->nccl_comm);
     for (auto& b : h->bufs) cudaFree(b.p);
     if (h->pin) cudaFreeHost(h->pin);
+    if (h->d_soa) cudaFree(h->d_soa);
     for (auto& e : h->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto& e : h->pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -2072,21 +2075,81 @@ static void unpack_macros(const double* m, size_t n, double* rho, double* U, dou
     }
 }
 
+// True if p points into page-locked host memory (cudaHostAlloc / cudaHostRegister, e.g. dugks_host_register).
+static bool host_pinned(const void* p) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+__global__ void k_unpack_macros(const double* m, int n, double* soa) {
+    // soa = rho[n] | U[n][3] | T[n] | q[n][3] | tau[n]
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const double* p = m + (size_t)k * MAC_N;
+    const size_t N = (size_t)n;
+    soa[k] = p[0];
+    soa[N + 3 * (size_t)k] = p[1]; soa[N + 3 * (size_t)k + 1] = p[2]; soa[N + 3 * (size_t)k + 2] = p[3];
+    soa[4 * N + k] = p[4];
+    soa[5 * N + 3 * (size_t)k] = p[6]; soa[5 * N + 3 * (size_t)k + 1] = p[7]; soa[5 * N + 3 * (size_t)k + 2] = p[8];
+    soa[8 * N + k] = p[5];
+}
+
+// Macro fields into the caller's arrays.  Page-locked arrays (dugks_host_register) are filled by asynchronous copies
+// straight from the device, laid out per field there; pageable ones through the handle's pinned staging buffer and a
+// host loop (4.9 ms instead of 0.5 for the 262,144 cells of the 64^3 case).
+static int get_macros(dugks_handle* h, const double* dev, size_t n, double* rho, double* U, double* T, double* q, double* tau) {
+    const bool all_pinned = (rho || U || T || q || tau) && (!rho || host_pinned(rho)) && (!U || host_pinned(U)) && (!T || host_pinned(T)) &&
+                            (!q || host_pinned(q)) && (!tau || host_pinned(tau));
+    if (!all_pinned) {
+        const double* m = nullptr;
+        int rc = fetch_pinned(h, dev, n * MAC_N, &m);
+        if (rc) return rc;
+        unpack_macros(m, n, rho, U, T, q, tau);
+        return 0;
+    }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (n * MAC_N > h->soa_count) {
+        if (h->d_soa) cudaFree(h->d_soa);
+        h->d_soa = nullptr; h->soa_count = 0;
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_soa, n * MAC_N * sizeof(double)));
+        h->soa_count = n * MAC_N;
+    }
+    k_unpack_macros<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(dev, (int)n, h->d_soa);
+    int rc = check_launch(h, "k_unpack_macros");
+    if (rc) return rc;
+    const double* s = h->d_soa;
+    if (rho) CUDA_TRY(h, cudaMemcpyAsync(rho, s, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (U) CUDA_TRY(h, cudaMemcpyAsync(U, s + n, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (T) CUDA_TRY(h, cudaMemcpyAsync(T, s + 4 * n, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (q) CUDA_TRY(h, cudaMemcpyAsync(q, s + 5 * n, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (tau) CUDA_TRY(h, cudaMemcpyAsync(tau, s + 8 * n, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 extern "C" int dugks_get_cell_macros(dugks_handle_t* h, double* rho, double* U, double* T, double* q, double* tau) {
     if (!h) return DUGKS_ERR_INVALID;
-    const double* m = nullptr;
-    int rc = fetch_pinned(h, h->A.cmac, (size_t)h->nc * MAC_N, &m);
-    if (rc) return rc;
-    unpack_macros(m, h->nc, rho, U, T, q, tau);
-    return 0;
+    return get_macros(h, h->A.cmac, (size_t)h->nc, rho, U, T, q, tau);
 }
 
 extern "C" int dugks_get_face_macros(dugks_handle_t* h, double* rho, double* U, double* T, double* q, double* tau) {
     if (!h) return DUGKS_ERR_INVALID;
-    const double* m = nullptr;
-    int rc = fetch_pinned(h, h->A.fmac, (size_t)h->nf * MAC_N, &m);
-    if (rc) return rc;
-    unpack_macros(m, h->nf, rho, U, T, q, tau);
+    return get_macros(h, h->A.fmac, (size_t)h->nf, rho, U, T, q, tau);
+}
+
+// Page-lock / release caller-owned host arrays (OpenFOAM field storage) so that the accessors copy straight into them.
+extern "C" int dugks_host_register(void* p, size_t bytes) {
+    if (!p || !bytes) return DUGKS_ERR_INVALID;
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterDefault);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { (void)cudaGetLastError(); return 0; }
+    if (e != cudaSuccess) return fail(nullptr, DUGKS_ERR_CUDA, "cudaHostRegister of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    return 0;
+}
+extern "C" int dugks_host_unregister(void* p) {
+    if (!p) return DUGKS_ERR_INVALID;
+    cudaError_t e = cudaHostUnregister(p);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(nullptr, DUGKS_ERR_CUDA, "cudaHostUnregister failed: %s", cudaGetErrorString(e)); }
     return 0;
 }
 

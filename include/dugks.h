@@ -233,6 +233,14 @@ int dugks_set_boundary_macros(dugks_handle_t* h, const double* rho_b,
 
 /* ---- accessors (synchronise, D2H into caller storage; NULL = skip) ------ */
 
+/* Page-lock caller-owned host arrays (the storage of the OpenFOAM fields the
+ * accessors below fill, Field<T>::data(), fvDVM.C:427-430): the macro accessors
+ * then copy asynchronously from the device straight into them instead of going
+ * through a staging buffer and a host loop.  Optional; register once, release
+ * before the array is freed.  Already registered memory is not an error. */
+int dugks_host_register(void* p, size_t bytes);
+int dugks_host_unregister(void* p);
+
 /* rhoVol(), Uvol(), Tvol(), qVol(), tauVol()  (fvDVM.H:309-322). */
 int dugks_get_cell_macros(dugks_handle_t* h, double* rho, double* U, double* T,
                           double* q, double* tau);

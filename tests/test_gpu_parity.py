@@ -112,6 +112,10 @@ _PATHS = [
     ("pencil_off", {"DUGKS_PENCIL": "0"}),              # phase 1 without CTA pencils (warp-per-cell kernels everywhere)
     ("pencil_unfused", {"DUGKS_PENCIL": "1"}),          # CTA pencils over gBarP written by the half-step kernel
     ("pencil_keep_one", {"DUGKS_KEEP_SLABS": "1"}),     # fused pencils on the face-storage slab, unfused on the others
+    ("pencil_ws", {"DUGKS_PENCIL_WS": "1"}),            # warp-specialised fused pencils (producer + consumer warp per line, mbarrier ring)
+    ("pencil_ws_keep_one", {"DUGKS_PENCIL_WS": "1", "DUGKS_KEEP_SLABS": "1"}),
+    ("gam_pingpong", {"DUGKS_GAM_PINGPONG": "1"}),      # two copies of the lagged boundary gradient (the default updates one in place)
+    ("gam_pingpong_keep_none", {"DUGKS_GAM_PINGPONG": "1", "DUGKS_KEEP_SLABS": "0"}),
     ("gen1_tma", {"DUGKS_NO_HOT": "1"}),                # first-generation bulk-copy kernels
     ("gen1_ldg", {"DUGKS_NO_HOT": "1", "DUGKS_NO_TMA": "1"}),
     ("generic", {"DUGKS_NO_HOT": "1", "DUGKS_FORCE_GENERIC": "1"}),   # cells with many faces
@@ -122,7 +126,7 @@ _PATHS = [
 def test_every_kernel_path(oracle_lib, monkeypatch, path, env):
     """Every device code path that can carry the step gives the oracle's answer."""
     for k in ("DUGKS_KEEP_SLABS", "DUGKS_NO_HOT", "DUGKS_NO_TMA", "DUGKS_FORCE_GENERIC", "DUGKS_NO_AXIS",
-              "DUGKS_NO_SPLIT_AXIS", "DUGKS_NO_WMODE", "DUGKS_ORDER", "DUGKS_PENCIL"):
+              "DUGKS_NO_SPLIT_AXIS", "DUGKS_NO_WMODE", "DUGKS_ORDER", "DUGKS_PENCIL", "DUGKS_PENCIL_WS", "DUGKS_GAM_PINGPONG"):
         monkeypatch.delenv(k, raising=False)
     for k, v in env.items():
         monkeypatch.setenv(k, v)
@@ -217,6 +221,27 @@ def test_set_get_state_roundtrip():
     assert np.array_equal(gd[dv.local_dvs()], g3[:, 3])
     st = dv.stats()
     assert st["kernel_launches"] > 0
+    dv.close()
+
+
+def test_page_locked_accessor_arrays():
+    """dugks_host_register: macro accessors that copy straight into page-locked caller arrays return the same bits as the
+    staged path (include/dugks.h, accessors)."""
+    case = cs.cavity3d_case(6, 8, perturb=0.01)
+    dv = capi.fvDVM(case)
+    dt = case.courant_dt(0.5)
+    for _ in range(2):
+        dv.evolution(dt)
+    a = dv.cell_macros()
+    b = dv.cell_macros(pinned=True)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    dv.evolution(dt)
+    a = dv.cell_macros()
+    b2 = dv.cell_macros(pinned=True)
+    assert b2["rho"] is b["rho"]                       # the same page-locked arrays, refilled
+    for k in a:
+        assert np.array_equal(a[k], b2[k]), k
     dv.close()
 
 
