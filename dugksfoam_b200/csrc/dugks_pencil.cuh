@@ -29,9 +29,6 @@
 #ifndef PEN_CTXS
 #define PEN_CTXS 1       // per-point row constants of the stencil loop from the constant bank (PenArgs::tx6) instead of shared memory
 #endif
-#ifndef PEN_PREPASS
-#define PEN_PREPASS 0    // fused half step as passes of their own (block of the own line, halo chunks) instead of inside the stencil loop
-#endif
 
 // One work item: `nsteps` consecutive x positions of a bundle.
 //   cells: offset into pen_cells of [(nsteps + 2)][4] cell ids, positions -1 .. nsteps of the four lines
@@ -254,19 +251,6 @@ k_pencil_phase1(StepArgs a, PenArgs P) {
                 build_table(mr + FCOEF_N, xtab + TW * 2, Ehy);
                 build_table(mr + 2 * FCOEF_N, xtab + 2 * TW * 2, Ehz);
                 __syncwarp();
-#if PEN_PREPASS
-                // own(k + 1) enters the window converted, in a pass of its own: Ln independent conversions hide the FP64
-                // latency that two points at a time inside the stencil loop cannot.  Its last chunk may still be in flight
-                // (newest commit group): that one is converted where the chunk loop has waited for it.
-                {
-                    double* blkp = wslot(k + 1, wl) + lane;
-                    const double* xt0 = xtab + (cb - tmin) * 2;
-                    const double* tx0 = txs + cb * 6 + 5;
-                    const int npre = (nchunk - 1) * PEN_CI;
-#pragma unroll 4
-                    for (int i = 0; i < npre; i++) blkp[i * 32] = convert(blkp[i * 32], xt0 + i * 2, tx0[i * 6], Exp);
-                }
-#endif
             }
             // ---- upwind sets (static codes), store pointers, accumulators: as hot_axis_item
             const unsigned ownmask = __ballot_sync(0xffffffffu, cur.own != 0);
@@ -356,23 +340,6 @@ k_pencil_phase1(StepArgs a, PenArgs P) {
                 const double* const cxt = xtab + (cb + c0 - tmin) * 2;
                 double* const kxc[2] = {kx[0] + c0 * 32, kx[1] + c0 * 32};
                 double* const kpc[2] = {kp[0] + c0 * 32, kp[1] + c0 * 32};
-#if PEN_PREPASS
-                if (FUSE) {
-                    // the two halo blocks of this chunk, converted in place (each lane owns its column of the stage)
-                    double* sgw = halo + (q & 1) * (2 * PEN_CI * 32) + lane;
-#pragma unroll
-                    for (int u = 0; u < PEN_CI; u++) {
-                        const double xq = ctx[u * 6 + 5];
-                        sgw[u * 32] = convert(sgw[u * 32], cxt + (TW + u) * 2, xq, Ehy);
-                        sgw[(PEN_CI + u) * 32] = convert(sgw[(PEN_CI + u) * 32], cxt + (2 * TW + u) * 2, xq, Ehz);
-                    }
-                    if (ch == nchunk - 1) {
-#pragma unroll
-                        for (int u = 0; u < PEN_CI; u++)
-                            if (c0 + u < Ln) cp[u * 32] = convert(cp[u * 32], cxt + u * 2, ctx[u * 6 + 5], Exp);
-                    }
-                }
-#endif
 #pragma unroll
                 for (int sub = 0; sub < PEN_CI / PEN_CU; sub++) {
                     if (sub >= nsub) break;                                        // warp-uniform (short last chunk)
@@ -395,16 +362,12 @@ k_pencil_phase1(StepArgs a, PenArgs P) {
                         double vxp = cp[(so + u) * 32];
                         const double vyi = cy_[(so + u) * 32], vzi = cz_[(so + u) * 32];
                         double vyh = sg[(so + u) * 32], vzh = sg[(PEN_CI + so + u) * 32];
-#if !PEN_PREPASS
                         if (FUSE) {
                             vxp = convert(vxp, cxt + (so + u) * 2, xq, Exp);
                             cp[(so + u) * 32] = vxp;                      // from now on the block holds gBarP
                             vyh = convert(vyh, cxt + (TW + so + u) * 2, xq, Ehy);
                             vzh = convert(vzh, cxt + (2 * TW + so + u) * 2, xq, Ehz);
                         }
-#else
-                        (void)xq;
-#endif
                         // gradient (stock leastSquaresGrad, zeroBoundaryGrad.C:90-99): one component per face
                         g0[u] = fma(Gxp, vxp, fma(Gxm, vxm, G0x * v[u]));
                         g1[u] = fma(Gyh, vyh, fma(Gyi, vyi, G0y * v[u]));
