@@ -77,7 +77,9 @@ k_pencil_ws(StepArgs a, PenArgs P) {
     extern __shared__ __align__(128) unsigned char dyn[];
     const DevDV& dv = a.dv;
     const int L = dv.L, nc = a.m.nc, blk = L * 32;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // the warp index as a broadcast: the compiler then knows that the role branch below is warp-uniform and does not wrap
+    // every shuffle / ballot / __syncwarp inside it in its divergent-collective sequence (WARPSYNC ... ENDCOLLECTIVE)
+    const int lane = threadIdx.x & 31, wid = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const bool producer = wid >= PEN_WARPS;
     const int wl = wid & (PEN_WARPS - 1);                   // line of the bundle: by + 2 bz
     const int by = wl & 1, bz = wl >> 1;
