@@ -314,6 +314,75 @@ def test_shipped_demo_cavity(oracle_lib):
     dv.close(); orc.close()
 
 
+def test_full_size_properties():
+    """BASELINE config 3 at its FULL size (64^3 cells x 28^3 velocities, 5.75e9 updates per step - the oracle would need
+    minutes per step) through properties that do not depend on the size:
+      * a gas at rest between walls at its own temperature stays where it is (every kernel path of the step: the half
+        step, the reconstruction, the wall rule and the update must cancel to round-off);
+      * the lid-driven cavity is mirror-symmetric about z = 1/2 (both signs of xi_z, owner and neighbour sides);
+      * its total mass changes only by the wall-flux imbalance of the scheme."""
+    import torch
+    if torch.cuda.get_device_properties(0).total_memory < 150e9:
+        pytest.skip("needs the 180 GB of a B200")
+    n, nDV = 64, 28
+    case = cs.cavity3d_case(n, nDV)
+    dt = case.courant_dt(0.8)
+    V = case.geom.V
+    cth = float(np.sqrt(2.0 * case.gas["R"] * cs.T0))
+    # ---- 1. equilibrium at rest
+    rest = cs.cavity3d_case(n, nDV)
+    rest.U_b[:] = 0.0
+    dv = capi.fvDVM(rest)
+    st = dv.stats()
+    assert st["pencil_mode"] == 2 and st["pencil_cells"] == (n - 2) ** 3 and st["keep_slabs"] >= 19
+    for _ in range(3):
+        dv.evolution(dt)
+    m = dv.cell_macros()
+    # the 28-point Gauss-Hermite sums carry the discrete Maxwellian's moments to a few 1e-13 (tests/test_oracle.py:
+    # test_uniform_equilibrium_is_steady holds the oracle to the same figures)
+    assert util.rel_err(m["rho"], rest.rho) < 1e-11 and util.rel_err(m["T"], rest.T) < 1e-11
+    assert np.abs(m["U"]).max() < 1e-8 * cth and np.abs(m["q"]).max() < 1e-7 * cs.RHO0 * cth ** 3
+    dv.close()
+    # ---- 2. and 3. the driven cavity
+    dv = capi.fvDVM(case)
+    for _ in range(3):
+        dv.evolution(dt)
+    m = dv.cell_macros()
+    rho = m["rho"].reshape(n, n, n)                   # [k (z)][j (y)][i (x)], polymesh.hex_block numbering
+    U = m["U"].reshape(n, n, n, 3)
+    assert util.rel_err(rho[::-1], rho) < 1e-12
+    assert np.abs(U[::-1, :, :, 0] - U[..., 0]).max() < 1e-11 * cth and np.abs(U[::-1, :, :, 2] + U[..., 2]).max() < 1e-11 * cth
+    assert np.abs(U[..., 0]).max() > 1e-3 * 50.0      # the lid does drive the gas
+    m0, m3 = float((case.rho * V).sum()), float((m["rho"] * V).sum())
+    assert abs(m3 - m0) <= 1e-6 * m0
+    assert np.isfinite(m["q"]).all() and np.isfinite(m["tau"]).all()
+    dv.close()
+
+
+@pytest.mark.parametrize("which", ["cfg2_cavity2d_256_nc101", "cfg4_ratchet_632x158_gh28"])
+def test_full_size_gas_at_rest(which):
+    """BASELINE configs 2 and 4 at their full sizes: a gas at rest between walls at its own temperature stays at rest
+    (chunked velocity rows with h stored; 199,712 triangular prisms on the general path)."""
+    if which.startswith("cfg2"):
+        case = cs.cavity2d_case(256, 101, quad="NC")
+    else:
+        case = cs.ratchet_channel_case(632, 158, 28, T_ratchet=cs.T0, T_top=cs.T0)
+    case.U_b[:] = 0.0
+    dv = capi.fvDVM(case)
+    dt = case.courant_dt(0.8)
+    for _ in range(3):
+        dv.evolution(dt)
+    m = dv.cell_macros()
+    cth = float(np.sqrt(2.0 * case.gas["R"] * cs.T0))
+    # Newton-Cotes on [-4 c, 4 c] integrates the Maxwellian to 1e-7 only (the tails), Gauss-Hermite to round-off:
+    # the discrete equilibrium is steady to that accuracy
+    tol = 1e-6 if which.startswith("cfg2") else 1e-10
+    assert util.rel_err(m["rho"], case.rho) < tol and util.rel_err(m["T"], case.T) < tol
+    assert np.abs(m["U"]).max() < tol * 1e2 * cth
+    assert np.isfinite(m["q"]).all()
+    dv.close()
+
+
 def _hypersonic_channel(nDV=29, nx=10, ny=6):
     """Free stream at Ma = 5 (argon, 273 K: a = 307.8 m/s) through far-field in / zeroGradient out, fixedValue-rho
     ("mixed") top, Maxwell wall bottom; Newton-Cotes grid wide enough for the shifted Maxwellian."""
