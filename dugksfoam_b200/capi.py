@@ -227,7 +227,7 @@ class fvDVM:
     def close(self):
         if getattr(self, "_pinned_cm", None):
             for a in self._pinned_cm.values():
-                self.L.dugks_host_unregister(a.ctypes.data_as(C.c_void_p))
+                self.L.dugks_host_unregister(a.ctypes.data_as(C.c_void_p))   # a no-op error for arrays that never got locked
             self._pinned_cm = None
         if getattr(self, "h", None):
             self.L.dugks_destroy(self.h)
@@ -284,8 +284,11 @@ class fvDVM:
         if self._pinned_cm is None:
             n = self.nCells
             out = dict(rho=np.zeros(n), U=np.zeros((n, 3)), T=np.zeros(n), q=np.zeros((n, 3)), tau=np.zeros(n))
+            self._pinned_ok = True
             for a in out.values():
-                self._chk(self.L.dugks_host_register(a.ctypes.data_as(C.c_void_p), a.nbytes), "dugks_host_register")
+                # page-locking is an optimisation: where the host refuses it (locked-memory limit) the accessor stages
+                if self.L.dugks_host_register(a.ctypes.data_as(C.c_void_p), a.nbytes):
+                    self._pinned_ok = False
             self._pinned_cm = out
         o = self._pinned_cm
         self._chk(self.L.dugks_get_cell_macros(self.h, dptr(o["rho"]), dptr(o["U"]), dptr(o["T"]), dptr(o["q"]), dptr(o["tau"])),
