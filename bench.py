@@ -37,6 +37,7 @@ WORKLOADS = {
     "tri2d_316_gh28": ("tri2d", dict(n=316, nDV=28)),                # ~200k distorted triangles in a square cavity
     # BASELINE configs[3]: micro-channel with a ratchet (saw-tooth) wall, 199,712 triangular prisms, Maxwell walls at three temperatures
     "ratchet_632x158_gh28": ("ratchet", dict(nx=632, ny=158, nDV=28)),
+    "poly2d_447_gh28": ("poly2d", dict(n=447, nDV=28)),              # the same size on polygonal (Voronoi) cells: 199,809 cells with 4 to 8 sides
     # BASELINE configs[4]: Ma = 5 past a cylinder, O-type mesh 1000 x 500 quadrilaterals, 81 x 81 Newton-Cotes velocities
     "cylinder_1000x500_nc81": ("cylinder", dict(ntheta=1000, nr=500, nDV=81)),
     "cylinder_200x100_nc81": ("cylinder", dict(ntheta=200, nr=100, nDV=81)),
@@ -57,6 +58,8 @@ def build_case(kind, kw):
         return cs.cylinder_case(kw["ntheta"], kw["nr"], kw["nDV"])
     if kind == "ratchet":
         return cs.ratchet_channel_case(kw["nx"], kw["ny"], kw["nDV"])
+    if kind == "poly2d":
+        return cs.poly_cavity_case(kw["n"], kw["nDV"])
     return cs.cavity2d_case(kw["n"], kw["nDV"], quad=kw.get("quad", "GH"))
 
 
@@ -185,7 +188,7 @@ def main():
                    f"{kw['nDV']}^2 GH velocities, Kn=0.075 argon, Maxwell walls at three temperatures")
     else:
         wl_name = f"{'3-D' if kind == 'cavity3d' else '2-D'} cavity {kw['n']}^{3 if kind == 'cavity3d' else 2} " \
-                  f"{'triangular-prism (unstructured)' if kind == 'tri2d' else 'hex'} cells x " \
+                   f"{'triangular-prism (unstructured)' if kind == 'tri2d' else ('polygonal (Voronoi, unstructured)' if kind == 'poly2d' else 'hex')} cells x " \
                   f"{kw['nDV']}^{3 if kind == 'cavity3d' else 2} {kw.get('quad', 'GH')} velocities, Kn=0.075 argon, Maxwell walls"
 
     if args.impl == "reference":

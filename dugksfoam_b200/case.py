@@ -14,7 +14,8 @@ import numpy as np
 
 from . import dvset as _dvset
 from . import foam
-from .polymesh import Geometry, PolyMesh, compute_geometry, hex_block, ogrid_cylinder, ratchet_profile, tri_prism_2d
+from .polymesh import (Geometry, PolyMesh, compute_geometry, hex_block, ogrid_cylinder, ratchet_profile, tri_prism_2d,
+                       voronoi_prism_2d)
 
 # dugks_patch_kind (include/dugks.h)
 PATCH_ZERO_GRADIENT, PATCH_MIXED, PATCH_MAXWELL_WALL, PATCH_FAR_FIELD = 0, 1, 2, 3
@@ -229,6 +230,14 @@ def tri_cavity_case(n: int, nDV: int = 28, *, distort: float = 0.15, wall_T=None
     Xis, w = gh_set(nDV)
     return _uniform_case(mesh, Xis, w, {}, wall_T=wall_T or {"movingWall": 300.0}, name=f"tri_{n}x{n}_GH{nDV}",
                          perturb=perturb)
+
+
+def poly_cavity_case(n: int, nDV: int = 28, *, jitter: float = 0.25, wall_T=None, perturb: float = 0.0) -> Case:
+    """2-D cavity on an unstructured POLYGONAL mesh (Voronoi cells with 4 to 8 sides, the "poly" of BASELINE config 4),
+    Maxwell walls at different temperatures, lid on top."""
+    mesh = voronoi_prism_2d(n, n, (1.0, 1.0, 0.1), jitter=jitter)
+    Xis, w = gh_set(nDV)
+    return _uniform_case(mesh, Xis, w, {}, wall_T=wall_T or {"movingWall": 300.0}, name=f"poly_{n}x{n}_GH{nDV}", perturb=perturb)
 
 
 def ratchet_channel_case(nx: int, ny: int, nDV: int = 28, *, teeth: int = 4, tooth_height: float = 0.3, aspect: float = 4.0,

@@ -265,6 +265,9 @@ static int do_allreduce(dugks_handle* h, double* buf, size_t n) {
 #define DUGKS_CI_RLX 2
 #endif
 constexpr int CI_OUT1 = DUGKS_CI_OUT1, CI_OUT2 = 2, CI_RLX = DUGKS_CI_RLX;
+// cells with up to 8 faces (polygonal meshes): 9 staged streams per field; with 4 points per chunk one CTA fills an SM's
+// shared memory (154 KB with h), with 2 points two fit
+#define CI_OUT1_NE(NE_) ((NE_) == 8 ? 2 : CI_OUT1)
 // axis-only launch of phase 1 (hot_axis_item): chunks of 4 points are staged, HOT_AXIS_CU = 2 points are advanced
 // together, which keeps it at 3 CTAs/SM without spills
 #ifndef DUGKS_CI_AXIS
@@ -325,7 +328,7 @@ static void launch_hot_outgoing(dugks_handle* h, const StepArgs& a) {
         h->launches++;
         return;
     }
-#define DUGKS_HOT_OUT(NE_, TW_) k_hot_outgoing<PHASE, H, NE_, TW_, (PHASE == 1 ? CI_OUT1 : CI_OUT2), 0><<<grid, HOT_WARPS * 32, sm, h->stream>>>(a)
+#define DUGKS_HOT_OUT(NE_, TW_) k_hot_outgoing<PHASE, H, NE_, TW_, (PHASE == 1 ? CI_OUT1_NE(NE_) : CI_OUT2), 0><<<grid, HOT_WARPS * 32, sm, h->stream>>>(a)
 #ifdef DUGKS_DEV_BUILD
     DUGKS_HOT_OUT(6, 32);
 #else
@@ -379,7 +382,7 @@ static cudaError_t hot_cfg_rlx(dugks_handle* h, int* occ) {
 }
 template <int PHASE, bool H, int NE, int TW>
 static cudaError_t hot_attr_out(size_t bytes) {
-    return cudaFuncSetAttribute(k_hot_outgoing<PHASE, H, NE, TW, (PHASE == 1 ? CI_OUT1 : CI_OUT2), 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    return cudaFuncSetAttribute(k_hot_outgoing<PHASE, H, NE, TW, (PHASE == 1 ? CI_OUT1_NE(NE) : CI_OUT2), 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 template <bool H>
 static int hot_configure(dugks_handle* h) {
@@ -388,7 +391,7 @@ static int hot_configure(dugks_handle* h) {
     int occ[6] = {1, 1, 1, 1, 1, 1};
 #define DUGKS_HOT_CFG(NE_)                                                                                   \
     do {                                                                                                     \
-        h->hsmem_out1 = HotPlan<1, H, NE_, 32, CI_OUT1>::total(ntab);                                                 \
+        h->hsmem_out1 = HotPlan<1, H, NE_, 32, CI_OUT1_NE(NE_)>::total(ntab);                                                 \
         h->hsmem_out2 = tw == 32 ? HotPlan<2, H, NE_, 32, CI_OUT2>::total(ntab) : HotPlan<2, H, NE_, 64, CI_OUT2>::total(ntab); \
         h->hsmem_upd = HotUpdPlan<H, NE_, CI_UPD>::total(ntab);                                                      \
         if (std::max(std::max(h->hsmem_out1, h->hsmem_out2), h->hsmem_upd) > 220 * 1024) { h->use_hot = false; return 0; } \
@@ -396,7 +399,7 @@ static int hot_configure(dugks_handle* h) {
         if (e == cudaSuccess) e = tw == 32 ? hot_attr_out<2, H, NE_, 32>(h->hsmem_out2) : hot_attr_out<2, H, NE_, 64>(h->hsmem_out2); \
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_hot_update<H, NE_, CI_UPD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->hsmem_upd); \
         /* persistent grids: CTAs the SM can hold (registers and shared memory) times the SM count */    \
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], k_hot_outgoing<1, H, NE_, 32, CI_OUT1, 0>, HOT_WARPS * 32, h->hsmem_out1); \
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], k_hot_outgoing<1, H, NE_, 32, CI_OUT1_NE(NE_), 0>, HOT_WARPS * 32, h->hsmem_out1); \
         if (e == cudaSuccess) e = tw == 32 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], k_hot_outgoing<2, H, NE_, 32, CI_OUT2, 0>, HOT_WARPS * 32, h->hsmem_out2) \
                                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], k_hot_outgoing<2, H, NE_, 64, CI_OUT2, 0>, HOT_WARPS * 32, h->hsmem_out2); \
         if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], k_hot_update<H, NE_, CI_UPD>, HOT_WARPS * 32, h->hsmem_upd); \

@@ -608,3 +608,80 @@ def tri_prism_2d(nx: int, ny: int, lengths=(1.0, 1.0, 0.1), *, distort: float = 
     patches.append(Patch("frontAndBack", "empty", 2 * nC, start))
     return PolyMesh(points=points, face_verts=np.array(verts), face_offsets=np.array(offs),
                     owner=np.array(owner), neighbour=np.array(neigh), patches=patches, nCells=nC)
+
+
+def voronoi_prism_2d(nx: int, ny: int, lengths=(1.0, 1.0, 0.1), *, jitter: float = 0.25, seed: int = 20260101,
+                     patch_names: Optional[Dict[str, str]] = None) -> PolyMesh:
+    """2-D unstructured POLYGONAL mesh (the "poly" of BASELINE config 4): the Voronoi diagram of nx*ny jittered seed
+    points in a rectangle, extruded one cell in z with an ``empty`` frontAndBack patch.  The seeds are mirrored in the
+    four walls, so the cells of the original seeds are cut exactly by the rectangle.  Cells are prisms over polygons
+    with 4 to about 8 sides (needs scipy)."""
+    from scipy.spatial import Voronoi
+    Lx, Ly, Lz = lengths
+    rng = np.random.default_rng(seed)
+    hx, hy = Lx / nx, Ly / ny
+    I, J = np.meshgrid(np.arange(nx), np.arange(ny), indexing="xy")
+    pts = np.column_stack([(I.ravel() + 0.5) * hx, (J.ravel() + 0.5) * hy])
+    pts += (rng.random(pts.shape) - 0.5) * 2 * jitter * np.array([hx, hy])
+    n0 = len(pts)
+    mirrored = [pts, pts * [-1, 1], pts * [-1, 1] + [2 * Lx, 0], pts * [1, -1], pts * [1, -1] + [0, 2 * Ly]]
+    vor = Voronoi(np.concatenate(mirrored))
+    # vertices used by the cells of the original seeds, renumbered; coordinates snapped onto the walls
+    used = sorted({v for i in range(n0) for v in vor.regions[vor.point_region[i]]})
+    assert -1 not in used, "open Voronoi region (seeds too close to a wall?)"
+    vid = {v: k for k, v in enumerate(used)}
+    xy = vor.vertices[used].copy()
+    tol = 1e-9 * max(Lx, Ly)
+    for d, L in ((0, Lx), (1, Ly)):
+        xy[np.abs(xy[:, d]) < tol, d] = 0.0
+        xy[np.abs(xy[:, d] - L) < tol, d] = L
+    npl = len(xy)
+    points = np.concatenate([np.column_stack([xy, np.zeros(npl)]), np.column_stack([xy, np.full(npl, Lz)])])
+    # polygons, counter-clockwise about their seed
+    polys = []
+    for i in range(n0):
+        vs = [vid[v] for v in vor.regions[vor.point_region[i]]]
+        ang = np.arctan2(xy[vs, 1] - pts[i, 1], xy[vs, 0] - pts[i, 0])
+        polys.append([vs[k] for k in np.argsort(ang)])
+    if patch_names is None:
+        patch_names = {"ymax": "movingWall", "xmin": "fixedWalls", "xmax": "fixedWalls", "ymin": "fixedWalls"}
+    internal, boundary = [], {}
+    for (p, q), rv in zip(vor.ridge_points, vor.ridge_vertices):
+        if -1 in rv or (p >= n0 and q >= n0) or rv[0] not in vid or rv[1] not in vid:
+            continue
+        a, b = vid[rv[0]], vid[rv[1]]
+        if np.hypot(*(xy[a] - xy[b])) < tol:
+            continue                                            # degenerate ridge (four seeds on a circle)
+        c0 = int(min(p, q)) if max(p, q) < n0 else int(p if p < n0 else q)
+        # orient the edge counter-clockwise as seen from c0: its outward normal then points away from c0
+        e, m = xy[b] - xy[a], 0.5 * (xy[a] + xy[b]) - pts[c0]
+        if e[0] * m[1] - e[1] * m[0] > 0:                       # seed on the left of a->b means clockwise about the seed: flip
+            a, b = b, a
+        if max(p, q) < n0:
+            internal.append((c0, int(max(p, q)), a, b))
+        else:
+            mx, my = 0.5 * (xy[a] + xy[b])
+            side = "ymax" if abs(my - Ly) < tol else ("ymin" if abs(my) < tol else ("xmin" if abs(mx) < tol else "xmax"))
+            boundary.setdefault(patch_names[side], []).append((c0, a, b))
+    internal.sort(key=lambda t: (t[0], t[1]))
+
+    def side_face(u, v):                                        # outward for the counter-clockwise edge u -> v
+        return [u, v, v + npl, u + npl]
+
+    verts, offs, owner, neigh = [], [0], [], []
+    for c0, c1, u, v in internal:
+        verts += side_face(u, v); offs.append(len(verts)); owner.append(c0); neigh.append(c1)
+    patches = []
+    for name in dict.fromkeys(patch_names.values()):
+        lst = sorted(boundary.get(name, []))
+        patches.append(Patch(name, "wall", len(lst), len(owner)))
+        for c0, u, v in lst:
+            verts += side_face(u, v); offs.append(len(verts)); owner.append(c0)
+    start = len(owner)
+    for c, poly in enumerate(polys):                            # back (z = 0): outward -z -> clockwise
+        verts += poly[::-1]; offs.append(len(verts)); owner.append(c)
+    for c, poly in enumerate(polys):                            # front (z = Lz)
+        verts += [v + npl for v in poly]; offs.append(len(verts)); owner.append(c)
+    patches.append(Patch("frontAndBack", "empty", 2 * n0, start))
+    return PolyMesh(points=points, face_verts=np.array(verts), face_offsets=np.array(offs),
+                    owner=np.array(owner), neighbour=np.array(neigh), patches=patches, nCells=n0)

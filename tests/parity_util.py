@@ -52,6 +52,7 @@ def cases_small():
     out.append(("cavity3d_5_gh8_storeh", cs.cavity3d_case(5, 8, perturb=0.01), True))
     out.append(("cavity3d_5_gh8_distort", cs.cavity3d_case(5, 8, distort=0.15, perturb=0.01), False))
     out.append(("tri_8_gh8", cs.tri_cavity_case(8, 8, perturb=0.01), False))
+    out.append(("poly_7_gh8", cs.poly_cavity_case(7, 8, perturb=0.01), False))            # config 4: polygonal (Voronoi) cells, 4 to 8 sides
     out.append(("ratchet_20x8_gh8", cs.ratchet_channel_case(20, 8, 8, teeth=2, perturb=0.01), False))   # config 4: saw-tooth wall, three wall temperatures
     return out
 

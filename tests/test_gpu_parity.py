@@ -142,6 +142,7 @@ def test_every_kernel_path(oracle_lib, monkeypatch, path, env):
            ("cavity2d_9_nc9_ties", cs.cavity2d_case(9, 9, quad="NC", perturb=0.01), False),
            ("tri_8_gh8", cs.tri_cavity_case(8, 8, perturb=0.01), False),
            ("ratchet_20x8_gh8", cs.ratchet_channel_case(20, 8, 8, teeth=2, perturb=0.01), False),   # config 4 as named
+           ("poly_7_gh8", cs.poly_cavity_case(7, 8, perturb=0.01), False),         # polygonal cells with up to 8 sides
            ("cavity3d_4_gh8_storeh", cs.cavity3d_case(4, 8, perturb=0.01), True)]
     for name, case, store_h in zoo:
         dv = capi.fvDVM(case, store_h=store_h)

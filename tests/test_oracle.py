@@ -10,7 +10,7 @@ import pytest
 import parity_util as util
 from dugksfoam_b200 import case as cs
 from dugksfoam_b200 import dvset
-from dugksfoam_b200.polymesh import compute_geometry, hex_block, tri_prism_2d
+from dugksfoam_b200.polymesh import compute_geometry, hex_block, tri_prism_2d, voronoi_prism_2d
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = json.load(open(os.path.join(HERE, "golden", "demo_cavity.json")))
@@ -91,7 +91,8 @@ def test_ratchet_channel_mesh():
 # ---- geometry identities ---------------------------------------------------------------
 @pytest.mark.parametrize("mesh", [hex_block(5, 4, 3, (1.0, 0.8, 0.6), distort=0.2),
                                   hex_block(6, 5, 1, (1.0, 1.0, 0.1), two_d=True, distort=0.2),
-                                  tri_prism_2d(5, 4, distort=0.15)], ids=["hex3d", "hex2d", "tri2d"])
+                                  tri_prism_2d(5, 4, distort=0.15), voronoi_prism_2d(6, 5, (1.0, 0.8, 0.1))],
+                         ids=["hex3d", "hex2d", "tri2d", "poly2d"])
 def test_geometry_identities(mesh):
     from dugksfoam_b200.polymesh import cell_centres_and_volumes, face_centres_and_areas
     Cf, Sf = face_centres_and_areas(mesh)
@@ -312,6 +313,7 @@ def _xcheck_zoo():
         ("cavity2d_6_gh8_distort", cs.cavity2d_case(6, 8, distort=0.2, perturb=0.02)),
         ("cavity3d_4_gh8_distort", cs.cavity3d_case(4, 8, distort=0.1, perturb=0.02)),
         ("tri_5_gh8", cs.tri_cavity_case(5, 8, perturb=0.02)),
+        ("poly_5_gh8", cs.poly_cavity_case(5, 8, perturb=0.02)),
         ("cavity2d_5_nc9_ties", cs.cavity2d_case(5, 9, quad="NC", perturb=0.02)),
         ("farfield_zg_mixed", util.channel_case(
             6, 4, 8, kinds={"inlet": K.PATCH_FAR_FIELD, "outlet": K.PATCH_ZERO_GRADIENT, "top": K.PATCH_MIXED},
