@@ -53,7 +53,11 @@ class fvDVM {
     }
     fvDVM(const fvDVM&) = delete;              // fvDVM.H:254-258
     fvDVM& operator=(const fvDVM&) = delete;
-    ~fvDVM() { dugks_destroy(h_); }
+    ~fvDVM() {
+        for (std::vector<double>* v : {&rho_, &U_, &T_, &q_, &tau_})
+            if (pinned_ && !v->empty()) dugks_host_unregister(v->data());
+        dugks_destroy(h_);
+    }
 
     // fvDVM.H:288 — one time step; dt = runTime.deltaTValue()
     void evolution(double dt) { check(dugks_step(h_, dt), "fvDVM::evolution"); dirty_ = true; }
@@ -120,8 +124,14 @@ class fvDVM {
     }
     void sync() {
         if (!dirty_ && !rho_.empty()) return;
-        rho_.resize(nCells_); T_.resize(nCells_); tau_.resize(nCells_);
-        U_.resize((size_t)nCells_ * 3); q_.resize((size_t)nCells_ * 3);
+        if (rho_.empty()) {
+            rho_.resize(nCells_); T_.resize(nCells_); tau_.resize(nCells_);
+            U_.resize((size_t)nCells_ * 3); q_.resize((size_t)nCells_ * 3);
+            // page-lock the field storage once (best effort): the accessor then copies straight into it
+            pinned_ = true;
+            for (std::vector<double>* v : {&rho_, &U_, &T_, &q_, &tau_})
+                if (dugks_host_register(v->data(), v->size() * sizeof(double)) != DUGKS_OK) pinned_ = false;
+        }
         check(dugks_get_cell_macros(h_, rho_.data(), U_.data(), T_.data(), q_.data(), tau_.data()), "fvDVM::sync");
         surfDirty_ = true; dirty_ = false;
     }
@@ -137,7 +147,7 @@ class fvDVM {
     int nCells_, nFaces_, nBnd_, nXiPerDim_, nXi_ = 0, nXiLocal_ = 0;
     double xiMax_, xiMin_;
     dugks_gas_t gas_;
-    bool dirty_ = true, surfDirty_ = true;
+    bool dirty_ = true, surfDirty_ = true, pinned_ = false;
     std::vector<double> rho_, U_, T_, q_, tau_, rhoS_, US_, TS_, qS_, tauS_;
 };
 
